@@ -1,0 +1,189 @@
+/*
+ * lidiff_b200 — C ABI of the B200-native (sm_100a) implementation of the LiDiff denoising hot path.
+ *
+ * The reference (PRBonn/LiDiff) reaches this path through three un-vendored Python packages, not
+ * through a C interface:
+ *     import MinkowskiEngine as ME      lidiff/models/minkunet.py:6, tools/diff_completion_pipeline.py:2
+ *     pykeops.torch.LazyTensor.argKmin  lidiff/models/minkunet.py:8,412-416
+ *     diffusers.DPMSolverMultistepScheduler.step   tools/diff_completion_pipeline.py:6,163
+ * Each entry point below names the reference call site(s) it stands behind.  The Python operator
+ * surface that mirrors those packages lives in lidiff_b200/ and binds this library with ctypes
+ * (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - every buffer is CALLER-OWNED device memory (a torch CUDA tensor); the library allocates nothing
+ *     the caller can see and keeps no state besides the handle's error string;
+ *   - all calls are asynchronous on the given `stream` (a cudaStream_t passed as void*), never
+ *     synchronise, never allocate => capturable in a CUDA graph;
+ *   - data-dependent row counts live in DEVICE int32 scalars (`d_n*`); buffers are sized by a host
+ *     capacity (`*_cap`) and kernels read the count on the device;
+ *   - return value: 0 = OK, negative = error; `lb2_last_error(h)` gives the message;
+ *   - coordinates are int32 rows [b, x, y, z]; features are fp32 row-major (rows, channels);
+ *   - no CPU fallback exists: without a CUDA device the calls fail with LB2_ERR_CUDA.
+ */
+#ifndef LIDIFF_B200_H_
+#define LIDIFF_B200_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LB2_OK            0
+#define LB2_ERR_ARG      -1
+#define LB2_ERR_CUDA     -2
+#define LB2_ERR_UNSUP    -3
+
+#define LB2_KEY_EMPTY 0xFFFFFFFFFFFFFFFFull
+
+/* ---- handle ----------------------------------------------------------------------------------- */
+int         lb2_create(int device, void** handle);
+void        lb2_destroy(void* handle);
+const char* lb2_last_error(void* handle);
+int         lb2_version(void);
+/* number of kernels this library has launched through `handle` since creation (bench gpu_launches) */
+int64_t     lb2_launch_count(void* handle);
+/* synchronising read-and-clear of the device status word; bit0 = a coordinate fell outside the key
+ * range (10 bit batch, 18 bit signed axes) and was clamped.  Returns the word (>= 0) or an error. */
+int         lb2_read_status(void* handle, void* stream);
+
+/* ---- hash grid (coordinate manager)  — replaces ME's CoordinateManager -------------------------
+ * One hash grid per coordinate level.  `keys` (uint64[cap_table]) and `vals` (int32[2*cap_table]:
+ * [0,cap) scratch "first point index", [cap,2cap) row id) are caller-owned; cap_table is a power
+ * of two >= 2 * max rows.  Key packing: 10 bit batch | 3 x 18 bit signed coordinate.
+ */
+typedef struct {
+    uint64_t* keys;
+    int32_t*  vals;
+    int32_t   cap_table;
+} lb2_grid;
+
+/* coord = round_half_even(x / resolution) on every column of an (n,ncol) fp32 array.
+ * Reference: tools/diff_completion_pipeline.py:71-72, utils/collations.py:8-12 (torch.round(x/res)).
+ * div_mode 0: true fp32 division; 1: multiply by fp32(1/resolution) (PyTorch CUDA scalar division). */
+int lb2_quantize(void* h, void* stream, const float* x, int64_t n_elem, float resolution, int div_mode,
+                 float* out_coord);
+
+/* ME.TensorField.sparse() coordinate part (pipeline:149, minkunet.py:135,597) and ME strided
+ * coordinate maps (conv stride 2, minkunet.py:103,184...).
+ * Input rows: either fp32 integer-valued coords (`in_f`, floor() is applied; TensorField) or int32
+ * coords (`in_i`; a parent level).  If ts_floor > 0 the xyz columns are floored to multiples of
+ * ts_floor (stride map).  Output: unique rows in FIRST-OCCURRENCE order, `inverse[i]` = output row of
+ * input row i, `*d_nout` = number of unique rows.  `scratch` >= lb2_unique_scratch_bytes(n_cap). */
+size_t lb2_unique_scratch_bytes(int64_t n_cap);
+int lb2_unique_build(void* h, void* stream,
+                     const float* in_f, const int32_t* in_i, const int32_t* d_nin, int32_t n_cap,
+                     int32_t ts_floor, lb2_grid grid,
+                     int32_t* out_coords, int32_t* inverse, int32_t* d_nout, void* scratch);
+
+/* UNWEIGHTED_AVERAGE voxel features (ME.SparseTensorQuantizationMode, pipeline:77): mean of member
+ * point features.  `counts` int32[m_cap] scratch. out (m_cap, c). */
+int lb2_voxel_mean(void* h, void* stream, const float* feats, const int32_t* inverse, int32_t n,
+                   int32_t c, const int32_t* d_m, int32_t m_cap, float* out, int32_t* counts);
+
+/* Kernel map (ME kernel maps for MinkowskiConvolution / ConvolutionTranspose; minkunet.py:17-24,36-42).
+ * Output-stationary neighbour table: nbr[k * nbr_stride + o] = input row at coords(o) + offset_k, or -1.
+ *   ks=3: offset_d = (k_d - 1) * step      ks=2: offset_d = k_d * step   (step < 0: transposed map)
+ *   k = kx + ks*ky + ks*ks*kz. */
+int lb2_kernel_map(void* h, void* stream, lb2_grid grid_in, const int32_t* out_coords,
+                   const int32_t* d_nout, int32_t nout_cap, int32_t ks, int32_t step,
+                   int32_t* nbr, int64_t nbr_stride);
+
+/* ---- sparse convolution  — replaces ME.MinkowskiConvolution(+Transpose) forward, with the
+ * MinkowskiBatchNorm(eval)/MinkowskiReLU/residual-add/ME.cat/gate-multiply that follow it in
+ * minkunet.py:13-80,431,464 fused as prologue/epilogue.
+ *   out[o] = epi( sum_k [in1|in2][nbr[k][o]] @ W[k] )
+ *   epi(y) = relu?( y*scale + shift + residual[o] );  optional second output out_gated = epi(y) *
+ *   gate_table[gate_idx[o]].
+ * Up to two guidance passes (conditional/unconditional) share W and the map. */
+typedef struct {
+    const float*   in1;         /* (rows_in, c1) */
+    const float*   in2;         /* (rows_in, c2) or NULL  (ME.cat as a second K segment) */
+    const float*   residual;    /* (m, cout) or NULL */
+    float*         out;         /* (m, cout) or NULL */
+    const float*   gate_table;  /* (rows_g, cout) or NULL */
+    const int32_t* gate_idx;    /* (m) or NULL (=> row 0 broadcast) */
+    float*         out_gated;   /* (m, cout) or NULL */
+} lb2_conv_io;
+
+typedef struct {
+    int32_t        c1, c2, cout, kvol;
+    const float*   weight;      /* (kvol, c1+c2, cout) fp32 */
+    const void*    weight_packed; /* tensor-core layout from lb2_pack_weights or NULL */
+    const float*   scale;       /* (cout) or NULL */
+    const float*   shift;       /* (cout) or NULL */
+    int32_t        relu;
+    const int32_t* nbr;         /* [kvol][nbr_stride] or NULL => identity map (1x1 conv) */
+    int64_t        nbr_stride;
+    const int32_t* d_mout;      /* device row count or NULL => mout_cap */
+    int32_t        mout_cap;
+    int32_t        npass;       /* 1 or 2 */
+    lb2_conv_io    io[2];
+} lb2_conv_desc;
+
+#define LB2_ALGO_AUTO  0
+#define LB2_ALGO_FFMA  1    /* fp32 CUDA-core implicit GEMM */
+#define LB2_ALGO_TC    2    /* tcgen05 BF16x3 implicit GEMM (needs weight_packed) */
+int lb2_spconv_forward(void* h, void* stream, const lb2_conv_desc* d, int algo);
+
+/* BF16 hi/lo split + UMMA shared-memory image of a (kvol, cin, cout) fp32 weight for LB2_ALGO_TC. */
+size_t lb2_packed_weight_bytes(int32_t kvol, int32_t cin, int32_t cout);
+int lb2_pack_weights(void* h, void* stream, const float* weight, int32_t kvol, int32_t cin, int32_t cout,
+                     void* packed);
+
+/* ---- nearest partial-scan voxel — replaces pykeops argKmin(1) in MinkUNetDiff.match_part_to_full
+ * (minkunet.py:403-418): idx[q] = argmin_j |cq - ck_j|^2 over [b*2*max, x, y, z], ties -> lowest j. */
+int lb2_nn_match(void* h, void* stream, const int32_t* q_coords, const int32_t* d_nq, int32_t nq_cap,
+                 const int32_t* k_coords, const int32_t* d_nk, int32_t nk_cap, int32_t batch_scale,
+                 int32_t* idx);
+
+/* ---- small dense layers — torch.nn.Linear (+LeakyReLU) of the gate / head MLPs
+ * (minkunet.py:165-181,376-380): y = act(x @ W^T + b [+ addend]); W is (n_out, n_in) torch layout.
+ * act: 0 none, 1 LeakyReLU(0.1), 2 tanh.  rows read from d_m if non-NULL.
+ * Optional input transform x' = pre_act(x + prebias[k]) (prebias (n_in) or NULL): evaluates the
+ * hoisted gate MLP  latemp(cat(p,t)) = W2 . leaky(Wp.p + (Wt.t + b1)) + b2  (SURVEY.md App. D.1). */
+int lb2_linear(void* h, void* stream, const float* x, int64_t ldx, const float* w, const float* b,
+               const float* addend, int64_t ld_addend, int32_t m_cap, const int32_t* d_m,
+               int32_t n_in, int32_t n_out, int32_t act, float* y, int64_t ldy,
+               const float* prebias, int32_t pre_act);
+
+/* x * w row-gather multiply (`x0*w0`, minkunet.py:431...): out[r] = x[r] * table[idx ? idx[r] : 0] */
+int lb2_gate_mul(void* h, void* stream, const float* x, const float* table, const int32_t* idx,
+                 const int32_t* d_m, int32_t m_cap, int32_t c, float* out);
+
+/* out[i] = src[idx[i]]  (SparseTensor.slice / x_part.F[match], minkunet.py:418,497) */
+int lb2_gather_rows(void* h, void* stream, const float* src, const int32_t* idx, int32_t n, int32_t c,
+                    float* out);
+
+/* ---- fused tail — classifier-free guidance (pipeline:153) + DPM-Solver++(2M) SDE update
+ * (pipeline:162-163; diffusers DPMSolverMultistepScheduler.step) + next TensorField features and
+ * coordinates (pipeline:164 -> :68-84), one thread per point coordinate.
+ *   eps      = eps_u[v] + w * (eps_c[v] - eps_u[v]),  v = inverse[point]   (voxel eps, (m,3) fp32)
+ *   sample   = x_t - x_init;  x0 = (sample - sigma_s*eps)/alpha_s           (fp64 like the pipeline)
+ *   prev     = c_sample*sample + c_x0*x0 [+ 0.5*c_x0*(x0 - x0_prev)/r0] + c_noise*noise
+ *   x_next   = fp32(x_init + prev);  coord = round_half_even(x_next / resolution)
+ * coord_next is (n,4) fp32 [b, x, y, z] ready for lb2_unique_build (b from batch_col or 0).
+ * x0_state (n*3 fp64) is read when second_order != 0 and always overwritten with the new x0. */
+typedef struct {
+    double c_sample, c_x0, c_noise, sigma_s, alpha_s, inv_r0;
+    float  guidance_w, resolution;
+    int32_t second_order, div_mode, f64_state;
+} lb2_dpm_coef;
+int lb2_guidance_dpm_step(void* h, void* stream, const float* eps_c, const float* eps_u,
+                          const int32_t* inverse, const float* x_t, const double* x_init,
+                          const float* noise, double* x0_state, int64_t n_points, lb2_dpm_coef coef,
+                          float* eps_out, float* x_next, float* coord_next /* (n,4) */,
+                          const float* batch_col /* (n) or NULL */);
+
+/* ---- farthest point sampling — open3d farthest_point_down_sample used by preprocess_scan
+ * (pipeline:97-99): start at point 0, repeatedly take the first argmax of the running min squared
+ * distance (fp64).  out_idx[n_samples] selection order; dist_scratch fp64[n]. */
+int lb2_farthest_point_sample(void* h, void* stream, const double* pts, int32_t n, int32_t n_samples,
+                              int32_t* out_idx, double* dist_scratch);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* LIDIFF_B200_H_ */

@@ -1,0 +1,336 @@
+// K1/K2/K3 — GPU hash-grid coordinate manager: quantise, voxelise (unique rows in first-occurrence
+// order), strided coordinate maps, kernel maps (neighbour tables).  Integer work, HBM/L2 bound:
+// int4 coalesced coordinate loads, one 8-byte CAS per insert, open addressing in an L2-resident table.
+//
+// Stands behind ME.TensorField.sparse() / ME coordinate manager as used at
+// /root/reference/lidiff/tools/diff_completion_pipeline.py:68-84,149 and lidiff/models/minkunet.py:17-24,36-42,135.
+#include "common.cuh"
+#include <limits.h>
+
+// ---------------------------------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------------------------------
+extern "C" int lb2_version(void) { return 100; }
+
+extern "C" int lb2_create(int device, void** handle) {
+    if (!handle) return LB2_ERR_ARG;
+    *handle = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return LB2_ERR_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return LB2_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return LB2_ERR_CUDA;
+    if (prop.major != 10) return LB2_ERR_UNSUP;          // sm_100a binary only
+    Lb2Handle* h = new Lb2Handle();
+    h->device = device; h->num_sms = prop.multiProcessorCount; h->launches = 0; h->err[0] = 0;
+    if (cudaMalloc(&h->d_status, sizeof(int32_t)) != cudaSuccess) { delete h; return LB2_ERR_CUDA; }
+    cudaMemset(h->d_status, 0, sizeof(int32_t));
+    *handle = h;
+    return LB2_OK;
+}
+
+extern "C" void lb2_destroy(void* handle) {
+    Lb2Handle* h = (Lb2Handle*)handle;
+    if (!h) return;
+    cudaFree(h->d_status);
+    delete h;
+}
+
+extern "C" const char* lb2_last_error(void* handle) {
+    return handle ? ((Lb2Handle*)handle)->err : "null handle";
+}
+
+extern "C" int64_t lb2_launch_count(void* handle) { return handle ? ((Lb2Handle*)handle)->launches : -1; }
+
+// synchronising read-and-clear of the device status word (bit0: coordinate outside the key range)
+extern "C" int lb2_read_status(void* handle, void* stream) {
+    Lb2Handle* h = (Lb2Handle*)handle;
+    if (!h) return LB2_ERR_ARG;
+    int32_t v = 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (cudaMemcpyAsync(&v, h->d_status, sizeof(v), cudaMemcpyDeviceToHost, s) != cudaSuccess) return LB2_ERR_CUDA;
+    if (cudaMemsetAsync(h->d_status, 0, sizeof(v), s) != cudaSuccess) return LB2_ERR_CUDA;
+    if (cudaStreamSynchronize(s) != cudaSuccess) return LB2_ERR_CUDA;
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// quantise: coord = rint(x / res)   (round-half-even == torch.round)
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_quantize(const float* __restrict__ x, long long n, float res, float inv_res, int div_mode,
+                           float* __restrict__ out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float v = x[i];
+    float q = div_mode == 0 ? __fdiv_rn(v, res) : __fmul_rn(v, inv_res);
+    out[i] = rintf(q);
+}
+
+extern "C" int lb2_quantize(void* handle, void* stream, const float* x, int64_t n_elem, float resolution,
+                            int div_mode, float* out_coord) {
+    Lb2Handle* h = (Lb2Handle*)handle;
+    LB2_REQUIRE(h, h && x && out_coord && resolution > 0.f, "quantize");
+    if (n_elem == 0) return LB2_OK;
+    float inv = 1.0f / resolution;       // fp32 reciprocal, as PyTorch's CUDA scalar-divide does
+    k_quantize<<<cdiv(n_elem, 256), 256, 0, (cudaStream_t)stream>>>(x, n_elem, resolution, inv, div_mode, out_coord);
+    LB2_POST_LAUNCH(h, "k_quantize");
+    return LB2_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// unique rows in first-occurrence order
+// ---------------------------------------------------------------------------------------------------
+#define SCAN_THREADS 512
+#define SCAN_ITEMS   4
+#define SCAN_TILE    (SCAN_THREADS * SCAN_ITEMS)
+
+struct UniqueScratch {     // carved out of the caller's scratch buffer
+    int* slot_of;          // [n_cap]
+    int* rank;             // [n_cap]
+    int* bsum;             // [SCAN_TILE]
+};
+
+extern "C" size_t lb2_unique_scratch_bytes(int64_t n_cap) {
+    size_t a = ((size_t)n_cap * sizeof(int) + 255) / 256 * 256;
+    return 2 * a + SCAN_TILE * sizeof(int) + 256;
+}
+
+static UniqueScratch carve(void* scratch, int64_t n_cap) {
+    size_t a = ((size_t)n_cap * sizeof(int) + 255) / 256 * 256;
+    char* p = (char*)scratch;
+    UniqueScratch s;
+    s.slot_of = (int*)p; s.rank = (int*)(p + a); s.bsum = (int*)(p + 2 * a);
+    return s;
+}
+
+__global__ void k_grid_clear(unsigned long long* keys, int* vals, int cap) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cap) { keys[i] = LB2_KEY_EMPTY; vals[i] = INT_MAX; vals[cap + i] = -1; }
+}
+
+__device__ __forceinline__ int4 load_row(const float* __restrict__ in_f, const int* __restrict__ in_i, int i, int ts) {
+    int4 c;
+    if (in_f) {
+        float4 f = __ldg(reinterpret_cast<const float4*>(in_f) + i);
+        c = make_int4((int)floorf(f.x), (int)floorf(f.y), (int)floorf(f.z), (int)floorf(f.w));
+    } else {
+        c = __ldg(reinterpret_cast<const int4*>(in_i) + i);
+    }
+    if (ts > 0) { c.y = floor_to_multiple(c.y, ts); c.z = floor_to_multiple(c.z, ts); c.w = floor_to_multiple(c.w, ts); }
+    return c;
+}
+
+__global__ void k_grid_insert(const float* __restrict__ in_f, const int* __restrict__ in_i,
+                              const int* __restrict__ d_n, int n_cap, int ts,
+                              unsigned long long* keys, int* vals, unsigned mask,
+                              int* __restrict__ slot_of, int* status) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int n = d_n ? min(*d_n, n_cap) : n_cap;
+    if (i >= n) return;
+    int4 c = load_row(in_f, in_i, i, ts);
+    unsigned long long key;
+    if (!lb2_pack_key(c.x, c.y, c.z, c.w, key)) atomicOr(status, 1);
+    unsigned slot = lb2_hash(key) & mask;
+    while (true) {
+        unsigned long long prev = atomicCAS(keys + slot, (unsigned long long)LB2_KEY_EMPTY, key);
+        if (prev == LB2_KEY_EMPTY || prev == key) break;
+        slot = (slot + 1) & mask;
+    }
+    atomicMin(vals + slot, i);          // first occurrence wins
+    slot_of[i] = (int)slot;
+}
+
+// block-level exclusive scan of the "is first occurrence" flags
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_local(const int* __restrict__ slot_of, const int* __restrict__ vals,
+                                                             const int* __restrict__ d_n, int n_cap,
+                                                             int* __restrict__ rank, int* __restrict__ bsum) {
+    __shared__ int warp_tot[SCAN_THREADS / 32];
+    int n = d_n ? min(*d_n, n_cap) : n_cap;
+    int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    int f[SCAN_ITEMS], tsum = 0;
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; ++j) {
+        int i = base + j;
+        f[j] = (i < n) ? (vals[slot_of[i]] == i) : 0;
+        tsum += f[j];
+    }
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int incl = tsum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+    if (lane == 31) warp_tot[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        int v = (lane < SCAN_THREADS / 32) ? warp_tot[lane] : 0, inc2 = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xffffffffu, inc2, d); if (lane >= d) inc2 += u; }
+        if (lane < SCAN_THREADS / 32) warp_tot[lane] = inc2 - v;      // exclusive warp offsets
+        if (lane == SCAN_THREADS / 32 - 1) bsum[blockIdx.x] = inc2;   // block total
+    }
+    __syncthreads();
+    int excl = warp_tot[w] + incl - tsum;
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; ++j) {
+        int i = base + j;
+        if (i < n) rank[i] = f[j] ? excl : -1;     // -1: not a first occurrence
+        excl += f[j];
+    }
+}
+
+// single block: exclusive scan of up to SCAN_TILE block totals; writes the grand total
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_bsum(int* __restrict__ bsum, int nblocks, int* __restrict__ d_total) {
+    __shared__ int warp_tot[SCAN_THREADS / 32];
+    int base = threadIdx.x * SCAN_ITEMS;
+    int v[SCAN_ITEMS], tsum = 0;
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; ++j) { v[j] = (base + j < nblocks) ? bsum[base + j] : 0; tsum += v[j]; }
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int incl = tsum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += u; }
+    if (lane == 31) warp_tot[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        int x = (lane < SCAN_THREADS / 32) ? warp_tot[lane] : 0, inc2 = x;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xffffffffu, inc2, d); if (lane >= d) inc2 += u; }
+        if (lane < SCAN_THREADS / 32) warp_tot[lane] = inc2 - x;
+        if (lane == SCAN_THREADS / 32 - 1) *d_total = inc2;
+    }
+    __syncthreads();
+    int excl = warp_tot[w] + incl - tsum;
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; ++j) { if (base + j < nblocks) bsum[base + j] = excl; excl += v[j]; }
+}
+
+// winners publish their row id and coordinates
+__global__ void k_unique_emit(const float* __restrict__ in_f, const int* __restrict__ in_i,
+                              const int* __restrict__ d_n, int n_cap, int ts,
+                              const int* __restrict__ slot_of, const int* __restrict__ rank,
+                              const int* __restrict__ bsum, int* __restrict__ vals, int cap,
+                              int4* __restrict__ out_coords) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int n = d_n ? min(*d_n, n_cap) : n_cap;
+    if (i >= n) return;
+    int r = rank[i];
+    if (r < 0) return;
+    r += bsum[i / SCAN_TILE];
+    vals[cap + slot_of[i]] = r;
+    out_coords[r] = load_row(in_f, in_i, i, ts);
+}
+
+__global__ void k_unique_inverse(const int* __restrict__ d_n, int n_cap, const int* __restrict__ slot_of,
+                                 const int* __restrict__ vals, int cap, int* __restrict__ inverse) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int n = d_n ? min(*d_n, n_cap) : n_cap;
+    if (i < n) inverse[i] = vals[cap + slot_of[i]];
+}
+
+extern "C" int lb2_unique_build(void* handle, void* stream, const float* in_f, const int32_t* in_i,
+                                const int32_t* d_nin, int32_t n_cap, int32_t ts_floor, lb2_grid grid,
+                                int32_t* out_coords, int32_t* inverse, int32_t* d_nout, void* scratch) {
+    Lb2Handle* h = (Lb2Handle*)handle;
+    LB2_REQUIRE(h, h != nullptr, "handle");
+    LB2_REQUIRE(h, (in_f != nullptr) != (in_i != nullptr), "exactly one of in_f / in_i");
+    LB2_REQUIRE(h, grid.keys && grid.vals && out_coords && d_nout && scratch, "null buffer");
+    LB2_REQUIRE(h, n_cap > 0 && n_cap <= SCAN_TILE * SCAN_TILE, "n_cap out of range (max 4M rows)");
+    LB2_REQUIRE(h, grid.cap_table >= 2 && (grid.cap_table & (grid.cap_table - 1)) == 0, "cap_table must be a power of two");
+    LB2_REQUIRE(h, (long long)grid.cap_table >= 2LL * n_cap, "cap_table must be >= 2 * n_cap");
+    LB2_REQUIRE(h, ts_floor >= 0, "ts_floor");
+    cudaStream_t s = (cudaStream_t)stream;
+    UniqueScratch sc = carve(scratch, n_cap);
+    unsigned long long* keys = (unsigned long long*)grid.keys;
+    int cap = grid.cap_table;
+    unsigned mask = (unsigned)cap - 1u;
+    int nblk = (int)cdiv(n_cap, SCAN_TILE);
+
+    k_grid_clear<<<cdiv(cap, 256), 256, 0, s>>>(keys, grid.vals, cap);
+    LB2_POST_LAUNCH(h, "k_grid_clear");
+    k_grid_insert<<<cdiv(n_cap, 256), 256, 0, s>>>(in_f, in_i, d_nin, n_cap, ts_floor, keys, grid.vals, mask, sc.slot_of, h->d_status);
+    LB2_POST_LAUNCH(h, "k_grid_insert");
+    k_scan_local<<<nblk, SCAN_THREADS, 0, s>>>(sc.slot_of, grid.vals, d_nin, n_cap, sc.rank, sc.bsum);
+    LB2_POST_LAUNCH(h, "k_scan_local");
+    k_scan_bsum<<<1, SCAN_THREADS, 0, s>>>(sc.bsum, nblk, d_nout);
+    LB2_POST_LAUNCH(h, "k_scan_bsum");
+    k_unique_emit<<<cdiv(n_cap, 256), 256, 0, s>>>(in_f, in_i, d_nin, n_cap, ts_floor, sc.slot_of, sc.rank, sc.bsum,
+                                                  grid.vals, cap, (int4*)out_coords);
+    LB2_POST_LAUNCH(h, "k_unique_emit");
+    if (inverse) {
+        k_unique_inverse<<<cdiv(n_cap, 256), 256, 0, s>>>(d_nin, n_cap, sc.slot_of, grid.vals, cap, inverse);
+        LB2_POST_LAUNCH(h, "k_unique_inverse");
+    }
+    return LB2_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// voxel mean features
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_voxel_accum(const float* __restrict__ feats, const int* __restrict__ inverse, int n, int c,
+                              float* __restrict__ out, int* __restrict__ counts) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)n * c) return;
+    int i = (int)(t / c), j = (int)(t % c);
+    int r = inverse[i];
+    atomicAdd(out + (long long)r * c + j, feats[t]);
+    if (j == 0) atomicAdd(counts + r, 1);
+}
+
+__global__ void k_voxel_div(float* __restrict__ out, const int* __restrict__ counts, const int* __restrict__ d_m,
+                            int m_cap, int c) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int m = d_m ? min(*d_m, m_cap) : m_cap;
+    if (t >= (long long)m * c) return;
+    out[t] = __fdiv_rn(out[t], (float)counts[t / c]);
+}
+
+extern "C" int lb2_voxel_mean(void* handle, void* stream, const float* feats, const int32_t* inverse, int32_t n,
+                              int32_t c, const int32_t* d_m, int32_t m_cap, float* out, int32_t* counts) {
+    Lb2Handle* h = (Lb2Handle*)handle;
+    LB2_REQUIRE(h, h && feats && inverse && out && counts && n > 0 && c > 0 && m_cap > 0, "voxel_mean");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (cudaMemsetAsync(out, 0, (size_t)m_cap * c * sizeof(float), s) != cudaSuccess ||
+        cudaMemsetAsync(counts, 0, (size_t)m_cap * sizeof(int), s) != cudaSuccess)
+        return lb2_fail(h, LB2_ERR_CUDA, "voxel_mean memset%s", "");
+    k_voxel_accum<<<cdiv((long long)n * c, 256), 256, 0, s>>>(feats, inverse, n, c, out, counts);
+    LB2_POST_LAUNCH(h, "k_voxel_accum");
+    k_voxel_div<<<cdiv((long long)m_cap * c, 256), 256, 0, s>>>(out, counts, d_m, m_cap, c);
+    LB2_POST_LAUNCH(h, "k_voxel_div");
+    return LB2_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// kernel map: neighbour table nbr[k][o]
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_kernel_map(const unsigned long long* __restrict__ keys, const int* __restrict__ rows, unsigned mask,
+                             const int4* __restrict__ out_coords, const int* __restrict__ d_n, int n_cap,
+                             int ks, int step, int* __restrict__ nbr, long long nbr_stride) {
+    int o = blockIdx.x * blockDim.x + threadIdx.x;
+    int k = blockIdx.y;
+    if (o >= n_cap) return;
+    int n = d_n ? min(*d_n, n_cap) : n_cap;
+    int res = -1;
+    if (o < n) {
+        int4 c = __ldg(out_coords + o);
+        int kx = k % ks, ky = (k / ks) % ks, kz = k / (ks * ks);
+        int cen = (ks & 1) ? ks / 2 : 0;
+        int x = c.y + (kx - cen) * step, y = c.z + (ky - cen) * step, z = c.w + (kz - cen) * step;
+        unsigned long long key;
+        if (lb2_pack_key(c.x, x, y, z, key)) res = lb2_grid_lookup(keys, rows, mask, key);
+    }
+    nbr[(long long)k * nbr_stride + o] = res;
+}
+
+extern "C" int lb2_kernel_map(void* handle, void* stream, lb2_grid grid_in, const int32_t* out_coords,
+                              const int32_t* d_nout, int32_t nout_cap, int32_t ks, int32_t step,
+                              int32_t* nbr, int64_t nbr_stride) {
+    Lb2Handle* h = (Lb2Handle*)handle;
+    LB2_REQUIRE(h, h && grid_in.keys && grid_in.vals && out_coords && nbr, "kernel_map null");
+    LB2_REQUIRE(h, ks >= 1 && ks <= 3 && step != 0 && nout_cap > 0 && nbr_stride >= nout_cap, "kernel_map args");
+    int kvol = ks * ks * ks;
+    dim3 grid(cdiv(nout_cap, 256), kvol);
+    k_kernel_map<<<grid, 256, 0, (cudaStream_t)stream>>>((const unsigned long long*)grid_in.keys,
+                                                        grid_in.vals + grid_in.cap_table, (unsigned)grid_in.cap_table - 1u,
+                                                        (const int4*)out_coords, d_nout, nout_cap, ks, step, nbr, nbr_stride);
+    LB2_POST_LAUNCH(h, "k_kernel_map");
+    return LB2_OK;
+}

@@ -1,0 +1,289 @@
+// K5/K6/K7 + FPS — the non-convolution kernels of the hot path.
+//   lb2_nn_match            exact 1-NN of voxel coordinates (pykeops argKmin, minkunet.py:403-418)
+//   lb2_linear              torch.nn.Linear (+LeakyReLU/tanh) of the gate / head MLPs (minkunet.py:165-181,376-380)
+//   lb2_gate_mul            x * w[idx]   (minkunet.py:431 ...)
+//   lb2_gather_rows         F[idx]       (minkunet.py:418,497)
+//   lb2_guidance_dpm_step   guidance + DPM-Solver++(2M) SDE + re-quantise (pipeline:153,162-164)
+//   lb2_farthest_point_sample  open3d FPS (pipeline:97-99)
+#include "common.cuh"
+#include <float.h>
+
+// ---------------------------------------------------------------------------------------------------
+// nn_match: brute force, keys staged through shared memory, exact 64-bit integer distances
+// ---------------------------------------------------------------------------------------------------
+#define NN_THREADS 256
+#define NN_KEYS    1024
+
+__global__ void __launch_bounds__(NN_THREADS) k_nn_match(const int4* __restrict__ q, const int* __restrict__ d_nq, int nq_cap,
+                                                          const int4* __restrict__ keys, const int* __restrict__ d_nk, int nk_cap,
+                                                          long long batch_scale, int* __restrict__ idx) {
+    __shared__ int4 ks[NN_KEYS];
+    const int nq = d_nq ? min(*d_nq, nq_cap) : nq_cap;
+    const int nk = d_nk ? min(*d_nk, nk_cap) : nk_cap;
+    if (blockIdx.x * NN_THREADS >= nq) return;
+    const int i = blockIdx.x * NN_THREADS + threadIdx.x;
+    int4 c = make_int4(0, 0, 0, 0);
+    if (i < nq) c = __ldg(q + i);
+    unsigned long long best = ~0ull;
+    int best_j = 0;
+    for (int j0 = 0; j0 < nk; j0 += NN_KEYS) {
+        const int cnt = min(NN_KEYS, nk - j0);
+        __syncthreads();
+        for (int j = threadIdx.x; j < cnt; j += NN_THREADS) ks[j] = __ldg(keys + j0 + j);
+        __syncthreads();
+#pragma unroll 4
+        for (int j = 0; j < cnt; ++j) {
+            const int4 kc = ks[j];
+            const long long dx = c.y - kc.y, dy = c.z - kc.z, dz = c.w - kc.w;
+            unsigned long long d = (unsigned long long)(dx * dx + dy * dy + dz * dz);
+            if (c.x != kc.x) {
+                if (batch_scale > 0) { long long db = (long long)(c.x - kc.x) * batch_scale; d += (unsigned long long)(db * db); }
+                else d += 1ull << 62;
+            }
+            if (d < best) { best = d; best_j = j0 + j; }     // strict '<' => lowest index on ties
+        }
+    }
+    if (i < nq) idx[i] = best_j;
+}
+
+extern "C" int lb2_nn_match(void* handle, void* stream, const int32_t* q_coords, const int32_t* d_nq, int32_t nq_cap,
+                            const int32_t* k_coords, const int32_t* d_nk, int32_t nk_cap, int32_t batch_scale,
+                            int32_t* idx) {
+    Lb2Handle* h = (Lb2Handle*)handle;
+    LB2_REQUIRE(h, h && q_coords && k_coords && idx && nq_cap > 0 && nk_cap > 0, "nn_match");
+    k_nn_match<<<cdiv(nq_cap, NN_THREADS), NN_THREADS, 0, (cudaStream_t)stream>>>(
+        (const int4*)q_coords, d_nq, nq_cap, (const int4*)k_coords, d_nk, nk_cap, (long long)batch_scale, idx);
+    LB2_POST_LAUNCH(h, "k_nn_match");
+    return LB2_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// linear: y = act(x W^T + b + addend)
+// ---------------------------------------------------------------------------------------------------
+#define LIN_BM 64
+#define LIN_BN 64
+#define LIN_BK 16
+
+__device__ __forceinline__ float lb2_act(float v, int act) {
+    if (act == 1) return v > 0.f ? v : 0.1f * v;
+    if (act == 2) return tanhf(v);
+    return v;
+}
+
+__global__ void __launch_bounds__(256) k_linear(const float* __restrict__ x, long long ldx, const float* __restrict__ w,
+                                                const float* __restrict__ b, const float* __restrict__ addend, long long ld_add,
+                                                int m_cap, const int* __restrict__ d_m, int n_in, int n_out, int act,
+                                                float* __restrict__ y, long long ldy,
+                                                const float* __restrict__ prebias, int pre_act) {
+    __shared__ float As[LIN_BK][LIN_BM + 4];
+    __shared__ float Bs[LIN_BK][LIN_BN + 4];
+    const int M = d_m ? min(*d_m, m_cap) : m_cap;
+    const int m0 = blockIdx.x * LIN_BM, n0 = blockIdx.y * LIN_BN;
+    if (m0 >= M) return;
+    const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
+    const int lr = t >> 2, lc = (t & 3) * 4;       // loader: row lr (of 64), k offset lc..lc+3
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < n_in; k0 += LIN_BK) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = k0 + lc + j;
+            const int row = m0 + lr, col = n0 + lr;
+            float xv = 0.f;
+            if (row < M && k < n_in) {
+                xv = __ldg(x + (long long)row * ldx + k);
+                if (prebias) xv = lb2_act(xv + __ldg(prebias + k), pre_act);
+            }
+            As[lc + j][lr] = xv;
+            Bs[lc + j][lr] = (col < n_out && k < n_in) ? __ldg(w + (long long)col * n_in + k) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < LIN_BK; ++kk) {
+            const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            const float4 bb = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int row = m0 + ty * 4 + i;
+        if (row >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int col = n0 + tx * 4 + j;
+            if (col >= n_out) continue;
+            float v = acc[i][j];
+            if (b) v += __ldg(b + col);
+            if (addend) v += __ldg(addend + (long long)row * ld_add + col);
+            y[(long long)row * ldy + col] = lb2_act(v, act);
+        }
+    }
+}
+
+extern "C" int lb2_linear(void* handle, void* stream, const float* x, int64_t ldx, const float* w, const float* b,
+                          const float* addend, int64_t ld_addend, int32_t m_cap, const int32_t* d_m,
+                          int32_t n_in, int32_t n_out, int32_t act, float* y, int64_t ldy,
+                          const float* prebias, int32_t pre_act) {
+    Lb2Handle* h = (Lb2Handle*)handle;
+    LB2_REQUIRE(h, h && x && w && y && m_cap > 0 && n_in > 0 && n_out > 0 && ldx >= n_in && ldy >= n_out, "linear");
+    dim3 grid(cdiv(m_cap, LIN_BM), cdiv(n_out, LIN_BN));
+    k_linear<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, w, b, addend, ld_addend, m_cap, d_m, n_in, n_out, act, y, ldy, prebias, pre_act);
+    LB2_POST_LAUNCH(h, "k_linear");
+    return LB2_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// gate multiply / row gather
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_gate_mul(const float* __restrict__ x, const float* __restrict__ table, const int* __restrict__ idx,
+                           const int* __restrict__ d_m, int m_cap, int c, float* __restrict__ out) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int M = d_m ? min(*d_m, m_cap) : m_cap;
+    if (t >= (long long)M * c) return;
+    const int r = (int)(t / c), j = (int)(t % c);
+    const int g = idx ? __ldg(idx + r) : 0;
+    out[t] = x[t] * __ldg(table + (long long)g * c + j);
+}
+
+extern "C" int lb2_gate_mul(void* handle, void* stream, const float* x, const float* table, const int32_t* idx,
+                            const int32_t* d_m, int32_t m_cap, int32_t c, float* out) {
+    Lb2Handle* h = (Lb2Handle*)handle;
+    LB2_REQUIRE(h, h && x && table && out && m_cap > 0 && c > 0, "gate_mul");
+    k_gate_mul<<<cdiv((long long)m_cap * c, 256), 256, 0, (cudaStream_t)stream>>>(x, table, idx, d_m, m_cap, c, out);
+    LB2_POST_LAUNCH(h, "k_gate_mul");
+    return LB2_OK;
+}
+
+__global__ void k_gather_rows(const float* __restrict__ src, const int* __restrict__ idx, int n, int c, float* __restrict__ out) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)n * c) return;
+    const int r = (int)(t / c), j = (int)(t % c);
+    out[t] = __ldg(src + (long long)__ldg(idx + r) * c + j);
+}
+
+extern "C" int lb2_gather_rows(void* handle, void* stream, const float* src, const int32_t* idx, int32_t n, int32_t c, float* out) {
+    Lb2Handle* h = (Lb2Handle*)handle;
+    LB2_REQUIRE(h, h && src && idx && out && n > 0 && c > 0, "gather_rows");
+    k_gather_rows<<<cdiv((long long)n * c, 256), 256, 0, (cudaStream_t)stream>>>(src, idx, n, c, out);
+    LB2_POST_LAUNCH(h, "k_gather_rows");
+    return LB2_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// guidance + DPM-Solver++(2M) SDE step + next-step features/coordinates, one thread per scalar.
+// Arithmetic order and precisions follow the torch expressions of the reference exactly (no FMA
+// contraction: explicit _rn intrinsics) so that, given identical eps, x_next and the coordinates
+// are bit-identical to the fp64 torch evaluation.
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_guidance_dpm(const float* __restrict__ eps_c, const float* __restrict__ eps_u, const int* __restrict__ inverse,
+                               const float* __restrict__ x_t, const double* __restrict__ x_init, const float* __restrict__ noise,
+                               double* __restrict__ x0_state, long long n_points, lb2_dpm_coef cf, float inv_res,
+                               float* __restrict__ eps_out, float* __restrict__ x_next, float* __restrict__ coord_next,
+                               const float* __restrict__ batch_col) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_points * 3) return;
+    const long long pnt = t / 3;
+    const int c = (int)(t - pnt * 3);
+    const long long v = inverse ? (long long)__ldg(inverse + pnt) : pnt;
+    const float ec = __ldg(eps_c + v * 3 + c), eu = __ldg(eps_u + v * 3 + c);
+    // pipeline:153  x_uncond + w * (x_cond - x_uncond)   (fp32)
+    const float eps = __fadd_rn(eu, __fmul_rn(cf.guidance_w, __fsub_rn(ec, eu)));
+    if (eps_out) eps_out[t] = eps;
+    // pipeline:162  input_noise = x_t.F - x_init   (fp32 - fp64 -> fp64)
+    const double sample = __dsub_rn((double)x_t[t], x_init[t]);
+    // diffusers convert_model_output: x0 = (sample - sigma_t * eps) / alpha_t   (sigma*eps in fp32)
+    const double se = (double)__fmul_rn((float)cf.sigma_s, eps);
+    const double x0 = __ddiv_rn(__dsub_rn(sample, se), cf.alpha_s);
+    double prev = __dadd_rn(__dmul_rn(cf.c_sample, sample), __dmul_rn(cf.c_x0, x0));
+    if (cf.second_order) {
+        const double d1 = __dmul_rn(cf.inv_r0, __dsub_rn(x0, x0_state[t]));
+        prev = __dadd_rn(prev, __dmul_rn(0.5 * cf.c_x0, d1));
+    }
+    prev = __dadd_rn(prev, __dmul_rn(cf.c_noise, (double)noise[t]));
+    x0_state[t] = x0;
+    // pipeline:163-164  x_t = x_init + prev ; batched_coordinates(dtype=float32)
+    const float xn = __double2float_rn(__dadd_rn(x_init[t], prev));
+    x_next[t] = xn;
+    if (coord_next) {
+        coord_next[pnt * 4 + 1 + c] = rintf(cf.div_mode == 0 ? __fdiv_rn(xn, cf.resolution) : __fmul_rn(xn, inv_res));
+        if (c == 0) coord_next[pnt * 4] = batch_col ? batch_col[pnt] : 0.f;
+    }
+}
+
+extern "C" int lb2_guidance_dpm_step(void* handle, void* stream, const float* eps_c, const float* eps_u,
+                                     const int32_t* inverse, const float* x_t, const double* x_init,
+                                     const float* noise, double* x0_state, int64_t n_points, lb2_dpm_coef coef,
+                                     float* eps_out, float* x_next, float* coord_next, const float* batch_col) {
+    Lb2Handle* h = (Lb2Handle*)handle;
+    LB2_REQUIRE(h, h && eps_c && eps_u && x_t && x_init && noise && x0_state && x_next && n_points > 0, "guidance_dpm_step");
+    LB2_REQUIRE(h, coef.resolution > 0.f, "resolution");
+    const float inv_res = 1.0f / coef.resolution;
+    k_guidance_dpm<<<cdiv(n_points * 3, 256), 256, 0, (cudaStream_t)stream>>>(eps_c, eps_u, inverse, x_t, x_init, noise, x0_state,
+                                                                              n_points, coef, inv_res, eps_out, x_next, coord_next, batch_col);
+    LB2_POST_LAUNCH(h, "k_guidance_dpm");
+    return LB2_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// farthest point sampling: one CTA, running min squared distance in global (L2-resident), fp64
+// ---------------------------------------------------------------------------------------------------
+#define FPS_THREADS 1024
+
+__global__ void __launch_bounds__(FPS_THREADS) k_fps(const double* __restrict__ pts, int n, int n_samples,
+                                                      int* __restrict__ out_idx, double* __restrict__ dist) {
+    __shared__ double s_val[FPS_THREADS / 32];
+    __shared__ int s_idx[FPS_THREADS / 32];
+    __shared__ int s_cur;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    for (int j = t; j < n; j += FPS_THREADS) dist[j] = DBL_MAX;
+    if (t == 0) s_cur = 0;
+    __syncthreads();
+    for (int it = 0; it < n_samples; ++it) {
+        const int cur = s_cur;
+        if (t == 0) out_idx[it] = cur;
+        const double cx = pts[3 * (long long)cur], cy = pts[3 * (long long)cur + 1], cz = pts[3 * (long long)cur + 2];
+        double bv = -1.0; int bi = 0x7fffffff;
+        for (int j = t; j < n; j += FPS_THREADS) {
+            const double dx = pts[3 * (long long)j] - cx, dy = pts[3 * (long long)j + 1] - cy, dz = pts[3 * (long long)j + 2] - cz;
+            // Eigen squaredNorm: x*x + y*y + z*z, left to right, no contraction
+            double d = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+            d = fmin(dist[j], d);
+            dist[j] = d;
+            if (d > bv) { bv = d; bi = j; }          // ascending j within a thread => first index kept
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        __syncthreads();          // previous iteration's readers of s_cur / s_val are done
+        if (lane == 0) { s_val[w] = bv; s_idx[w] = bi; }
+        __syncthreads();
+        if (w == 0) {
+            bv = s_val[lane]; bi = s_idx[lane];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            }
+            if (lane == 0) s_cur = bi;
+        }
+        __syncthreads();
+    }
+}
+
+extern "C" int lb2_farthest_point_sample(void* handle, void* stream, const double* pts, int32_t n, int32_t n_samples,
+                                         int32_t* out_idx, double* dist_scratch) {
+    Lb2Handle* h = (Lb2Handle*)handle;
+    LB2_REQUIRE(h, h && pts && out_idx && dist_scratch && n > 0 && n_samples > 0 && n_samples <= n, "fps");
+    k_fps<<<1, FPS_THREADS, 0, (cudaStream_t)stream>>>(pts, n, n_samples, out_idx, dist_scratch);
+    LB2_POST_LAUNCH(h, "k_fps");
+    return LB2_OK;
+}
