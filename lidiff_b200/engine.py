@@ -1,0 +1,406 @@
+"""Fused denoising engine: the sampling loop of
+/root/reference/lidiff/tools/diff_completion_pipeline.py:148-169 restructured for the B200
+(SURVEY.md App. D), every arithmetic step a call into the C-ABI CUDA library, no host
+synchronisation inside the loop (row counts stay in device scalars), buffers sized once.
+
+Exact restructurings relative to the operator-by-operator path (results equal up to fp32 summation
+order):
+  D.1  gate MLPs hoisted to the <= M_part distinct rows and split into step-invariant and
+       time-dependent halves; `x*w` is fused into the producing convolution's epilogue;
+  D.2  the conditional encoder output is computed once per scan, the unconditional one (a single
+       voxel at the origin) once per engine; the 8 unconditional gate rows for all T steps are
+       precomputed;
+  D.3  both guidance passes run through every convolution in ONE launch (shared maps/weights);
+       the stem (identical for both passes) runs once;
+  D.4  head + guidance on voxel rows, then one fused per-point kernel: devoxelise, guidance,
+       DPM-Solver++(2M) SDE update in fp64, next TensorField features + coordinates;
+  D.5  eval-mode BatchNorm folded into a per-channel affine epilogue (+ReLU, + residual add);
+  ME.cat is never materialised (second K segment of the consuming convolution).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, ConvIO, DpmCoef
+from .scheduler import DPMSolverMultistepScheduler
+
+GATE_NAMES = ("stage1", "stage2", "stage3", "stage4", "up1", "up2", "up3", "up4")
+GATE_LEVEL = (0, 1, 2, 3, 4, 3, 2, 1)
+BN_EPS = 1e-5
+
+
+class ConvLayer:
+    """conv weight + folded eval-BatchNorm affine"""
+
+    def __init__(self, h, sd, pconv, pbn, device):
+        W = sd[f"{pconv}.kernel"].detach().to(device=device, dtype=torch.float32)
+        if W.dim() == 2:
+            W = W[None]
+        self.W = W.contiguous()
+        self.kvol, self.cin, self.cout = self.W.shape
+        if pbn is not None:
+            g = lambda k: sd[f"{pbn}.bn.{k}"].detach().to(device=device, dtype=torch.float32)
+            scale = g("weight") / torch.sqrt(g("running_var") + BN_EPS)
+            self.scale = scale.contiguous()
+            self.shift = (g("bias") - g("running_mean") * scale).contiguous()
+        else:
+            self.scale = self.shift = None
+        self.Wp = h.pack_weights(self.W)          # tensor-core image (None when unsupported)
+
+
+class Linear:
+    def __init__(self, sd, p, device, cols=None):
+        w = sd[f"{p}.weight"].detach().to(device=device, dtype=torch.float32)
+        self.w = (w if cols is None else w[:, cols[0]:cols[1]]).contiguous()
+        self.b = sd[f"{p}.bias"].detach().to(device=device, dtype=torch.float32).contiguous()
+        self.n_out, self.n_in = self.w.shape
+
+
+def _net_layers(h, sd, device, decoder: bool):
+    L = {}
+
+    def add(pconv, pbn):
+        L[pconv] = ConvLayer(h, sd, pconv, pbn, device)
+
+    def res(p):
+        add(f"{p}.net.0", f"{p}.net.1")
+        add(f"{p}.net.3", f"{p}.net.4")
+        if f"{p}.downsample.0.kernel" in sd:
+            add(f"{p}.downsample.0", f"{p}.downsample.1")
+
+    add("stem.0", "stem.1")
+    add("stem.3", "stem.4")
+    for n in range(1, 5):
+        add(f"stage{n}.0.net.0", f"stage{n}.0.net.1")
+        res(f"stage{n}.1")
+        res(f"stage{n}.2")
+    if decoder:
+        for n in range(1, 5):
+            add(f"up{n}.0.net.0", f"up{n}.0.net.1")
+            res(f"up{n}.1.0")
+            res(f"up{n}.1.1")
+    return L
+
+
+class Geometry:
+    """Device-resident coordinate manager of one point set: 5 levels of voxel rows + hash grids, the
+    3^3 / 2^3-stride / transposed kernel maps, all at a fixed row capacity, row counts on device."""
+
+    def __init__(self, h, n_cap: int, with_up: bool = True, levels: int = 5):
+        dev = h.device
+        self.h, self.n_cap, self.levels = h, n_cap, levels
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.C = [torch.zeros((n_cap, 4), **i32) for _ in range(levels)]
+        self.d_n = [torch.zeros(1, **i32) for _ in range(levels)]
+        self.grid = [h.new_grid(n_cap) for _ in range(levels)]
+        self.inv = [torch.zeros(n_cap, **i32) for _ in range(levels)]     # [0]: point -> voxel; [l]: fine row -> coarse row
+        self.nbr3 = [torch.empty((27, n_cap), **i32) for _ in range(levels)]
+        self.nbr_dn = [None] + [torch.empty((8, n_cap), **i32) for _ in range(levels - 1)]
+        self.nbr_up = [torch.empty((8, n_cap), **i32) for _ in range(levels - 1)] + [None] if with_up else None
+        self.scratch = h.unique_scratch(n_cap)
+        self.counts = torch.empty(n_cap, **i32)
+
+    def build(self, coords_f: torch.Tensor, n_points: int):
+        """coords_f (n_points,4) fp32 integer-valued [b,x,y,z] -> all levels and maps (async)."""
+        h, N = self.h, self.n_cap
+        h.unique_build(coords_f, None, None, n_points, 0, self.grid[0], self.C[0], self.inv[0], self.d_n[0], self.scratch)
+        for l in range(1, self.levels):
+            h.unique_build(None, self.C[l - 1], self.d_n[l - 1], N, 1 << l, self.grid[l], self.C[l], self.inv[l], self.d_n[l], self.scratch)
+        for l in range(self.levels):
+            h.kernel_map(self.grid[l], self.C[l], self.d_n[l], N, 3, 1 << l, self.nbr3[l], N)
+        for l in range(1, self.levels):
+            h.kernel_map(self.grid[l - 1], self.C[l], self.d_n[l], N, 2, 1 << (l - 1), self.nbr_dn[l], N)
+        if self.nbr_up is not None:
+            for l in range(self.levels - 1):
+                h.kernel_map(self.grid[l + 1], self.C[l], self.d_n[l], N, 2, -(1 << l), self.nbr_up[l], N)
+
+    def voxel_mean(self, feats, n_points, out):
+        self.h.voxel_mean(feats, self.inv[0], n_points, feats.shape[1], self.d_n[0], self.n_cap, out, self.counts)
+
+    def sizes(self):
+        return [int(d.item()) for d in self.d_n]
+
+
+class DenoiseEngine:
+    def __init__(self, sd_enc: dict, sd_diff: dict, *, device="cuda", n_points=180000, denoising_steps=50,
+                 cond_weight=6.0, resolution=0.05, t_steps=1000, beta_start=3.5e-5, beta_end=0.007,
+                 div_mode=1, conv_algo=_lib.ALGO_AUTO, batch_coord=0.0):
+        self.device = torch.device(device)
+        self.h = _lib.get_handle(self.device)
+        self.N = int(n_points)
+        self.w = float(cond_weight)
+        self.resolution = float(resolution)
+        self.div_mode = int(div_mode)
+        self.conv_algo = conv_algo
+        h, dev = self.h, self.device
+        self.enc = _net_layers(h, sd_enc, dev, decoder=False)
+        self.diff = _net_layers(h, sd_diff, dev, decoder=True)
+        self.sched = DPMSolverMultistepScheduler(num_train_timesteps=t_steps, beta_start=beta_start, beta_end=beta_end,
+                                                 beta_schedule="linear", algorithm_type="sde-dpmsolver++", solver_order=2)
+        self.sched.set_timesteps(denoising_steps)
+        self.T = len(self.sched.timesteps)
+        # gate / head MLPs (minkunet.py:165-181 ..., :376-380)
+        self.latent = [(Linear(sd_diff, f"latent_{g}.0", dev), Linear(sd_diff, f"latent_{g}.2", dev)) for g in GATE_NAMES]
+        self.temp = [(Linear(sd_diff, f"{g}_temp.0", dev), Linear(sd_diff, f"{g}_temp.2", dev)) for g in GATE_NAMES]
+        self.lat_p, self.lat_t, self.lat_2 = [], [], []
+        for g in GATE_NAMES:
+            half = sd_diff[f"latemp_{g}.0.weight"].shape[1] // 2
+            pc, tc = ((half, 2 * half), (0, half)) if g == "up1" else ((0, half), (half, 2 * half))   # :461 swaps the cat order
+            self.lat_p.append(Linear(sd_diff, f"latemp_{g}.0", dev, cols=pc))
+            self.lat_t.append(Linear(sd_diff, f"latemp_{g}.0", dev, cols=tc))
+            self.lat_2.append(Linear(sd_diff, f"latemp_{g}.2", dev))
+        self.head = (Linear(sd_diff, "last.0", dev), Linear(sd_diff, "last.2", dev))
+        self._bufs = {}
+        self.geom = Geometry(h, self.N, with_up=True)
+        self.geom_cond = None
+        self.part_cap = 0
+        self._zero_i = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._one_i = torch.ones(1, dtype=torch.int32, device=dev)
+        self._prepare_time_tables()
+        self._prepare_uncond()
+
+    # ------------------------------------------------------------------------------------------------
+    @classmethod
+    def from_modules(cls, pipe, **kw):
+        sd_e = {k: v for k, v in pipe.partial_enc.state_dict().items()}
+        sd_d = {k: v for k, v in pipe.model.state_dict().items()}
+        hp = pipe.hparams
+        return cls(sd_e, sd_d, device=pipe.device, n_points=hp["data"]["num_points"], denoising_steps=hp["diff"]["s_steps"],
+                   cond_weight=pipe.w_uncond, resolution=hp["data"]["resolution"], t_steps=hp["diff"]["t_steps"],
+                   beta_start=hp["diff"]["beta_start"], beta_end=hp["diff"]["beta_end"], **kw)
+
+    def buf(self, name, shape, dtype=torch.float32):
+        t = self._bufs.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = torch.zeros(shape, dtype=dtype, device=self.device)
+            self._bufs[name] = t
+        return t
+
+    # ---- small dense helpers ------------------------------------------------------------------------
+    def _linear(self, x, lin: Linear, out, act=0, m_cap=None, d_m=None, prebias=None, pre_act=0, bias=True):
+        m_cap = x.shape[0] if m_cap is None else m_cap
+        self.h.linear(x, x.stride(0), lin.w, lin.b if bias else None, None, 0, m_cap, d_m, lin.n_in, lin.n_out, act,
+                      out, out.stride(0), prebias, pre_act)
+        return out
+
+    def _timestep_embedding(self, ts: torch.Tensor) -> torch.Tensor:
+        """MinkUNetDiff.get_timestep_embedding (minkunet.py:390-401) for all T steps at once."""
+        half = 48
+        freq = torch.from_numpy(np.exp(np.arange(0, half) * -(np.log(10000) / (half - 1)))).float().to(self.device)
+        arg = ts.to(self.device)[:, None] * freq[None, :]
+        return torch.cat([torch.sin(arg), torch.cos(arg)], dim=1).contiguous()
+
+    def _prepare_time_tables(self):
+        """bvec[g] (T, hidden_g) = W1t . temp_g(temb(t)) + b1 for every step (time-only half of each gate)."""
+        T, dev = self.T, self.device
+        temb = self._timestep_embedding(self.sched.timesteps)
+        self.bvec = []
+        for g in range(8):
+            l0, l2 = self.temp[g]
+            u = self._linear(temb, l0, torch.empty((T, l0.n_out), device=dev), act=1)
+            tv = self._linear(u, l2, torch.empty((T, l2.n_out), device=dev))
+            self.bvec.append(self._linear(tv, self.lat_t[g], torch.empty((T, self.lat_t[g].n_out), device=dev)))
+
+    def _gate_tables(self, A_list, rows_cap, d_rows, step, tag):
+        """table_g = W2 . leaky(A_g + bvec_g[step]) + b2  -> (rows_cap, C_g) per gate"""
+        out = []
+        for g in range(8):
+            t = self.buf(f"gate_{tag}_{g}", (rows_cap, self.lat_2[g].n_out))
+            self._linear(A_list[g], self.lat_2[g], t, m_cap=rows_cap, d_m=d_rows, prebias=self.bvec[g][step], pre_act=1)
+            out.append(t)
+        return out
+
+    def _part_A(self, part_F, rows_cap, d_rows, tag):
+        """A_g = W1p . latent_g(part_F)   (step-invariant half of each gate)"""
+        A = []
+        for g in range(8):
+            l0, l2 = self.latent[g]
+            h1 = self._linear(part_F, l0, self.buf(f"lat_h_{tag}", (rows_cap, l0.n_out)), act=1, m_cap=rows_cap, d_m=d_rows)
+            p = self._linear(h1, l2, self.buf(f"lat_p_{tag}", (rows_cap, l2.n_out)), m_cap=rows_cap, d_m=d_rows)
+            a = torch.empty((rows_cap, self.lat_p[g].n_out), device=self.device)
+            A.append(self._linear(p, self.lat_p[g], a, m_cap=rows_cap, d_m=d_rows, bias=False))
+        return A
+
+    # ---- convolution helper ---------------------------------------------------------------------------
+    def _conv(self, lay: ConvLayer, nbr, d_m, cap, in1, in2=None, out=None, residual=None, relu=True,
+              gate=None, out_gated=None, npass=1):
+        """in1/in2/residual/out/out_gated: tensors shaped (P, cap, C) with P in {1, npass}; gate: list per
+        pass of (table, idx-or-None)."""
+        d = ConvDesc()
+        d.c1 = in1.shape[-1]
+        d.c2 = in2.shape[-1] if in2 is not None else 0
+        assert d.c1 + d.c2 == lay.cin, (d.c1, d.c2, lay.cin)
+        d.cout, d.kvol = lay.cout, lay.kvol
+        d.weight = lay.W.data_ptr()
+        d.weight_packed = lay.Wp.data_ptr() if lay.Wp is not None else None
+        d.scale = lay.scale.data_ptr() if lay.scale is not None else None
+        d.shift = lay.shift.data_ptr() if lay.shift is not None else None
+        d.relu = 1 if relu else 0
+        d.nbr = nbr.data_ptr() if nbr is not None else None
+        d.nbr_stride = nbr.stride(0) if nbr is not None else cap
+        d.d_mout = d_m.data_ptr() if d_m is not None else None
+        d.mout_cap, d.npass = cap, npass
+        sel = lambda t, p: None if t is None else t[min(p, t.shape[0] - 1)].data_ptr()
+        for p in range(npass):
+            gt = gi = None
+            if gate is not None:
+                gt = gate[p][0].data_ptr()
+                gi = gate[p][1].data_ptr() if gate[p][1] is not None else None
+            d.io[p] = ConvIO(sel(in1, p), sel(in2, p), sel(residual, p), sel(out, p), gt, gi, sel(out_gated, p))
+        self.h.spconv(d, self.conv_algo)
+
+    def _res(self, L, p, geom, lvl, in1, in2, npass, tag, gate=None, want_plain=True):
+        cap = geom.n_cap
+        nbr, d_m = geom.nbr3[lvl], geom.d_n[lvl]
+        cmid = L[f"{p}.net.0"].cout
+        hbuf = self.buf(f"{tag}.h", (npass, cap, cmid))
+        self._conv(L[f"{p}.net.0"], nbr, d_m, cap, in1, in2, out=hbuf, npass=npass)
+        if f"{p}.downsample.0" in L:
+            sbuf = self.buf(f"{tag}.s", (npass, cap, cmid))
+            self._conv(L[f"{p}.downsample.0"], None, d_m, cap, in1, in2, out=sbuf, relu=False, npass=npass)
+        else:
+            assert in2 is None
+            sbuf = in1
+        out = self.buf(f"{tag}.o", (npass, cap, cmid)) if want_plain else None
+        og = self.buf(f"{tag}.g", (npass, cap, cmid)) if gate is not None else None
+        self._conv(L[f"{p}.net.3"], nbr, d_m, cap, hbuf, None, out=out, residual=sbuf, relu=True, gate=gate, out_gated=og, npass=npass)
+        return out, og
+
+    def _encoder(self, L, geom, F0, npass, tag, gates=None):
+        """stem + 4 stages.  gates: None (MinkGlobalEnc) or per-gate list of per-pass (table, idx)."""
+        cap = geom.n_cap
+        s0 = self.buf(f"{tag}.stem0", (1, cap, 32))
+        self._conv(L["stem.0"], geom.nbr3[0], geom.d_n[0], cap, F0, out=s0, npass=1)
+        x0 = self.buf(f"{tag}.x0", (1, cap, 32))
+        self._conv(L["stem.3"], geom.nbr3[0], geom.d_n[0], cap, s0, out=x0, npass=1)
+        skips = [x0]
+        if gates is not None:
+            cur = self.buf(f"{tag}.x0g", (npass, cap, 32))
+            for p in range(npass):
+                tb, ix = gates[0][p]
+                self.h.gate_mul(x0[0], tb, ix, geom.d_n[0], cap, 32, cur[p])
+        else:
+            cur = x0
+        for n in range(1, 5):
+            a = self.buf(f"{tag}.s{n}a", (npass, cap, L[f"stage{n}.0.net.0"].cout))
+            self._conv(L[f"stage{n}.0.net.0"], geom.nbr_dn[n], geom.d_n[n], cap, cur, out=a, npass=npass)
+            b, _ = self._res(L, f"stage{n}.1", geom, n, a, None, npass, f"{tag}.s{n}r1")
+            g = gates[n] if gates is not None else None
+            x, xg = self._res(L, f"stage{n}.2", geom, n, b, None, npass, f"{tag}.s{n}r2", gate=g)
+            skips.append(x)
+            cur = xg if gates is not None else x
+        return skips, cur
+
+    def _decoder(self, L, geom, skips, cur, npass, tag, gates):
+        cap = geom.n_cap
+        y = cur
+        for n in range(1, 5):
+            lvl = 4 - n
+            d = self.buf(f"{tag}.u{n}d", (npass, cap, L[f"up{n}.0.net.0"].cout))
+            self._conv(L[f"up{n}.0.net.0"], geom.nbr_up[lvl], geom.d_n[lvl], cap, y, out=d, npass=npass)
+            b, _ = self._res(L, f"up{n}.1.0", geom, lvl, d, skips[lvl], npass, f"{tag}.u{n}r1")
+            g = gates[4 + n] if (gates is not None and n < 4) else None
+            o, og = self._res(L, f"up{n}.1.1", geom, lvl, b, None, npass, f"{tag}.u{n}r2", gate=g, want_plain=(g is None))
+            y = og if g is not None else o
+        return y
+
+    # ---- conditioning ------------------------------------------------------------------------------------
+    def _prepare_uncond(self):
+        """x_uncond = all-zero points -> one voxel at the origin with zero feature; its encoder output is
+        a single 256-vector that depends on the weights only (App. D.2).  Gate rows for all steps."""
+        dev = self.device
+        g1 = Geometry(self.h, 16, with_up=False)
+        coords = torch.zeros((16, 4), dtype=torch.float32, device=dev)
+        g1.build(coords, 16)
+        F0 = torch.zeros((1, 16, 3), device=dev)
+        skips, _ = self._encoder(self.enc, g1, F0, 1, "uenc")
+        part_u = skips[4][0][:1].clone()                              # (1,256)
+        A = self._part_A(part_u, 1, None, "u")
+        self.table_u = []                                             # [g] -> (T, C_g)
+        for g in range(8):
+            t = torch.empty((self.T, self.lat_2[g].n_out), device=dev)
+            for s in range(self.T):
+                self._linear(A[g], self.lat_2[g], t[s:s + 1], prebias=self.bvec[g][s], pre_act=1)
+            self.table_u.append(t)
+        for k in [k for k in self._bufs if k.startswith("uenc")]:
+            del self._bufs[k]
+
+    def set_condition(self, scan: torch.Tensor):
+        """scan (N,3): the conditioning point cloud (x_cond).  Runs MinkGlobalEnc once (App. D.2)."""
+        dev, N = self.device, scan.shape[0]
+        pts = scan.to(device=dev, dtype=torch.float32).contiguous()
+        if self.geom_cond is None or self.geom_cond.n_cap != N:
+            self.geom_cond = Geometry(self.h, N, with_up=False)
+        coords = self.buf("cond.coords", (N, 4))
+        coords[:, 0] = 0
+        self.h.quantize(pts, self.resolution, self.div_mode, self.buf("cond.q", (N, 3)))
+        coords[:, 1:] = self._bufs["cond.q"]
+        g = self.geom_cond
+        g.build(coords, N)
+        F0 = self.buf("cond.F0", (1, N, 3))
+        g.voxel_mean(pts, N, F0[0])
+        skips, _ = self._encoder(self.enc, g, F0, 1, "cenc")
+        self.part_F = skips[4][0]                                      # (N cap, 256), rows valid < d_n[4]
+        self.part_C, self.part_dn = g.C[4], g.d_n[4]
+        self.part_cap = N
+        self.A_cond = self._part_A(self.part_F, N, self.part_dn, "c")
+
+    # ---- one denoising step ----------------------------------------------------------------------------------
+    def step(self, i: int, x_t, x_next, coords, coords_next, x_init, noise_i, x0_state, eps_out=None):
+        h, N, g = self.h, self.N, self.geom
+        g.build(coords, N)
+        F0 = self.buf("F0", (1, N, 3))
+        g.voxel_mean(x_t, N, F0[0])
+        nn = []
+        for l in range(5):
+            ix = self.buf(f"nn{l}", (N,), torch.int32)
+            h.nn_match(g.C[l], g.d_n[l], N, self.part_C, self.part_dn, self.part_cap, 0, ix)
+            nn.append(ix)
+        tabs_c = self._gate_tables(self.A_cond, self.part_cap, self.part_dn, i, "c")
+        gates = [[(tabs_c[k], nn[GATE_LEVEL[k]]), (self.table_u[k][i:i + 1], None)] for k in range(8)]
+        skips, cur = self._encoder(self.diff, g, F0, 2, "d", gates)
+        y4 = self._decoder(self.diff, g, skips, cur, 2, "d", gates)
+        eps = self.buf("eps_vox", (2, N, 3))
+        hid = self.buf("head_h", (N, 20))
+        for p in range(2):
+            self._linear(y4[p], self.head[0], hid, act=1, m_cap=N, d_m=g.d_n[0])
+            self._linear(hid, self.head[1], eps[p], m_cap=N, d_m=g.d_n[0])
+        c = self.sched.coefficients(i)
+        second = i > 0 and not (i == self.T - 1 and self.T < 15)
+        cf = DpmCoef(c["c_sample"], c["c_x0"], c["c_noise"], c["sigma_s"], c["alpha_s"], c.get("inv_r0", 0.0) if second else 0.0,
+                     self.w, self.resolution, 1 if second else 0, self.div_mode, 1)
+        h.guidance_dpm_step(eps[0], eps[1], g.inv[0], x_t, x_init, noise_i, x0_state, N, cf, eps_out, x_next, coords_next)
+
+    # ---- the loop (completion_loop, pipeline:155-169) -----------------------------------------------------------
+    def run(self, x_init: torch.Tensor, x_feats: torch.Tensor, step_noise=None, n_steps=None, return_device=False):
+        """x_init (1,N,3) fp64 conditioning scan, x_feats (1,N,3) noisy start.  Returns final x_t.F (N,3)."""
+        dev, N = self.device, self.N
+        x_init = x_init.reshape(-1, 3).to(device=dev, dtype=torch.float64).contiguous()
+        assert x_init.shape[0] == N, f"engine built for {N} points, got {x_init.shape[0]}"
+        self.set_condition(x_init)
+        T = self.T if n_steps is None else n_steps
+        if step_noise is None:
+            step_noise = torch.randn((T, N, 3), device=dev)
+        step_noise = step_noise.reshape(-1, N, 3).to(device=dev, dtype=torch.float32).contiguous()
+        xa = self.buf("x_a", (N, 3))
+        xb = self.buf("x_b", (N, 3))
+        ca = self.buf("c_a", (N, 4))
+        cb = self.buf("c_b", (N, 4))
+        x0s = self.buf("x0_state", (N, 3), torch.float64)
+        xa.copy_(x_feats.reshape(-1, 3).to(device=dev, dtype=torch.float32))
+        ca[:, 0] = 0
+        self.h.quantize(xa, self.resolution, self.div_mode, self.buf("q0", (N, 3)))
+        ca[:, 1:] = self._bufs["q0"]
+        for i in range(T):
+            self.step(i, xa, xb, ca, cb, x_init, step_noise[i], x0s)
+            xa, xb, ca, cb = xb, xa, cb, ca
+        if return_device:
+            return xa
+        out = xa.cpu().numpy()
+        if self.h.read_status() & 1:
+            raise RuntimeError("lidiff_b200: a coordinate left the supported key range during sampling")
+        return out

@@ -11,7 +11,7 @@ from __future__ import annotations
 
 import torch
 
-from . import _lib
+from . import _lib, me
 
 
 class LazyTensor:
@@ -19,13 +19,15 @@ class LazyTensor:
         if _kind is None:
             if x.dim() != 3 or (x.shape[0] != 1 and x.shape[1] != 1):
                 raise RuntimeError("LazyTensor: expected x[:, None, :] or x[None, :, :]")
-            self.kind = "i" if x.shape[1] == 1 else "j"
+            # (1,1,D) is both an i- and a j-variable (a single row broadcasts either way), as in KeOps
+            self.kind = "var"
+            self.can_i, self.can_j = x.shape[1] == 1, x.shape[0] == 1
             self.data = x.reshape(-1, x.shape[-1])
         else:
             self.kind, self.a, self.b = _kind, _a, _b
 
     def __sub__(self, o):
-        if self.kind == "i" and getattr(o, "kind", None) == "j":
+        if self.kind == "var" and getattr(o, "kind", None) == "var" and self.can_i and o.can_j:
             return LazyTensor(None, "diff", self, o)
         raise RuntimeError("LazyTensor shim: only (x_i - y_j) is supported")
 
@@ -43,8 +45,7 @@ class LazyTensor:
         if self.kind != "sqdist" or K != 1 or dim != 1:
             raise RuntimeError("LazyTensor shim: only sqdist.argKmin(1, dim=1) is supported")
         q, k = self.a.data, self.b.data
-        if not q.is_cuda:
-            raise RuntimeError("LazyTensor shim: CUDA tensors only (no CPU backend)")
+        me._require_cuda(q, "LazyTensor operands")
         if q.shape[1] != 4 or k.shape[1] != 4:
             raise RuntimeError("LazyTensor shim: (N,4) [b,x,y,z] coordinates expected")
         h = _lib.get_handle(q.device)

@@ -1,0 +1,235 @@
+"""TEST INFRASTRUCTURE: a CPU stand-in for `lidiff_b200._lib.Handle` so the HOST logic of the product
+(operator surface wiring, engine orchestration, buffer/pointer plumbing, ctypes descriptors) can be
+exercised without a GPU.  Every entry point is implemented with the oracle's primitives on CPU
+memory reached through the same raw pointers the CUDA library would get.  Never shipped, never used
+by the product: tests install it by monkeypatching `_lib.get_handle`."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from oracle import me_cpu as ome
+
+
+def _arr(ptr, shape, ctype, npdtype):
+    n = int(np.prod(shape))
+    if n == 0:
+        return np.zeros(shape, npdtype)
+    buf = (ctype * n).from_address(ptr)
+    return np.frombuffer(buf, dtype=npdtype).reshape(shape)
+
+
+def _f(ptr, shape):
+    return _arr(ptr, shape, C.c_float, np.float32)
+
+
+def _i(ptr, shape):
+    return _arr(ptr, shape, C.c_int32, np.int32)
+
+
+class FakeHandle:
+    def __init__(self):
+        self.device = torch.device("cpu")
+        self.grids = {}
+        self.launches = 0
+        self.status = 0
+
+    # plumbing -------------------------------------------------------------------------------------
+    def launch_count(self):
+        return self.launches
+
+    def read_status(self):
+        s, self.status = self.status, 0
+        return s
+
+    def new_grid(self, n_cap):
+        cap = 1 << max(4, (2 * n_cap - 1).bit_length())
+        return (torch.empty(cap, dtype=torch.int64), torch.empty(2 * cap, dtype=torch.int32), cap)
+
+    def unique_scratch(self, n_cap):
+        return torch.empty(16, dtype=torch.uint8)
+
+    @staticmethod
+    def _n(d_n, cap):
+        return cap if d_n is None else min(int(d_n[0]), cap)
+
+    # coords ---------------------------------------------------------------------------------------
+    def quantize(self, x, resolution, div_mode, out):
+        self.launches += 1
+        out.copy_(ome.quantize(x, resolution, "div" if div_mode == 0 else "mul").reshape(out.shape))
+
+    def unique_build(self, in_f, in_i, d_nin, n_cap, ts_floor, grid, out_coords, inverse, d_nout, scratch):
+        self.launches += 6
+        n = self._n(d_nin, n_cap)
+        rows = torch.floor(in_f[:n]).long().numpy() if in_f is not None else in_i[:n].long().numpy()
+        rows = rows.copy()
+        if ts_floor > 0:
+            rows[:, 1:] = np.floor_divide(rows[:, 1:], ts_floor) * ts_floor
+        first, inv = ome.unique_first_occurrence(rows)
+        M = first.shape[0]
+        out_coords[:M] = torch.from_numpy(rows[first].astype(np.int32))
+        if inverse is not None:
+            inverse[:n] = torch.from_numpy(inv.astype(np.int32))
+        d_nout[0] = M
+        keys = ome.pack_keys(rows[first])
+        order = np.argsort(keys, kind="stable")
+        self.grids[grid[0].data_ptr()] = (keys[order], order)
+
+    def voxel_mean(self, feats, inverse, n, c, d_m, m_cap, out, counts):
+        self.launches += 2
+        M = self._n(d_m, m_cap)
+        inv = inverse[:n].long()
+        sums = torch.zeros(M, c)
+        sums.index_add_(0, inv, feats[:n])
+        cnt = torch.bincount(inv, minlength=M).float()
+        out[:M] = sums / cnt[:, None]
+
+    def kernel_map(self, grid_in, out_coords, d_nout, nout_cap, ks, step, nbr, nbr_stride):
+        self.launches += 1
+        n = self._n(d_nout, nout_cap)
+        skeys, order = self.grids[grid_in[0].data_ptr()]
+        Cq = out_coords[:n].long().numpy()
+        r = np.arange(ks)
+        kz, ky, kx = np.meshgrid(r, r, r, indexing="ij")
+        offs = np.stack([kx.reshape(-1), ky.reshape(-1), kz.reshape(-1)], 1)
+        if ks % 2 == 1:
+            offs = offs - ks // 2
+        nb = nbr.reshape(-1)[: ks ** 3 * nbr_stride].view(ks ** 3, nbr_stride)
+        for k, off in enumerate(offs * step):
+            q = Cq.copy()
+            q[:, 1:] += off[None, :]
+            ok = (np.abs(q[:, 1:]) < ome.AXIS_OFF).all(1)
+            qk = ome.pack_keys(np.where(ok[:, None], q, 0))
+            pos = np.minimum(np.searchsorted(skeys, qk), max(skeys.shape[0] - 1, 0))
+            hit = ok & (skeys[pos] == qk) if skeys.shape[0] else np.zeros(n, bool)
+            res = np.where(hit, order[pos], -1).astype(np.int32)
+            nb[k, :n] = torch.from_numpy(res)
+            nb[k, n:nout_cap] = -1
+
+    # conv -----------------------------------------------------------------------------------------
+    def packed_weight_bytes(self, kvol, cin, cout):
+        return 0
+
+    def pack_weights(self, w):
+        return None
+
+    def spconv(self, d, algo=0):
+        self.launches += 1
+        M = d.mout_cap if not d.d_mout else min(int(_i(d.d_mout, (1,))[0]), d.mout_cap)
+        ctot = d.c1 + d.c2
+        W = torch.from_numpy(_f(d.weight, (d.kvol, ctot, d.cout)).copy()).double()
+        nbr = _i(d.nbr, (d.kvol, d.nbr_stride))[:, :M] if d.nbr else np.arange(M, dtype=np.int32)[None]
+        rows_in = int(nbr.max()) + 1 if nbr.size else 0
+        for p in range(d.npass):
+            io = d.io[p]
+            x = torch.from_numpy(_f(io.in1, (rows_in, d.c1)).copy())
+            if d.c2:
+                x = torch.cat([x, torch.from_numpy(_f(io.in2, (rows_in, d.c2)).copy())], 1)
+            x = x.double()
+            y = torch.zeros(M, d.cout, dtype=torch.float64)
+            for k in range(d.kvol):
+                o = np.nonzero(nbr[k] >= 0)[0]
+                if o.size:
+                    y[torch.from_numpy(o)] += x[torch.from_numpy(nbr[k][o].astype(np.int64))] @ W[k]
+            if d.scale:
+                y = y * torch.from_numpy(_f(d.scale, (d.cout,)).copy()).double() + torch.from_numpy(_f(d.shift, (d.cout,)).copy()).double()
+            if io.residual:
+                y = y + torch.from_numpy(_f(io.residual, (M, d.cout)).copy()).double()
+            if d.relu:
+                y = torch.relu(y)
+            if io.out:
+                _f(io.out, (M, d.cout))[:] = y.float().numpy()
+            if io.out_gated:
+                g = y
+                if io.gate_table:
+                    gi = _i(io.gate_idx, (M,)).astype(np.int64) if io.gate_idx else np.zeros(M, np.int64)
+                    rows_g = int(gi.max()) + 1 if M else 0
+                    tab = torch.from_numpy(_f(io.gate_table, (rows_g, d.cout)).copy()).double()
+                    g = y * tab[torch.from_numpy(gi)]
+                _f(io.out_gated, (M, d.cout))[:] = g.float().numpy()
+
+    # misc -----------------------------------------------------------------------------------------
+    def nn_match(self, q, d_nq, nq_cap, k, d_nk, nk_cap, batch_scale, idx):
+        self.launches += 1
+        nq, nk = self._n(d_nq, nq_cap), self._n(d_nk, nk_cap)
+        qq, kk = q[:nq].double(), k[:nk].double()
+        if batch_scale == 0:
+            qq, kk = qq.clone(), kk.clone()
+            qq[:, 0] *= 1e9
+            kk[:, 0] *= 1e9
+        out = torch.empty(nq, dtype=torch.int64)
+        for s in range(0, nq, 4096):
+            d = ((qq[s:s + 4096, None, :] - kk[None]) ** 2).sum(-1)
+            out[s:s + 4096] = torch.argmin(d, 1)
+        idx[:nq] = out.int()
+
+    @staticmethod
+    def _act(v, act):
+        return torch.nn.functional.leaky_relu(v, 0.1) if act == 1 else (torch.tanh(v) if act == 2 else v)
+
+    def linear(self, x, ldx, w, b, addend, ld_add, m_cap, d_m, n_in, n_out, act, y, ldy, prebias=None, pre_act=0):
+        self.launches += 1
+        M = self._n(d_m, m_cap)
+        xs = torch.as_strided(x, (M, n_in), (ldx, 1))
+        if prebias is not None:
+            xs = self._act(xs + prebias, pre_act)
+        v = xs.double() @ w.double().t()
+        if b is not None:
+            v = v + b.double()
+        if addend is not None:
+            v = v + torch.as_strided(addend, (M, n_out), (ld_add, 1)).double()
+        torch.as_strided(y, (M, n_out), (ldy, 1)).copy_(self._act(v, act).float())
+
+    def gate_mul(self, x, table, idx, d_m, m_cap, c, out):
+        self.launches += 1
+        M = self._n(d_m, m_cap)
+        g = table[idx[:M].long()] if idx is not None else table[0:1]
+        out[:M] = x[:M] * g
+
+    def gather_rows(self, src, idx, n, c, out):
+        self.launches += 1
+        out[:n] = src[idx[:n].long()]
+
+    def guidance_dpm_step(self, eps_c, eps_u, inverse, x_t, x_init, noise, x0_state, n_points, cf, eps_out, x_next, coord_next, batch_col=None):
+        self.launches += 1
+        n = n_points
+        inv = inverse[:n].long() if inverse is not None else torch.arange(n)
+        ec, eu = eps_c[inv], eps_u[inv]
+        eps = eu + torch.tensor(cf.guidance_w, dtype=torch.float32) * (ec - eu)
+        if eps_out is not None:
+            eps_out[:n] = eps
+        f32 = lambda v: torch.tensor(v, dtype=torch.float32)
+        sample = x_t[:n] - x_init[:n]
+        x0 = (sample - f32(cf.sigma_s) * eps) / f32(cf.alpha_s)
+        prev = f32(cf.c_sample) * sample + f32(cf.c_x0) * x0
+        if cf.second_order:
+            prev = prev + 0.5 * f32(cf.c_x0) * (f32(cf.inv_r0) * (x0 - x0_state[:n]))
+        prev = prev + f32(cf.c_noise) * noise[:n].double()
+        x0_state[:n] = x0
+        xn = (x_init[:n] + prev).float()
+        x_next[:n] = xn
+        if coord_next is not None:
+            coord_next[:n, 1:] = ome.quantize(xn, cf.resolution, "div" if cf.div_mode == 0 else "mul")
+            coord_next[:n, 0] = 0 if batch_col is None else batch_col[:n]
+
+    def farthest_point_sample(self, pts, n, n_samples, out_idx, dist):
+        from oracle.pipeline import farthest_point_sample
+        self.launches += 1
+        p = pts[:n].numpy()
+        sel = np.empty(n_samples, np.int64)
+        d = np.full(n, np.inf)
+        cur = 0
+        for i in range(n_samples):
+            sel[i] = cur
+            d = np.minimum(d, ((p - p[cur]) ** 2).sum(1))
+            cur = int(np.argmax(d))
+        out_idx[:n_samples] = torch.from_numpy(sel.astype(np.int32))
+
+
+def install(monkeypatch):
+    """route the product's handle lookup to the CPU fake (host-logic tests only)"""
+    from lidiff_b200 import _lib, me
+    h = FakeHandle()
+    monkeypatch.setattr(_lib, "get_handle", lambda device=None: h)
+    monkeypatch.setattr(me, "_require_cuda", lambda t, what: None)
+    return h

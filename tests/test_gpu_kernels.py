@@ -1,0 +1,257 @@
+"""GPU parity tests, kernel by kernel: the CUDA library (through its C ABI) against the CPU oracle on
+identical seeded inputs.  Integer / index results bit-exact, floating point within the tolerance
+stated at each assert (north star: 1e-3 relative fp32)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import me_cpu as ome
+from oracle.dpm import DPMSolverSDE2M
+from oracle.pipeline import farthest_point_sample as fps_oracle
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def H():
+    from lidiff_b200 import _lib
+    return _lib.get_handle(DEV)
+
+
+def rel_err(a, b):
+    """per-element |a-b| / (|b| + rms(b)) as in SURVEY.md 8c-iii"""
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return ((a - b).abs() / (b.abs() + b.pow(2).mean().sqrt() + 1e-30)).max().item()
+
+
+def random_field(n, spread, seed, batch=1):
+    g = torch.Generator().manual_seed(seed)
+    pts = torch.randn(n, 3, generator=g) * spread
+    b = torch.sort(torch.randint(0, batch, (n, 1), generator=g).float(), dim=0).values
+    coords = torch.cat([b, torch.round(pts / 0.05)], 1)
+    return pts, coords
+
+
+# ---------------------------------------------------------------------------------------------------------
+def test_torch_cuda_scalar_division_is_reciprocal_multiply():
+    """pins which quantisation form the reference's own CUDA path computes"""
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2_000_000, generator=g) * 30
+    ref_gpu = torch.round(x.to(DEV) / 0.05).cpu()
+    mul = ome.quantize(x, 0.05, "mul")
+    div = ome.quantize(x, 0.05, "div")
+    n_mul, n_div = int((ref_gpu != mul).sum()), int((ref_gpu != div).sum())
+    print(f"torch CUDA round(x/0.05): differs from x*20f in {n_mul}, from true division in {n_div} of {x.numel()}")
+    assert n_mul == 0, "engine div_mode=1 would not match torch's CUDA lowering"
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_quantize_bit_exact(mode):
+    g = torch.Generator().manual_seed(1)
+    x = torch.cat([torch.randn(500_000, generator=g) * 30, torch.tensor([0.025, 0.075, 0.125, -0.025, -0.075, 0.0])])
+    out = torch.empty_like(x, device=DEV)
+    H().quantize(x.to(DEV), 0.05, mode, out)
+    assert torch.equal(out.cpu(), ome.quantize(x, 0.05, "div" if mode == 0 else "mul"))
+
+
+@pytest.mark.parametrize("n,spread,batch", [(50_000, 2.0, 1), (20_000, 0.2, 3), (7, 1.0, 1), (4096, 0.0, 1)])
+def test_voxelise_and_levels_bit_exact(n, spread, batch):
+    from lidiff_b200 import me
+    pts, coords = random_field(n, spread, n, batch)
+    of = ome.TensorField(pts, coords)
+    os_ = of.sparse()
+    f = me.TensorField(pts.to(DEV), coords.to(DEV))
+    s = f.sparse()
+    assert torch.equal(s.C.cpu(), os_.C), "level-0 rows / order"
+    assert torch.equal(f.inverse_mapping.cpu(), torch.from_numpy(os_.geom.inverse)), "inverse map"
+    assert rel_err(s.F, os_.F) < 1e-5
+    cm = s.coordinate_manager
+    for ts in (2, 4, 8, 16):
+        assert torch.equal(cm.level(ts).C.cpu(), torch.from_numpy(os_.geom.stride_level(ts))), f"stride {ts} rows"
+        assert torch.equal(cm.level(ts).parent_inverse[:cm.level(ts // 2).n].long().cpu(),
+                           torch.from_numpy(os_.geom.fine2coarse[ts])), f"fine->coarse {ts}"
+
+
+def _pairs_from_nbr(nbr):
+    nbr = nbr.cpu().numpy()
+    out = []
+    for k in range(nbr.shape[0]):
+        o = np.nonzero(nbr[k] >= 0)[0]
+        out.append(set(zip(nbr[k][o].tolist(), o.tolist())))
+    return out
+
+
+@pytest.mark.parametrize("spread", [1.0, 0.1])
+def test_kernel_maps_equal_oracle_pair_sets(spread):
+    from lidiff_b200 import me
+    pts, coords = random_field(30_000, spread, 5)
+    og = ome.TensorField(pts, coords).sparse().geom
+    cm = me.TensorField(pts.to(DEV), coords.to(DEV)).sparse().coordinate_manager
+    for ts in (1, 2, 4):
+        for (ks, stride, tr) in ((3, 1, False), (2, 2, False)):
+            got = _pairs_from_nbr(cm.kernel_map(ts, ks, stride, tr))
+            ref = [set(zip(i.tolist(), o.tolist())) for (i, o) in og.kernel_map(ts, ks, stride, tr)]
+            assert got == ref, (ts, ks, stride)
+        got = _pairs_from_nbr(cm.kernel_map(ts * 2, 2, 2, True))
+        ref = [set(zip(i.tolist(), o.tolist())) for (i, o) in og.kernel_map(ts * 2, 2, 2, True)]
+        assert got == ref, (ts, "transposed")
+
+
+CONV_CASES = [  # cin, cout, ks, stride, transposed
+    (3, 32, 3, 1, False), (32, 32, 3, 1, False), (32, 64, 2, 2, False), (64, 48, 2, 2, True),
+    (96, 96, 3, 1, False), (128, 256, 1, 1, False), (20, 7, 3, 1, False),
+]
+
+
+@pytest.mark.parametrize("cin,cout,ks,stride,tr", CONV_CASES)
+@pytest.mark.parametrize("algo", [1])
+def test_sparse_conv_matches_oracle(cin, cout, ks, stride, tr, algo):
+    from lidiff_b200 import me
+    pts, coords = random_field(12_000, 0.3, 11)
+    g = torch.Generator().manual_seed(cin * 131 + cout)
+    of = ome.TensorField(pts, coords).sparse()
+    f = me.TensorField(pts.to(DEV), coords.to(DEV)).sparse()
+    ts_in = 2 if tr else 1
+    Min = of.geom.stride_level(ts_in).shape[0]
+    Fin = torch.randn(Min, cin, generator=g)
+    if ks == 1:
+        layer = me.MinkowskiConvolution(cin, cout, kernel_size=1, stride=1, dimension=3)
+    elif tr:
+        layer = me.MinkowskiConvolutionTranspose(cin, cout, kernel_size=ks, stride=stride, dimension=3)
+    else:
+        layer = me.MinkowskiConvolution(cin, cout, kernel_size=ks, stride=stride, dimension=3)
+    layer.algo = algo
+    W = torch.randn(layer.kernel.shape, generator=g) / np.sqrt(cin * ks ** 3)
+    layer.kernel.data = W.clone()
+    layer = layer.to(DEV)
+    xin = me.SparseTensor(Fin.to(DEV), coordinate_manager=f.coordinate_manager, tensor_stride=ts_in)
+    y = layer(xin)
+    oy = ome.conv(ome.SparseTensor(Fin.double(), of.geom, ts_in), W.double(), ks, stride, tr)
+    assert y.F.shape == oy.F.shape
+    assert rel_err(y.F, oy.F) < 1e-4, "fp32 conv vs fp64 oracle"
+
+
+def test_sparse_conv_fused_epilogue_two_passes_and_concat():
+    """BN affine + residual + ReLU + gate + two K segments + two guidance passes in one launch"""
+    from lidiff_b200 import _lib, me
+    from lidiff_b200._lib import ConvDesc, ConvIO
+    pts, coords = random_field(9_000, 0.2, 21)
+    g = torch.Generator().manual_seed(5)
+    of = ome.TensorField(pts, coords).sparse()
+    f = me.TensorField(pts.to(DEV), coords.to(DEV)).sparse()
+    cm = f.coordinate_manager
+    M = of.F.shape[0]
+    c1, c2, cout = 32, 16, 24
+    A = torch.randn(2, M, c1, generator=g)
+    B = torch.randn(1, M, c2, generator=g)
+    R = torch.randn(2, M, cout, generator=g)
+    W = torch.randn(27, c1 + c2, cout, generator=g) * 0.05
+    scale, shift = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g)
+    table = torch.randn(50, cout, generator=g)
+    gidx = torch.randint(0, 50, (M,), generator=g, dtype=torch.int32)
+    dev = lambda t: t.to(DEV).contiguous()
+    dA, dB, dR, dW, dS, dT, dTab, dG = map(dev, (A, B, R, W, scale, shift, table, gidx))
+    out = torch.zeros(2, M, cout, device=DEV)
+    outg = torch.zeros(2, M, cout, device=DEV)
+    nbr = cm.kernel_map(1, 3, 1, False)
+    d_m = torch.tensor([M], dtype=torch.int32, device=DEV)
+    d = ConvDesc()
+    d.c1, d.c2, d.cout, d.kvol = c1, c2, cout, 27
+    d.weight, d.scale, d.shift, d.relu = dW.data_ptr(), dS.data_ptr(), dT.data_ptr(), 1
+    d.nbr, d.nbr_stride, d.d_mout, d.mout_cap, d.npass = nbr.data_ptr(), nbr.stride(0), d_m.data_ptr(), M, 2
+    d.io[0] = ConvIO(dA[0].data_ptr(), dB[0].data_ptr(), dR[0].data_ptr(), out[0].data_ptr(), dTab.data_ptr(), dG.data_ptr(), outg[0].data_ptr())
+    d.io[1] = ConvIO(dA[1].data_ptr(), dB[0].data_ptr(), dR[1].data_ptr(), out[1].data_ptr(), dTab.data_ptr(), None, outg[1].data_ptr())
+    H().spconv(d, _lib.ALGO_FFMA)
+    for p in range(2):
+        xin = ome.SparseTensor(torch.cat([A[p], B[0]], 1).double(), of.geom, 1)
+        y = ome.conv(xin, W.double(), 3).F * scale.double() + shift.double() + R[p].double()
+        y = torch.relu(y)
+        assert rel_err(out[p], y) < 1e-4
+        gate = table[gidx.long()] if p == 0 else table[0:1]
+        assert rel_err(outg[p], y * gate.double()) < 1e-4
+
+
+def test_nn_match_bit_exact_with_ties():
+    g = torch.Generator().manual_seed(3)
+    q = torch.cat([torch.zeros(40_000, 1), torch.randint(-60, 60, (40_000, 3), generator=g).float() * 2], 1)
+    k = torch.cat([torch.zeros(3_000, 1), torch.randint(-8, 8, (3_000, 3), generator=g).float() * 16], 1)   # many duplicates/ties
+    ref = ome.match_part_to_full(q.int(), k.int())
+    idx = torch.empty(q.shape[0], dtype=torch.int32, device=DEV)
+    H().nn_match(q.int().to(DEV), None, q.shape[0], k.int().to(DEV), None, k.shape[0], 0, idx)
+    assert torch.equal(idx.long().cpu(), ref)
+    # the reference's own expression through the keops surface, two batches
+    from lidiff_b200.keops import LazyTensor
+    q2, k2 = q.clone(), k.clone()
+    q2[20_000:, 0], k2[1_500:, 0] = 1, 1
+    ref2 = ome.match_part_to_full(q2.int(), k2.int())
+    fc, pc = q2.to(DEV), k2.to(DEV)
+    s = fc.max() * 2.0
+    fc[:, 0] *= s
+    pc[:, 0] *= s
+    got = ((LazyTensor(fc[:, None, :]) - LazyTensor(pc[None, :, :])) ** 2).sum(-1).argKmin(1, dim=1)[:, 0]
+    assert torch.equal(got.cpu(), ref2)
+
+
+@pytest.mark.parametrize("m,n_in,n_out,act", [(5000, 256, 256, 1), (777, 96, 20, 1), (777, 20, 3, 0), (1, 512, 96, 0), (300, 20, 18, 2)])
+def test_linear_matches_torch(m, n_in, n_out, act):
+    g = torch.Generator().manual_seed(m + n_out)
+    x, w, b = torch.randn(m, n_in, generator=g), torch.randn(n_out, n_in, generator=g) * 0.1, torch.randn(n_out, generator=g)
+    y = torch.empty(m, n_out, device=DEV)
+    H().linear(x.to(DEV), n_in, w.to(DEV), b.to(DEV), None, 0, m, None, n_in, n_out, act, y, n_out)
+    ref = torch.nn.functional.linear(x.double(), w.double(), b.double())
+    ref = torch.nn.functional.leaky_relu(ref, 0.1) if act == 1 else (torch.tanh(ref) if act == 2 else ref)
+    assert rel_err(y, ref) < 1e-5
+    # hoisted-gate form: W2 . leaky(x + prebias) + b
+    pre = torch.randn(n_in, generator=g)
+    H().linear(x.to(DEV), n_in, w.to(DEV), b.to(DEV), None, 0, m, None, n_in, n_out, 0, y, n_out, pre.to(DEV), 1)
+    ref = torch.nn.functional.linear(torch.nn.functional.leaky_relu(x.double() + pre.double(), 0.1), w.double(), b.double())
+    assert rel_err(y, ref) < 1e-5
+
+
+@pytest.mark.parametrize("second", [0, 1])
+def test_guidance_dpm_step_bit_exact(second):
+    """given identical eps the fused tail reproduces torch's fp64 evaluation bit for bit (x_next AND coords)"""
+    from lidiff_b200._lib import DpmCoef
+    from lidiff_b200.scheduler import DPMSolverMultistepScheduler as S
+    n, m = 60_000, 20_000
+    g = torch.Generator().manual_seed(9 + second)
+    inv = torch.randint(0, m, (n,), generator=g)
+    e_c, e_u = torch.randn(m, 3, generator=g), torch.randn(m, 3, generator=g)
+    x_init = torch.randn(1, n, 3, generator=g, dtype=torch.float64) * 20
+    x_t = (x_init + torch.randn(1, n, 3, generator=g, dtype=torch.float64)).float()
+    noise = torch.randn(1, n, 3, generator=g)
+    x0_prev = torch.randn(1, n, 3, generator=g, dtype=torch.float64)
+    o = DPMSolverSDE2M()
+    o.set_timesteps(50)
+    i = 7 if second else 0
+    if second:
+        o.model_outputs = [None, x0_prev.clone()]
+        o.lower_order_nums = 1
+    eps = (e_u + 6.0 * (e_c - e_u))[inv][None]
+    sample = x_t - x_init
+    x_next_ref = (x_init + o.step(eps, o.timesteps[i], sample, noise[0][None])).float()
+    coord_ref = ome.quantize(x_next_ref, 0.05, "mul")
+    s = S(1000, 3.5e-5, 0.007, "linear", algorithm_type="sde-dpmsolver++", solver_order=2)
+    s.set_timesteps(50)
+    c = s.coefficients(i)
+    cf = DpmCoef(c["c_sample"], c["c_x0"], c["c_noise"], c["sigma_s"], c["alpha_s"], c.get("inv_r0", 0.0) if second else 0.0,
+                 6.0, 0.05, second, 1, 1)
+    d = lambda t: t.to(DEV).contiguous()
+    x0s = d(x0_prev[0])
+    x_next = torch.empty(n, 3, device=DEV)
+    coord = torch.empty(n, 4, device=DEV)
+    eps_out = torch.empty(n, 3, device=DEV)
+    H().guidance_dpm_step(d(e_c), d(e_u), d(inv.int()), d(x_t[0]), d(x_init[0]), d(noise[0]), x0s, n, cf, eps_out, x_next, coord)
+    assert torch.equal(eps_out.cpu(), eps[0]), "guidance"
+    assert torch.equal(x_next.cpu(), x_next_ref[0]), "x_next"
+    assert torch.equal(coord[:, 1:].cpu(), coord_ref[0]) and (coord[:, 0] == 0).all(), "next coordinates"
+    assert torch.equal(x0s.cpu(), o.model_outputs[-1][0]), "multistep state"
+
+
+def test_farthest_point_sampling_bit_exact():
+    from lidiff_b200.preprocess import farthest_point_sample
+    g = np.random.default_rng(0)
+    p = g.normal(size=(20_000, 3)) * 10
+    ref = fps_oracle(p, 500)
+    got = farthest_point_sample(torch.tensor(p, device=DEV), 500).cpu().numpy()
+    assert np.array_equal(got, ref)
