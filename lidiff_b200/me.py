@@ -240,6 +240,18 @@ class _ConvBase(nn.Module):
             stdv = 1.0 / math.sqrt(n)
             self.kernel.data.uniform_(-stdv, stdv)
 
+    def _packed_weight(self, h):
+        """tensor-core image of the kernel (bf16 hi/lo, UMMA layout), cached until the parameter changes"""
+        if self.training or getattr(self, "algo", _lib.ALGO_AUTO) == _lib.ALGO_FFMA:
+            return None
+        W = self.kernel
+        key = (W.data_ptr(), W._version)
+        if getattr(self, "_pack_key", None) != key:
+            W3 = W.detach() if W.dim() == 3 else W.detach()[None]
+            self._pack = h.pack_weights(W3.contiguous())
+            self._pack_key = key
+        return self._pack.data_ptr() if self._pack is not None else None
+
     def forward(self, x: SparseTensor) -> SparseTensor:
         if not isinstance(x, SparseTensor):
             raise RuntimeError(f"{type(self).__name__} expects a SparseTensor")
@@ -262,6 +274,7 @@ class _ConvBase(nn.Module):
         d = ConvDesc()
         d.c1, d.c2, d.cout, d.kvol = self.in_channels, 0, self.out_channels, self.kernel_volume
         d.weight = W.data_ptr()
+        d.weight_packed = self._packed_weight(cm.h)
         d.relu = 0
         d.nbr = nbr.data_ptr() if nbr is not None else None
         d.nbr_stride = lout.n

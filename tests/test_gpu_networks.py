@@ -19,16 +19,17 @@ def rel_err(a, b):
     return ((a - b).abs() / (b.abs() + b.pow(2).mean().sqrt() + 1e-30)).max().item()
 
 
-@pytest.fixture(scope="module")
-def setup(small_scan, calibrated_sds):
+@pytest.fixture(scope="module", params=[1, 0], ids=["ffma", "auto_tc"])
+def setup(request, small_scan, calibrated_sds):
+    algo = request.param
     from lidiff_b200.pipeline import DiffCompletion
     g = torch.Generator().manual_seed(1234)
     start = torch.randn(small_scan.shape, generator=g)
     noise = torch.randn((3,) + tuple(small_scan.shape), generator=g)
     oracle = DiffCompletionOracle(calibrated_sds["enc"], calibrated_sds["diff"], calibrated_sds["refine"], denoising_steps=50)
     hp = {"data": {"num_points": small_scan.shape[1]}}
-    pipe = DiffCompletion(state_dicts=calibrated_sds, denoising_steps=50, cond_weight=6.0, device=DEV, hparams=hp, engine=False, conv_algo=1)
-    return dict(scan=small_scan, start=start, noise=noise, oracle=oracle, pipe=pipe, sds=calibrated_sds)
+    pipe = DiffCompletion(state_dicts=calibrated_sds, denoising_steps=50, cond_weight=6.0, device=DEV, hparams=hp, engine=False, conv_algo=algo)
+    return dict(algo=algo, scan=small_scan, start=start, noise=noise, oracle=oracle, pipe=pipe, sds=calibrated_sds)
 
 
 def test_operator_path_networks_match_oracle(setup):
@@ -71,7 +72,7 @@ def test_engine_step_matches_oracle(setup):
     o.completion_loop(scan, ot, oc, ou, setup["noise"], n_steps=3)
     hist = o.trace["hist"]
 
-    eng = DenoiseEngine(sds["enc"], sds["diff"], device=DEV, n_points=N, denoising_steps=50, conv_algo=1)
+    eng = DenoiseEngine(sds["enc"], sds["diff"], device=DEV, n_points=N, denoising_steps=50, conv_algo=setup["algo"])
     x_init = scan.reshape(-1, 3).to(DEV)
     eng.set_condition(x_init)
     xa = x_feats.reshape(-1, 3).float().to(DEV).contiguous()
@@ -127,7 +128,7 @@ def test_pipeline_paths_agree_and_complete_scan_runs(setup):
     g = torch.Generator().manual_seed(7)
     start = torch.randn(scan.shape, generator=g)
     noise = torch.randn((4, 1) + tuple(scan.shape[1:]), generator=g).to(DEV)
-    pipe = DiffCompletion(state_dicts=sds, denoising_steps=4, cond_weight=6.0, device=DEV, hparams=hp, engine=True, conv_algo=1)
+    pipe = DiffCompletion(state_dicts=sds, denoising_steps=4, cond_weight=6.0, device=DEV, hparams=hp, engine=True, conv_algo=setup["algo"])
     dscan = scan.to(DEV)
     x_feats = dscan + start.to(DEV)
     a = pipe.completion_loop(dscan, pipe.points_to_tensor(x_feats), pipe.points_to_tensor(dscan),
