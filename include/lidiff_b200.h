@@ -86,10 +86,11 @@ int lb2_voxel_mean(void* h, void* stream, const float* feats, const int32_t* inv
 /* Kernel map (ME kernel maps for MinkowskiConvolution / ConvolutionTranspose; minkunet.py:17-24,36-42).
  * Output-stationary neighbour table: nbr[k * nbr_stride + o] = input row at coords(o) + offset_k, or -1.
  *   ks=3: offset_d = (k_d - 1) * step      ks=2: offset_d = k_d * step   (step < 0: transposed map)
- *   k = kx + ks*ky + ks*ks*kz. */
+ *   k = kx + ks*ky + ks*ks*kz.
+ * pair_count (device uint64, optional): += number of (in,out) pairs found (roofline accounting). */
 int lb2_kernel_map(void* h, void* stream, lb2_grid grid_in, const int32_t* out_coords,
                    const int32_t* d_nout, int32_t nout_cap, int32_t ks, int32_t step,
-                   int32_t* nbr, int64_t nbr_stride);
+                   int32_t* nbr, int64_t nbr_stride, uint64_t* pair_count);
 
 /* ---- sparse convolution  — replaces ME.MinkowskiConvolution(+Transpose) forward, with the
  * MinkowskiBatchNorm(eval)/MinkowskiReLU/residual-add/ME.cat/gate-multiply that follow it in
@@ -125,10 +126,11 @@ typedef struct {
 
 #define LB2_ALGO_AUTO  0
 #define LB2_ALGO_FFMA  1    /* fp32 CUDA-core implicit GEMM */
-#define LB2_ALGO_TC    2    /* tcgen05 BF16x3 implicit GEMM (needs weight_packed) */
+#define LB2_ALGO_TC    2    /* tcgen05 FP16x3 split-precision implicit GEMM (needs weight_packed) */
 int lb2_spconv_forward(void* h, void* stream, const lb2_conv_desc* d, int algo);
 
-/* BF16 hi/lo split + UMMA shared-memory image of a (kvol, cin, cout) fp32 weight for LB2_ALGO_TC. */
+/* FP16 hi/lo split (power-of-two pre-scaled) + UMMA shared-memory image of a (kvol, cin, cout) fp32 weight
+ * for LB2_ALGO_TC. */
 size_t lb2_packed_weight_bytes(int32_t kvol, int32_t cin, int32_t cout);
 int lb2_pack_weights(void* h, void* stream, const float* weight, int32_t kvol, int32_t cin, int32_t cout,
                      void* packed);

@@ -84,7 +84,7 @@ class Lib:
         d.lb2_quantize.argtypes = [vp, vp, vp, i64, f32, C.c_int, vp]
         d.lb2_unique_build.argtypes = [vp, vp, vp, vp, vp, i32, i32, Grid, vp, vp, vp, vp]
         d.lb2_voxel_mean.argtypes = [vp, vp, vp, vp, i32, i32, vp, i32, vp, vp]
-        d.lb2_kernel_map.argtypes = [vp, vp, Grid, vp, vp, i32, i32, i32, vp, i64]
+        d.lb2_kernel_map.argtypes = [vp, vp, Grid, vp, vp, i32, i32, i32, vp, i64, vp]
         d.lb2_spconv_forward.argtypes = [vp, vp, C.POINTER(ConvDesc), C.c_int]
         d.lb2_pack_weights.argtypes = [vp, vp, vp, i32, i32, i32, vp]
         d.lb2_nn_match.argtypes = [vp, vp, vp, vp, i32, vp, vp, i32, i32, vp]
@@ -161,9 +161,9 @@ class Handle:
         self._check(self.dll.lb2_voxel_mean(self.hp, self._stream(), _ptr(feats), _ptr(inverse), int(n), int(c), _ptr(d_m), int(m_cap),
                                             _ptr(out), _ptr(counts)), "lb2_voxel_mean")
 
-    def kernel_map(self, grid_in, out_coords, d_nout, nout_cap, ks, step, nbr, nbr_stride):
+    def kernel_map(self, grid_in, out_coords, d_nout, nout_cap, ks, step, nbr, nbr_stride, pair_count=None):
         self._check(self.dll.lb2_kernel_map(self.hp, self._stream(), self._grid(grid_in), _ptr(out_coords), _ptr(d_nout), int(nout_cap),
-                                            int(ks), int(step), _ptr(nbr), int(nbr_stride)), "lb2_kernel_map")
+                                            int(ks), int(step), _ptr(nbr), int(nbr_stride), _ptr(pair_count)), "lb2_kernel_map")
 
     # -- conv ----------------------------------------------------------------------------------------
     def spconv(self, desc: ConvDesc, algo: int = ALGO_AUTO):

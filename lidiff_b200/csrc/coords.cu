@@ -303,10 +303,10 @@ extern "C" int lb2_voxel_mean(void* handle, void* stream, const float* feats, co
 // ---------------------------------------------------------------------------------------------------
 __global__ void k_kernel_map(const unsigned long long* __restrict__ keys, const int* __restrict__ rows, unsigned mask,
                              const int4* __restrict__ out_coords, const int* __restrict__ d_n, int n_cap,
-                             int ks, int step, int* __restrict__ nbr, long long nbr_stride) {
+                             int ks, int step, int* __restrict__ nbr, long long nbr_stride,
+                             unsigned long long* __restrict__ pair_count) {
     int o = blockIdx.x * blockDim.x + threadIdx.x;
     int k = blockIdx.y;
-    if (o >= n_cap) return;
     int n = d_n ? min(*d_n, n_cap) : n_cap;
     int res = -1;
     if (o < n) {
@@ -317,12 +317,16 @@ __global__ void k_kernel_map(const unsigned long long* __restrict__ keys, const 
         unsigned long long key;
         if (lb2_pack_key(c.x, x, y, z, key)) res = lb2_grid_lookup(keys, rows, mask, key);
     }
-    nbr[(long long)k * nbr_stride + o] = res;
+    if (o < n_cap) nbr[(long long)k * nbr_stride + o] = res;
+    if (pair_count) {        // algorithmic work counter for the roofline: one atomic per warp
+        unsigned found = __ballot_sync(0xffffffffu, res >= 0);
+        if ((threadIdx.x & 31) == 0 && found) atomicAdd(pair_count, (unsigned long long)__popc(found));
+    }
 }
 
 extern "C" int lb2_kernel_map(void* handle, void* stream, lb2_grid grid_in, const int32_t* out_coords,
                               const int32_t* d_nout, int32_t nout_cap, int32_t ks, int32_t step,
-                              int32_t* nbr, int64_t nbr_stride) {
+                              int32_t* nbr, int64_t nbr_stride, uint64_t* pair_count) {
     Lb2Handle* h = (Lb2Handle*)handle;
     LB2_REQUIRE(h, h && grid_in.keys && grid_in.vals && out_coords && nbr, "kernel_map null");
     LB2_REQUIRE(h, ks >= 1 && ks <= 3 && step != 0 && nout_cap > 0 && nbr_stride >= nout_cap, "kernel_map args");
@@ -330,7 +334,8 @@ extern "C" int lb2_kernel_map(void* handle, void* stream, lb2_grid grid_in, cons
     dim3 grid(cdiv(nout_cap, 256), kvol);
     k_kernel_map<<<grid, 256, 0, (cudaStream_t)stream>>>((const unsigned long long*)grid_in.keys,
                                                         grid_in.vals + grid_in.cap_table, (unsigned)grid_in.cap_table - 1u,
-                                                        (const int4*)out_coords, d_nout, nout_cap, ks, step, nbr, nbr_stride);
+                                                        (const int4*)out_coords, d_nout, nout_cap, ks, step, nbr, nbr_stride,
+                                                        (unsigned long long*)pair_count);
     LB2_POST_LAUNCH(h, "k_kernel_map");
     return LB2_OK;
 }

@@ -103,6 +103,10 @@ class Geometry:
         self.nbr_up = [torch.empty((8, n_cap), **i32) for _ in range(levels - 1)] + [None] if with_up else None
         self.scratch = h.unique_scratch(n_cap)
         self.counts = torch.empty(n_cap, **i32)
+        # (in,out) pair counters filled by lb2_kernel_map: [0:5] 3^3 per level, [5:9] stride-2 (out level 1..4),
+        # [9:13] transposed (out level 0..3); [13:18] row counts per level (copied from d_n)
+        self.pairs = torch.zeros(18, dtype=torch.int64, device=dev)
+        self.map_id = {}
 
     def build(self, coords_f: torch.Tensor, n_points: int):
         """coords_f (n_points,4) fp32 integer-valued [b,x,y,z] -> all levels and maps (async)."""
@@ -110,13 +114,17 @@ class Geometry:
         h.unique_build(coords_f, None, None, n_points, 0, self.grid[0], self.C[0], self.inv[0], self.d_n[0], self.scratch)
         for l in range(1, self.levels):
             h.unique_build(None, self.C[l - 1], self.d_n[l - 1], N, 1 << l, self.grid[l], self.C[l], self.inv[l], self.d_n[l], self.scratch)
+        self.pairs.zero_()
         for l in range(self.levels):
-            h.kernel_map(self.grid[l], self.C[l], self.d_n[l], N, 3, 1 << l, self.nbr3[l], N)
+            h.kernel_map(self.grid[l], self.C[l], self.d_n[l], N, 3, 1 << l, self.nbr3[l], N, self.pairs[l:l + 1])
+            self.map_id[self.nbr3[l].data_ptr()] = l
         for l in range(1, self.levels):
-            h.kernel_map(self.grid[l - 1], self.C[l], self.d_n[l], N, 2, 1 << (l - 1), self.nbr_dn[l], N)
+            h.kernel_map(self.grid[l - 1], self.C[l], self.d_n[l], N, 2, 1 << (l - 1), self.nbr_dn[l], N, self.pairs[4 + l:5 + l])
+            self.map_id[self.nbr_dn[l].data_ptr()] = 4 + l
         if self.nbr_up is not None:
             for l in range(self.levels - 1):
-                h.kernel_map(self.grid[l + 1], self.C[l], self.d_n[l], N, 2, -(1 << l), self.nbr_up[l], N)
+                h.kernel_map(self.grid[l + 1], self.C[l], self.d_n[l], N, 2, -(1 << l), self.nbr_up[l], N, self.pairs[9 + l:10 + l])
+                self.map_id[self.nbr_up[l].data_ptr()] = 9 + l
 
     def voxel_mean(self, feats, n_points, out):
         self.h.voxel_mean(feats, self.inv[0], n_points, feats.shape[1], self.d_n[0], self.n_cap, out, self.counts)
@@ -158,8 +166,12 @@ class DenoiseEngine:
         self.geom = Geometry(h, self.N, with_up=True)
         self.geom_cond = None
         self.part_cap = 0
-        self._zero_i = torch.zeros(1, dtype=torch.int32, device=dev)
-        self._one_i = torch.ones(1, dtype=torch.int32, device=dev)
+        # optional instrumentation (bench.py): per-conv CUDA events + layer inventory + pair-count history
+        self.conv_events = None          # list of (start, end, layer_index) when enabled
+        self.layer_log = None            # list of dict(map, lvl, cin, cout, kvol, npass, tc) recorded during one step
+        self.pair_hist = None            # (steps, 18) int64 device tensor when enabled
+        self._hist_row = 0
+        self._conv_counter = 0
         self._prepare_time_tables()
         self._prepare_uncond()
 
@@ -251,7 +263,19 @@ class DenoiseEngine:
                 gt = gate[p][0].data_ptr()
                 gi = gate[p][1].data_ptr() if gate[p][1] is not None else None
             d.io[p] = ConvIO(sel(in1, p), sel(in2, p), sel(residual, p), sel(out, p), gt, gi, sel(out_gated, p))
-        self.h.spconv(d, self.conv_algo)
+        if self.layer_log is not None:
+            self.layer_log.append(dict(map=(nbr.data_ptr() if nbr is not None else None), d_m=d_m.data_ptr() if d_m is not None else None,
+                                       cin=lay.cin, cout=lay.cout, kvol=lay.kvol, npass=npass,
+                                       tc=bool(lay.Wp is not None and self.conv_algo != _lib.ALGO_FFMA)))
+        if self.conv_events is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            self.h.spconv(d, self.conv_algo)
+            e1.record()
+            self.conv_events.append((e0, e1, self._conv_counter))
+            self._conv_counter += 1
+        else:
+            self.h.spconv(d, self.conv_algo)
 
     def _res(self, L, p, geom, lvl, in1, in2, npass, tag, gate=None, want_plain=True):
         cap = geom.n_cap
@@ -352,7 +376,12 @@ class DenoiseEngine:
     # ---- one denoising step ----------------------------------------------------------------------------------
     def step(self, i: int, x_t, x_next, coords, coords_next, x_init, noise_i, x0_state, eps_out=None):
         h, N, g = self.h, self.N, self.geom
+        self._conv_counter = 0
         g.build(coords, N)
+        if self.pair_hist is not None:
+            g.pairs[13:18] = torch.cat(g.d_n).long()
+            self.pair_hist[self._hist_row % self.pair_hist.shape[0]] = g.pairs
+            self._hist_row += 1
         F0 = self.buf("F0", (1, N, 3))
         g.voxel_mean(x_t, N, F0[0])
         nn = []
@@ -376,31 +405,46 @@ class DenoiseEngine:
         h.guidance_dpm_step(eps[0], eps[1], g.inv[0], x_t, x_init, noise_i, x0_state, N, cf, eps_out, x_next, coords_next)
 
     # ---- the loop (completion_loop, pipeline:155-169) -----------------------------------------------------------
-    def run(self, x_init: torch.Tensor, x_feats: torch.Tensor, step_noise=None, n_steps=None, return_device=False):
-        """x_init (1,N,3) fp64 conditioning scan, x_feats (1,N,3) noisy start.  Returns final x_t.F (N,3)."""
+    def start(self, x_init: torch.Tensor, x_feats: torch.Tensor):
+        """condition on the scan and load the noisy start; returns the loop state dict"""
         dev, N = self.device, self.N
         x_init = x_init.reshape(-1, 3).to(device=dev, dtype=torch.float64).contiguous()
         assert x_init.shape[0] == N, f"engine built for {N} points, got {x_init.shape[0]}"
         self.set_condition(x_init)
+        st = dict(x_init=x_init, xa=self.buf("x_a", (N, 3)), xb=self.buf("x_b", (N, 3)), ca=self.buf("c_a", (N, 4)),
+                  cb=self.buf("c_b", (N, 4)), x0s=self.buf("x0_state", (N, 3), torch.float64), i=0)
+        st["xa"].copy_(x_feats.reshape(-1, 3).to(device=dev, dtype=torch.float32))
+        st["ca"][:, 0] = 0
+        self.h.quantize(st["xa"], self.resolution, self.div_mode, self.buf("q0", (N, 3)))
+        st["ca"][:, 1:] = self._bufs["q0"]
+        return st
+
+    def advance(self, st, noise_i, host_noise=None, host_out=None):
+        """one denoising step on the loop state.  host_noise (pinned (N,3) fp32): copied H2D inside the step;
+        host_out (pinned (N,3) fp32): the step's x_t is copied D2H (what a caller that visualises / logs every
+        step pays)."""
+        if host_noise is not None:
+            noise_i = self.buf("noise_in", (self.N, 3))
+            noise_i.copy_(host_noise, non_blocking=True)
+        self.step(st["i"] % self.T, st["xa"], st["xb"], st["ca"], st["cb"], st["x_init"], noise_i, st["x0s"])
+        st["xa"], st["xb"], st["ca"], st["cb"] = st["xb"], st["xa"], st["cb"], st["ca"]
+        st["i"] += 1
+        if host_out is not None:
+            host_out.copy_(st["xa"], non_blocking=True)
+
+    def run(self, x_init: torch.Tensor, x_feats: torch.Tensor, step_noise=None, n_steps=None, return_device=False):
+        """x_init (1,N,3) fp64 conditioning scan, x_feats (1,N,3) noisy start.  Returns final x_t.F (N,3)."""
+        dev, N = self.device, self.N
+        st = self.start(x_init, x_feats)
         T = self.T if n_steps is None else n_steps
         if step_noise is None:
             step_noise = torch.randn((T, N, 3), device=dev)
         step_noise = step_noise.reshape(-1, N, 3).to(device=dev, dtype=torch.float32).contiguous()
-        xa = self.buf("x_a", (N, 3))
-        xb = self.buf("x_b", (N, 3))
-        ca = self.buf("c_a", (N, 4))
-        cb = self.buf("c_b", (N, 4))
-        x0s = self.buf("x0_state", (N, 3), torch.float64)
-        xa.copy_(x_feats.reshape(-1, 3).to(device=dev, dtype=torch.float32))
-        ca[:, 0] = 0
-        self.h.quantize(xa, self.resolution, self.div_mode, self.buf("q0", (N, 3)))
-        ca[:, 1:] = self._bufs["q0"]
         for i in range(T):
-            self.step(i, xa, xb, ca, cb, x_init, step_noise[i], x0s)
-            xa, xb, ca, cb = xb, xa, cb, ca
+            self.advance(st, step_noise[i])
         if return_device:
-            return xa
-        out = xa.cpu().numpy()
+            return st["xa"]
+        out = st["xa"].cpu().numpy()
         if self.h.read_status() & 1:
             raise RuntimeError("lidiff_b200: a coordinate left the supported key range during sampling")
         return out

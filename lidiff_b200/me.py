@@ -241,8 +241,8 @@ class _ConvBase(nn.Module):
             self.kernel.data.uniform_(-stdv, stdv)
 
     def _packed_weight(self, h):
-        """tensor-core image of the kernel (bf16 hi/lo, UMMA layout), cached until the parameter changes"""
-        if self.training or getattr(self, "algo", _lib.ALGO_AUTO) == _lib.ALGO_FFMA:
+        """tensor-core image of the kernel (fp16 hi/lo, UMMA layout), cached until the parameter changes"""
+        if getattr(self, "algo", _lib.ALGO_AUTO) == _lib.ALGO_FFMA:
             return None
         W = self.kernel
         key = (W.data_ptr(), W._version)

@@ -84,7 +84,7 @@ class FakeHandle:
         cnt = torch.bincount(inv, minlength=M).float()
         out[:M] = sums / cnt[:, None]
 
-    def kernel_map(self, grid_in, out_coords, d_nout, nout_cap, ks, step, nbr, nbr_stride):
+    def kernel_map(self, grid_in, out_coords, d_nout, nout_cap, ks, step, nbr, nbr_stride, pair_count=None):
         self.launches += 1
         n = self._n(d_nout, nout_cap)
         skeys, order = self.grids[grid_in[0].data_ptr()]
@@ -105,6 +105,8 @@ class FakeHandle:
             res = np.where(hit, order[pos], -1).astype(np.int32)
             nb[k, :n] = torch.from_numpy(res)
             nb[k, n:nout_cap] = -1
+            if pair_count is not None:
+                pair_count += int(hit.sum())
 
     # conv -----------------------------------------------------------------------------------------
     def packed_weight_bytes(self, kvol, cin, cout):
