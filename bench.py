@@ -36,6 +36,21 @@ METRIC = "denoising_steps_per_sec_180k_pts_T50"
 UNIT = "steps/s"
 
 
+def log(msg):
+    print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
+def usable_cpus() -> int:
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:                                    # cgroup v2 CPU quota of the container, if any
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = max(1, min(n, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return n
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -106,9 +121,12 @@ def build_pipeline(device, scan):
 # ---------------------------------------------------------------------------------------------------------------
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
+    from lidiff_b200.sharding import max_over_ranks
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
+    log("building inputs (synthetic scan, GPU farthest point sampling)")
     scan, start, g = build_inputs(device, seed=rank)
+    log("building pipeline (seeded weights, BN calibration)")
     pipe = build_pipeline(device, scan)
     eng = pipe.engine()
     h = eng.h
@@ -122,6 +140,7 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     # ---- warm-up --------------------------------------------------------------------------------------------
+    log(f"warm-up {W} steps")
     st = eng.start(scan, x_feats)
     for i in range(W):
         eng.advance(st, noise[i % K])
@@ -146,6 +165,7 @@ def run_ours(args, rank, world, local_rank):
         barrier()
     launches = h.launch_count() - l0
     ms = e0.elapsed_time(e1)
+    log(f"timed region: {K} steps in {ms:.1f} ms")
     conv_events, eng.conv_events = eng.conv_events, None
     pair_hist, eng.pair_hist = eng.pair_hist.cpu().numpy(), None
     if h.read_status() & 1:
@@ -165,11 +185,9 @@ def run_ours(args, rank, world, local_rank):
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
+    log(f"e2e region: {K} steps in {ms_e2e:.1f} ms")
 
-    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = t.tolist()
+    ms, ms_e2e = max_over_ranks(ms, device), max_over_ranks(ms_e2e, device)
     if rank != 0:
         return None
 
@@ -199,11 +217,11 @@ def run_ours(args, rank, world, local_rank):
                 "algorithmic_flops_per_launch": flops / n_launch, "avg_launch_ms": round(avg_ms, 4),
                 "conv_share_of_step": round(conv_ms / ms, 3), "tc_share_of_conv_time": round(tc_ms / max(conv_ms, 1e-9), 3),
                 "gather_scatter_model_GBps": round(bytes_gs / (conv_ms * 1e-3) / 1e9, 1), "hbm_peak_GBps": peaks["hbm_gbs"],
-                "note": "algorithmic FLOPs = 2*pairs*Cin*Cout per pass (SURVEY 8d); BF16x3 issues 3 MMAs per product, so the tensor ceiling for this figure is peak/3"}
+                "note": "algorithmic FLOPs = 2*pairs*Cin*Cout per pass (SURVEY 8d); the FP16x3 split issues 3 MMAs per product, so the tensor ceiling for this figure is peak/3"}
 
     out = {"metric": METRIC, "value": round(K * world / (ms * 1e-3), 3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
            "ms_per_step": round(ms / K, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": "bf16x3 tensor-core MMA with fp32 accumulate (fp32 CUDA cores for Cin=3), fp64 DPM update",
+           "dtype": "fp16x3 split tensor-core MMA, fp32 accumulate (fp32 CUDA cores for the Cin=3 stem), fp64 DPM update",
            "data": "synthetic",
            "config": {"workload": "BASELINE configs[1]: one synthetic KITTI-shape scan of 180000 points per GPU, T=50 schedule, guidance s=6.0",
                       "points": N_POINTS, "T": T_STEPS, "guidance_w": GUIDANCE_W, "resolution_m": 0.05,
@@ -216,7 +234,8 @@ def run_ours(args, rank, world, local_rank):
                    "what": "same K steps through DenoiseEngine.start/advance with pinned HOST buffers: scan + start uploaded, per-step SDE noise H2D and x_t D2H inside the timed region"},
            "gpu_launches": int(launches), "roofline": roofline}
     if world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_reference(scan.cpu(), pipe, sample_budget_s=25.0, steps=1, warmup=0)
+        log("cpu baseline leg")
+        out["cpu_baseline"] = cpu_reference(scan.cpu(), pipe, sample_budget_s=20.0, steps=1, warmup=0)
     return out
 
 
@@ -224,7 +243,9 @@ def run_ours(args, rank, world, local_rank):
 def cpu_reference(scan, pipe, sample_budget_s, steps, warmup):
     """CPU restatement of the reference path (oracle port) on the host cores, bounded sample."""
     from oracle.pipeline import DiffCompletionOracle
-    torch.set_num_threads(os.cpu_count())
+    cores = usable_cpus()
+    torch.set_num_threads(cores)
+    log(f"cpu reference: {cores} threads")
     sd_e = {k: v.detach().cpu() for k, v in pipe.partial_enc.state_dict().items()}
     sd_d = {k: v.detach().cpu() for k, v in pipe.model.state_dict().items()}
     o = DiffCompletionOracle(sd_e, sd_d, None, denoising_steps=T_STEPS, cond_weight=GUIDANCE_W)
@@ -240,16 +261,21 @@ def cpu_reference(scan, pipe, sample_budget_s, steps, warmup):
     # size the per-step sample: probe on 1/20 of the points, then pick the largest fraction inside the budget
     n_probe = N_POINTS // 20
     t_probe = one_step(scan[:: N_POINTS // n_probe][:n_probe])
-    per_point = t_probe / n_probe
+    log(f"cpu reference: probe step on {n_probe} points took {t_probe:.2f} s")
+    per_point = 1.5 * t_probe / n_probe          # cost grows a little faster than linearly (denser neighbourhoods)
     total = max(steps + warmup, 1)
     n_s = int(min(N_POINTS, max(n_probe, sample_budget_s / total / per_point)))
     sub = scan[torch.linspace(0, N_POINTS - 1, n_s).long()]
+    log(f"cpu reference: {total} step(s) on {n_s} points each")
     for _ in range(warmup):
         one_step(sub)
-    ts = [one_step(sub) for _ in range(steps)]
+    ts = []
+    for _ in range(steps):
+        ts.append(one_step(sub))
+        log(f"cpu reference: step took {ts[-1]:.2f} s")
     t_step = sum(ts) / len(ts)
     value = (1.0 / t_step) * (n_s / N_POINTS)
-    return {"value": round(value, 5), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+    return {"value": round(value, 5), "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{steps} denoising step(s) of the oracle (fp32 torch-CPU restatement of the ME/KeOps/diffusers path, all host threads) on "
                       f"{n_s} of the {N_POINTS} points; steps/s scaled linearly by {n_s}/{N_POINTS} to the full scan ({t_step:.2f} s per sampled step)"}
 

@@ -87,10 +87,18 @@ int lb2_voxel_mean(void* h, void* stream, const float* feats, const int32_t* inv
  * Output-stationary neighbour table: nbr[k * nbr_stride + o] = input row at coords(o) + offset_k, or -1.
  *   ks=3: offset_d = (k_d - 1) * step      ks=2: offset_d = k_d * step   (step < 0: transposed map)
  *   k = kx + ks*ky + ks*ks*kz.
- * pair_count (device uint64, optional): += number of (in,out) pairs found (roofline accounting). */
+ * pair_count (device uint64, optional): += number of (in,out) pairs found (roofline accounting).
+ * row_mask (uint32[nout_cap], optional): bit k of row_mask[o] set iff nbr[k][o] >= 0. */
 int lb2_kernel_map(void* h, void* stream, lb2_grid grid_in, const int32_t* out_coords,
                    const int32_t* d_nout, int32_t nout_cap, int32_t ks, int32_t step,
-                   int32_t* nbr, int64_t nbr_stride, uint64_t* pair_count);
+                   int32_t* nbr, int64_t nbr_stride, uint64_t* pair_count, uint32_t* row_mask);
+
+/* Execution order of the output rows for lb2_spconv_forward (no reference counterpart: scheduling only).
+ * perm[0..n) = the rows 0..n-1 grouped by the class of their neighbour mask so that 128-row tiles skip
+ * unpopulated kernel offsets.  Results do not depend on the order.  scratch >= lb2_row_order_scratch_bytes(). */
+size_t lb2_row_order_scratch_bytes(void);
+int lb2_row_order(void* h, void* stream, const uint32_t* row_mask, const int32_t* d_n, int32_t n_cap,
+                  int32_t kvol, int32_t* perm, void* scratch);
 
 /* ---- sparse convolution  — replaces ME.MinkowskiConvolution(+Transpose) forward, with the
  * MinkowskiBatchNorm(eval)/MinkowskiReLU/residual-add/ME.cat/gate-multiply that follow it in
@@ -120,6 +128,7 @@ typedef struct {
     int64_t        nbr_stride;
     const int32_t* d_mout;      /* device row count or NULL => mout_cap */
     int32_t        mout_cap;
+    const int32_t* row_perm;    /* execution order from lb2_row_order or NULL (natural order) */
     int32_t        npass;       /* 1 or 2 */
     lb2_conv_io    io[2];
 } lb2_conv_desc;
@@ -140,6 +149,13 @@ int lb2_pack_weights(void* h, void* stream, const float* weight, int32_t kvol, i
 int lb2_nn_match(void* h, void* stream, const int32_t* q_coords, const int32_t* d_nq, int32_t nq_cap,
                  const int32_t* k_coords, const int32_t* d_nk, int32_t nk_cap, int32_t batch_scale,
                  int32_t* idx);
+
+/* Same result as lb2_nn_match when the keys are the rows of a hash grid on a lattice of pitch key_stride
+ * (the stride-16 partial-scan level): exact shell search around the query's lattice cell, exhaustive
+ * fallback after max_ring shells.  Different-batch keys never match (lb2_nn_match batch_scale = 0). */
+int lb2_nn_match_grid(void* h, void* stream, const int32_t* q_coords, const int32_t* d_nq, int32_t nq_cap,
+                      const int32_t* k_coords, const int32_t* d_nk, int32_t nk_cap, lb2_grid key_grid,
+                      int32_t key_stride, int32_t max_ring, int32_t* idx);
 
 /* ---- small dense layers — torch.nn.Linear (+LeakyReLU) of the gate / head MLPs
  * (minkunet.py:165-181,376-380): y = act(x @ W^T + b [+ addend]); W is (n_out, n_in) torch layout.

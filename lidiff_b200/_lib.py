@@ -31,7 +31,7 @@ class ConvDesc(C.Structure):
                 ("weight", C.c_void_p), ("weight_packed", C.c_void_p),
                 ("scale", C.c_void_p), ("shift", C.c_void_p), ("relu", C.c_int32),
                 ("nbr", C.c_void_p), ("nbr_stride", C.c_int64),
-                ("d_mout", C.c_void_p), ("mout_cap", C.c_int32), ("npass", C.c_int32),
+                ("d_mout", C.c_void_p), ("mout_cap", C.c_int32), ("row_perm", C.c_void_p), ("npass", C.c_int32),
                 ("io", ConvIO * 2)]
 
 
@@ -47,6 +47,7 @@ EXPORTS = [
     "lb2_quantize", "lb2_unique_scratch_bytes", "lb2_unique_build", "lb2_voxel_mean", "lb2_kernel_map",
     "lb2_spconv_forward", "lb2_packed_weight_bytes", "lb2_pack_weights", "lb2_nn_match", "lb2_linear",
     "lb2_gate_mul", "lb2_gather_rows", "lb2_guidance_dpm_step", "lb2_farthest_point_sample",
+    "lb2_row_order", "lb2_row_order_scratch_bytes", "lb2_nn_match_grid",
 ]
 
 
@@ -84,10 +85,13 @@ class Lib:
         d.lb2_quantize.argtypes = [vp, vp, vp, i64, f32, C.c_int, vp]
         d.lb2_unique_build.argtypes = [vp, vp, vp, vp, vp, i32, i32, Grid, vp, vp, vp, vp]
         d.lb2_voxel_mean.argtypes = [vp, vp, vp, vp, i32, i32, vp, i32, vp, vp]
-        d.lb2_kernel_map.argtypes = [vp, vp, Grid, vp, vp, i32, i32, i32, vp, i64, vp]
+        d.lb2_kernel_map.argtypes = [vp, vp, Grid, vp, vp, i32, i32, i32, vp, i64, vp, vp]
+        d.lb2_row_order.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp]
+        d.lb2_row_order_scratch_bytes.restype = C.c_size_t
         d.lb2_spconv_forward.argtypes = [vp, vp, C.POINTER(ConvDesc), C.c_int]
         d.lb2_pack_weights.argtypes = [vp, vp, vp, i32, i32, i32, vp]
         d.lb2_nn_match.argtypes = [vp, vp, vp, vp, i32, vp, vp, i32, i32, vp]
+        d.lb2_nn_match_grid.argtypes = [vp, vp, vp, vp, i32, vp, vp, i32, Grid, i32, i32, vp]
         d.lb2_linear.argtypes = [vp, vp, vp, i64, vp, vp, vp, i64, i32, vp, i32, i32, i32, vp, i64,
                                  vp, i32]
         d.lb2_gate_mul.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, vp]
@@ -161,9 +165,13 @@ class Handle:
         self._check(self.dll.lb2_voxel_mean(self.hp, self._stream(), _ptr(feats), _ptr(inverse), int(n), int(c), _ptr(d_m), int(m_cap),
                                             _ptr(out), _ptr(counts)), "lb2_voxel_mean")
 
-    def kernel_map(self, grid_in, out_coords, d_nout, nout_cap, ks, step, nbr, nbr_stride, pair_count=None):
+    def kernel_map(self, grid_in, out_coords, d_nout, nout_cap, ks, step, nbr, nbr_stride, pair_count=None, row_mask=None):
         self._check(self.dll.lb2_kernel_map(self.hp, self._stream(), self._grid(grid_in), _ptr(out_coords), _ptr(d_nout), int(nout_cap),
-                                            int(ks), int(step), _ptr(nbr), int(nbr_stride), _ptr(pair_count)), "lb2_kernel_map")
+                                            int(ks), int(step), _ptr(nbr), int(nbr_stride), _ptr(pair_count), _ptr(row_mask)), "lb2_kernel_map")
+
+    def row_order(self, row_mask, d_n, n_cap, kvol, perm, scratch):
+        self._check(self.dll.lb2_row_order(self.hp, self._stream(), _ptr(row_mask), _ptr(d_n), int(n_cap), int(kvol), _ptr(perm), _ptr(scratch)),
+                    "lb2_row_order")
 
     # -- conv ----------------------------------------------------------------------------------------
     def spconv(self, desc: ConvDesc, algo: int = ALGO_AUTO):
@@ -185,6 +193,10 @@ class Handle:
     def nn_match(self, q, d_nq, nq_cap, k, d_nk, nk_cap, batch_scale, idx):
         self._check(self.dll.lb2_nn_match(self.hp, self._stream(), _ptr(q), _ptr(d_nq), int(nq_cap), _ptr(k), _ptr(d_nk), int(nk_cap),
                                           int(batch_scale), _ptr(idx)), "lb2_nn_match")
+
+    def nn_match_grid(self, q, d_nq, nq_cap, k, d_nk, nk_cap, key_grid, key_stride, max_ring, idx):
+        self._check(self.dll.lb2_nn_match_grid(self.hp, self._stream(), _ptr(q), _ptr(d_nq), int(nq_cap), _ptr(k), _ptr(d_nk), int(nk_cap),
+                                               self._grid(key_grid), int(key_stride), int(max_ring), _ptr(idx)), "lb2_nn_match_grid")
 
     def linear(self, x, ldx, w, b, addend, ld_add, m_cap, d_m, n_in, n_out, act, y, ldy, prebias=None, pre_act=0):
         self._check(self.dll.lb2_linear(self.hp, self._stream(), _ptr(x), int(ldx), _ptr(w), _ptr(b), _ptr(addend), int(ld_add), int(m_cap),

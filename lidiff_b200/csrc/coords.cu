@@ -6,6 +6,7 @@
 // /root/reference/lidiff/tools/diff_completion_pipeline.py:68-84,149 and lidiff/models/minkunet.py:17-24,36-42,135.
 #include "common.cuh"
 #include <limits.h>
+#include <algorithm>
 
 // ---------------------------------------------------------------------------------------------------
 // handle
@@ -304,7 +305,7 @@ extern "C" int lb2_voxel_mean(void* handle, void* stream, const float* feats, co
 __global__ void k_kernel_map(const unsigned long long* __restrict__ keys, const int* __restrict__ rows, unsigned mask,
                              const int4* __restrict__ out_coords, const int* __restrict__ d_n, int n_cap,
                              int ks, int step, int* __restrict__ nbr, long long nbr_stride,
-                             unsigned long long* __restrict__ pair_count) {
+                             unsigned long long* __restrict__ pair_count, unsigned* __restrict__ row_mask) {
     int o = blockIdx.x * blockDim.x + threadIdx.x;
     int k = blockIdx.y;
     int n = d_n ? min(*d_n, n_cap) : n_cap;
@@ -318,6 +319,7 @@ __global__ void k_kernel_map(const unsigned long long* __restrict__ keys, const 
         if (lb2_pack_key(c.x, x, y, z, key)) res = lb2_grid_lookup(keys, rows, mask, key);
     }
     if (o < n_cap) nbr[(long long)k * nbr_stride + o] = res;
+    if (row_mask && res >= 0) atomicOr(row_mask + o, 1u << k);
     if (pair_count) {        // algorithmic work counter for the roofline: one atomic per warp
         unsigned found = __ballot_sync(0xffffffffu, res >= 0);
         if ((threadIdx.x & 31) == 0 && found) atomicAdd(pair_count, (unsigned long long)__popc(found));
@@ -326,16 +328,93 @@ __global__ void k_kernel_map(const unsigned long long* __restrict__ keys, const 
 
 extern "C" int lb2_kernel_map(void* handle, void* stream, lb2_grid grid_in, const int32_t* out_coords,
                               const int32_t* d_nout, int32_t nout_cap, int32_t ks, int32_t step,
-                              int32_t* nbr, int64_t nbr_stride, uint64_t* pair_count) {
+                              int32_t* nbr, int64_t nbr_stride, uint64_t* pair_count, uint32_t* row_mask) {
     Lb2Handle* h = (Lb2Handle*)handle;
     LB2_REQUIRE(h, h && grid_in.keys && grid_in.vals && out_coords && nbr, "kernel_map null");
     LB2_REQUIRE(h, ks >= 1 && ks <= 3 && step != 0 && nout_cap > 0 && nbr_stride >= nout_cap, "kernel_map args");
     int kvol = ks * ks * ks;
+    if (row_mask && cudaMemsetAsync(row_mask, 0, (size_t)nout_cap * sizeof(uint32_t), (cudaStream_t)stream) != cudaSuccess)
+        return lb2_fail(h, LB2_ERR_CUDA, "kernel_map memset%s", "");
     dim3 grid(cdiv(nout_cap, 256), kvol);
     k_kernel_map<<<grid, 256, 0, (cudaStream_t)stream>>>((const unsigned long long*)grid_in.keys,
                                                         grid_in.vals + grid_in.cap_table, (unsigned)grid_in.cap_table - 1u,
                                                         (const int4*)out_coords, d_nout, nout_cap, ks, step, nbr, nbr_stride,
-                                                        (unsigned long long*)pair_count);
+                                                        (unsigned long long*)pair_count, row_mask);
     LB2_POST_LAUNCH(h, "k_kernel_map");
+    return LB2_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// row order: counting sort of the output rows by the class of their neighbour mask, so that the 128-row
+// tiles of the convolution kernels are (nearly) homogeneous in which kernel offsets are populated and
+// skip the rest.  kvol <= 8: bucket = the 8-bit mask itself; kvol == 27: 0 = centre only,
+// 1..27 = centre + exactly one other offset j, 28..54 = two or more others (bucketed by the lowest).
+// The order inside a bucket is irrelevant for the results (each output row is computed independently).
+// ---------------------------------------------------------------------------------------------------
+#define RO_BINS 256
+__device__ __forceinline__ int ro_bucket(unsigned mask, int kvol) {
+    if (kvol <= 8) return (int)(mask & 0xffu);
+    const unsigned extras = mask & ~(1u << 13);
+    if (!extras) return 0;
+    const int j = __ffs(extras);            // 1..27
+    return (__popc(extras) == 1) ? j : 27 + j;
+}
+
+__global__ void k_ro_hist(const unsigned* __restrict__ mask, const int* __restrict__ d_n, int n_cap, int kvol, int* __restrict__ bins) {
+    __shared__ int sh[RO_BINS];
+    for (int i = threadIdx.x; i < RO_BINS; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const int n = d_n ? min(*d_n, n_cap) : n_cap;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) atomicAdd(&sh[ro_bucket(mask[i], kvol)], 1);
+    __syncthreads();
+    for (int i = threadIdx.x; i < RO_BINS; i += blockDim.x) if (sh[i]) atomicAdd(&bins[i], sh[i]);
+}
+
+__global__ void k_ro_scan(int* __restrict__ bins) {        // 1 block of RO_BINS threads: exclusive scan in place
+    __shared__ int sh[RO_BINS];
+    const int t = threadIdx.x;
+    const int v = bins[t];
+    sh[t] = v;
+    __syncthreads();
+    for (int d = 1; d < RO_BINS; d <<= 1) {
+        const int u = (t >= d) ? sh[t - d] : 0;
+        __syncthreads();
+        sh[t] += u;
+        __syncthreads();
+    }
+    bins[t] = sh[t] - v;
+}
+
+__global__ void k_ro_scatter(const unsigned* __restrict__ mask, const int* __restrict__ d_n, int n_cap, int kvol,
+                             int* __restrict__ cursor, int* __restrict__ perm) {
+    __shared__ int cnt[RO_BINS];
+    __shared__ int base[RO_BINS];
+    for (int i = threadIdx.x; i < RO_BINS; i += blockDim.x) cnt[i] = 0;
+    __syncthreads();
+    const int n = d_n ? min(*d_n, n_cap) : n_cap;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int b = -1, local = 0;
+    if (i < n) { b = ro_bucket(mask[i], kvol); local = atomicAdd(&cnt[b], 1); }
+    __syncthreads();
+    for (int j = threadIdx.x; j < RO_BINS; j += blockDim.x) if (cnt[j]) base[j] = atomicAdd(&cursor[j], cnt[j]);
+    __syncthreads();
+    if (i < n) perm[base[b] + local] = i;
+}
+
+extern "C" size_t lb2_row_order_scratch_bytes(void) { return RO_BINS * sizeof(int); }
+
+extern "C" int lb2_row_order(void* handle, void* stream, const uint32_t* row_mask, const int32_t* d_n, int32_t n_cap,
+                             int32_t kvol, int32_t* perm, void* scratch) {
+    Lb2Handle* h = (Lb2Handle*)handle;
+    LB2_REQUIRE(h, h && row_mask && perm && scratch && n_cap > 0 && (kvol == 27 || (kvol >= 1 && kvol <= 8)), "row_order");
+    cudaStream_t s = (cudaStream_t)stream;
+    int* bins = (int*)scratch;
+    if (cudaMemsetAsync(bins, 0, RO_BINS * sizeof(int), s) != cudaSuccess) return lb2_fail(h, LB2_ERR_CUDA, "row_order memset%s", "");
+    k_ro_hist<<<std::min<unsigned>(cdiv(n_cap, 256), 1024u), 256, 0, s>>>(row_mask, d_n, n_cap, kvol, bins);
+    LB2_POST_LAUNCH(h, "k_ro_hist");
+    k_ro_scan<<<1, RO_BINS, 0, s>>>(bins);
+    LB2_POST_LAUNCH(h, "k_ro_scan");
+    k_ro_scatter<<<cdiv(n_cap, 256), 256, 0, s>>>(row_mask, d_n, n_cap, kvol, bins, perm);
+    LB2_POST_LAUNCH(h, "k_ro_scatter");
     return LB2_OK;
 }

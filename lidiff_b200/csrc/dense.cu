@@ -58,6 +58,76 @@ extern "C" int lb2_nn_match(void* handle, void* stream, const int32_t* q_coords,
 }
 
 // ---------------------------------------------------------------------------------------------------
+// nn_match, grid-accelerated: the keys are voxels on a lattice of pitch `ks` (the stride-16 partial-scan
+// level) that already own a hash grid (coordinate -> row).  Each query walks the lattice in growing cube
+// shells around its nearest lattice cell; every key outside shell r is at least ks*(r+0.5) away along one
+// axis, so the search stops as soon as the best squared distance is strictly below ks^2*(r+0.5)^2 (strict:
+// an equal-distance key further out could still win the lowest-index tie rule).  Same result as the brute
+// force kernel, ~50x fewer distance evaluations for queries near the scan; a query that is not settled
+// after `max_ring` shells falls back to the exhaustive scan.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int floor_div(int a, int b) { int q = a / b; return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q; }
+
+__global__ void __launch_bounds__(256) k_nn_match_grid(const int4* __restrict__ q, const int* __restrict__ d_nq, int nq_cap,
+                                                       const int4* __restrict__ keys, const int* __restrict__ d_nk, int nk_cap,
+                                                       const unsigned long long* __restrict__ gkeys, const int* __restrict__ grows, unsigned gmask,
+                                                       int ks, int max_ring, int* __restrict__ idx) {
+    const int nq = d_nq ? min(*d_nq, nq_cap) : nq_cap;
+    const int nk = d_nk ? min(*d_nk, nk_cap) : nk_cap;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    const int4 c = __ldg(q + i);
+    const int cx = floor_div(c.y + ks / 2, ks), cy = floor_div(c.z + ks / 2, ks), cz = floor_div(c.w + ks / 2, ks);
+    unsigned long long best = ~0ull;
+    int best_j = 0x7fffffff;
+    bool settled = false;
+    for (int r = 0; r <= max_ring && !settled; ++r) {
+        for (int dz = -r; dz <= r; ++dz) {
+            for (int dy = -r; dy <= r; ++dy) {
+                const bool face = (abs(dz) == r) || (abs(dy) == r);
+                const int step = face ? 1 : max(2 * r, 1);
+                for (int dx = -r; dx <= r; dx += step) {
+                    const int kx = (cx + dx) * ks, ky = (cy + dy) * ks, kz = (cz + dz) * ks;
+                    unsigned long long key;
+                    if (!lb2_pack_key(c.x, kx, ky, kz, key)) continue;
+                    const int j = lb2_grid_lookup(gkeys, grows, gmask, key);
+                    if (j < 0) continue;
+                    const long long ex = c.y - kx, ey = c.z - ky, ez = c.w - kz;
+                    const unsigned long long d = (unsigned long long)(ex * ex + ey * ey + ez * ez);
+                    if (d < best || (d == best && j < best_j)) { best = d; best_j = j; }
+                }
+            }
+        }
+        const unsigned long long bound = (unsigned long long)ks * ks * (2 * r + 1) * (2 * r + 1);   // 4 * ks^2 (r+0.5)^2
+        settled = (best != ~0ull) && (4ull * best < bound);
+    }
+    if (!settled) {        // far from every key: exhaustive scan (identical tie rule)
+        best = ~0ull; best_j = 0;
+        for (int j = 0; j < nk; ++j) {
+            const int4 kc = __ldg(keys + j);
+            const long long ex = c.y - kc.y, ey = c.z - kc.z, ez = c.w - kc.w;
+            unsigned long long d = (unsigned long long)(ex * ex + ey * ey + ez * ez);
+            if (c.x != kc.x) d += 1ull << 62;
+            if (d < best) { best = d; best_j = j; }
+        }
+    }
+    idx[i] = best_j;
+}
+
+extern "C" int lb2_nn_match_grid(void* handle, void* stream, const int32_t* q_coords, const int32_t* d_nq, int32_t nq_cap,
+                                 const int32_t* k_coords, const int32_t* d_nk, int32_t nk_cap, lb2_grid key_grid,
+                                 int32_t key_stride, int32_t max_ring, int32_t* idx) {
+    Lb2Handle* h = (Lb2Handle*)handle;
+    LB2_REQUIRE(h, h && q_coords && k_coords && idx && key_grid.keys && key_grid.vals && nq_cap > 0 && nk_cap > 0, "nn_match_grid");
+    LB2_REQUIRE(h, key_stride > 0 && key_stride % 2 == 0 && max_ring >= 0 && max_ring <= 16, "nn_match_grid stride/ring");
+    k_nn_match_grid<<<cdiv(nq_cap, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const int4*)q_coords, d_nq, nq_cap, (const int4*)k_coords, d_nk, nk_cap, (const unsigned long long*)key_grid.keys,
+        key_grid.vals + key_grid.cap_table, (unsigned)key_grid.cap_table - 1u, key_stride, max_ring, idx);
+    LB2_POST_LAUNCH(h, "k_nn_match_grid");
+    return LB2_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // linear: y = act(x W^T + b + addend)
 // ---------------------------------------------------------------------------------------------------
 #define LIN_BM 64

@@ -8,15 +8,21 @@
 // power of two per layer so their low parts stay in fp16's normal range; activations saturate at
 // +-65504.)
 //
-// One CTA owns 128 output rows x all Cout channels.  Warp roles (192 threads):
+// One CTA owns 128 output rows x all Cout channels.  Warp roles (320 threads):
 //   warps 0-3  A producers: gather the neighbour rows of kernel offset k / channel chunk c from the
 //              fp32 feature matrix, split to fp16 hi/lo in registers, store into the UMMA K-major
-//              SWIZZLE_128B shared-memory image; afterwards they are the epilogue warps
-//              (tcgen05.ld -> BN affine + residual + ReLU + gate -> global).
+//              SWIZZLE_128B shared-memory image.
 //   warp 4     MMA issuer: one thread issues 3 x (chunk/16) tcgen05.mma per stage, tcgen05.commit
-//              releases the stage / signals the epilogue.
+//              releases the stage / signals the drain warps.
 //   warp 5     B producer: one thread streams the pre-packed weight image of (k, c) with one
 //              cp.async.bulk (TMA bulk copy, mbarrier complete_tx) per stage.
+//   warps 6-9  drain + epilogue: TWO-LEVEL ACCUMULATION.  The tensor core adds into TMEM with
+//              truncation, so the error of a chained accumulation grows linearly with the number of MMA
+//              steps (measured: ~1300 steps -> 8e-5 relative per layer, 1e-3 through the 49-layer
+//              U-Net).  The MMA chain is therefore cut into groups of <= ~128 steps; after each group
+//              these warps tcgen05.ld the partial sum, add it to a running fp32 total (round-to-nearest,
+//              kept in a second TMEM region via tcgen05.st) and release the accumulator.  The last
+//              group's drain is the epilogue: BN affine + residual + ReLU + gate -> global.
 // Kernel offsets where none of the tile's 128 rows has a neighbour are skipped by every role.
 //
 // Stands behind ME.MinkowskiConvolution(+Transpose) forward, /root/reference/lidiff/models/minkunet.py:17-24,36-42,53-74.
@@ -31,7 +37,9 @@ constexpr int KC = 64;               // channels per pipeline stage (one 128-byt
 constexpr int A_TILE = BM * KC * 2;  // bytes of one fp16 A tile (hi or lo): 16 KB
 constexpr int PACK_HEADER = 256;     // bytes: [0] max|W| bits, [1] 2^-k output scale
 constexpr int NUM_PRODUCER = 128;
-constexpr int THREADS = 192;
+constexpr int THREADS = 320;
+constexpr int DRAIN_WARP0 = 6;        // warps 6..9
+constexpr int STEP_BUDGET = 128;      // max chained MMA steps per TMEM accumulation group
 constexpr int MAX_KVOL = 27;
 constexpr int MAX_STAGES = 4;
 
@@ -45,7 +53,8 @@ struct Params {
     long long nbr_stride;
     const int* d_mout;
     int mout_cap;
-    int stages, nchunks, tmem_cols;
+    const int* row_perm;
+    int stages, nchunks, tmem_cols, tot_col, group;     // tot_col: TMEM column of the running total; group: offsets per drain
     lb2_conv_io io[2];
 };
 
@@ -94,6 +103,30 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+                 "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+                 "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+                 :: "r"(taddr),
+                    "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                    "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+                    "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+                    "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+                 : "memory");
+}
+
 // byte offset of (row, 16-byte chunk) inside a K-major SWIZZLE_128B tile (rows of 128 B, Swizzle<3,4,3>)
 __device__ __forceinline__ uint32_t sw128(int row, int chunk) {
     return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4));
@@ -134,16 +167,19 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc(const Params p) {
     unsigned char* tail = gen + (size_t)p.stages * stage_bytes;
     int* idx_s = reinterpret_cast<int*>(tail);                       // [kvol][BM]
     uint64_t* bars = reinterpret_cast<uint64_t*>(tail + MAX_KVOL * BM * sizeof(int));
-    uint32_t* misc = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + 1);   // [0] tmem base, [1] offset mask
+    uint32_t* misc = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + 2);   // [0] tmem base, [1] offset mask
+    int* row_s = reinterpret_cast<int*>(misc + 4);                             // [BM] output row of each tile slot
     const uint32_t bar0 = smem_u32(bars);
     auto full_a = [&](int s) { return bar0 + 8u * s; };
     auto full_b = [&](int s) { return bar0 + 8u * (MAX_STAGES + s); };
     auto empty = [&](int s) { return bar0 + 8u * (2 * MAX_STAGES + s); };
-    const uint32_t acc_full = bar0 + 8u * (3 * MAX_STAGES);
+    const uint32_t acc_full = bar0 + 8u * (3 * MAX_STAGES);        // MMA group complete  -> drain warps
+    const uint32_t acc_empty = bar0 + 8u * (3 * MAX_STAGES + 1);   // drain complete      -> MMA issuer
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(full_a(s), NUM_PRODUCER); mbar_init(full_b(s), 1); mbar_init(empty(s), 1); }
         mbar_init(acc_full, 1);
+        mbar_init(acc_empty, 128);
         misc[1] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -154,11 +190,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc(const Params p) {
     __syncthreads();
     // ---- neighbour indices of this tile + mask of non-empty kernel offsets -----------------------------
     if (threadIdx.x < BM) {
-        const int row = m0 + threadIdx.x;
+        const int slot = m0 + threadIdx.x;
+        const int row = (slot < M) ? (p.row_perm ? __ldg(p.row_perm + slot) : slot) : -1;
+        row_s[threadIdx.x] = row;
         uint32_t mymask = 0;
         for (int k = 0; k < p.kvol; ++k) {
             int v = -1;
-            if (row < M) v = p.nbr ? __ldg(p.nbr + (long long)k * p.nbr_stride + row) : row;
+            if (row >= 0) v = p.nbr ? __ldg(p.nbr + (long long)k * p.nbr_stride + row) : row;
             idx_s[k * BM + threadIdx.x] = v;
             if (__any_sync(0xffffffffu, v >= 0)) mymask |= 1u << k;
         }
@@ -169,7 +207,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc(const Params p) {
     tc_fence_after();
     const uint32_t tmem_d = misc[0];
     const uint32_t kmask = misc[1];
-    const int n_iters = __popc(kmask) * p.nchunks;
+    const int n_off = __popc(kmask);
+    const int n_groups = (n_off + p.group - 1) / p.group;
 
     if (warp < 4) {
         // =========================== A producers ===========================
@@ -216,67 +255,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc(const Params p) {
                 mbar_arrive(full_a(s));
             }
         }
-        // =========================== epilogue ===========================
-        const int row = m0 + warp * 32 + lane;
-        if (n_iters > 0) { mbar_wait(acc_full, 0); }
-        tc_fence_after();
-        const long long ro = (long long)row * p.cout;
-        const float* gate_row = nullptr;
-        if (io.gate_table && row < M) gate_row = io.gate_table + (long long)(io.gate_idx ? __ldg(io.gate_idx + row) : 0) * p.cout;
-        for (int c0 = 0; c0 < p.cout; c0 += 32) {
-            uint32_t r[32];
-            if (n_iters > 0) {
-                const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
-                asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                             "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                               "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                               "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                               "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                             : "r"(taddr) : "memory");
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) r[j] = 0u;
-            }
-            if (row < M) {
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    float y[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int col = c0 + q * 4 + j;
-                        float v = __uint_as_float(r[q * 4 + j]) * out_scale;
-                        if (p.scale) v = fmaf(v, __ldg(p.scale + col), __ldg(p.shift + col));
-                        y[j] = v;
-                    }
-                    if (io.residual) {
-                        const float4 rr = __ldg(reinterpret_cast<const float4*>(io.residual + ro + c0 + q * 4));
-                        y[0] += rr.x; y[1] += rr.y; y[2] += rr.z; y[3] += rr.w;
-                    }
-                    if (p.relu) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) y[j] = fmaxf(y[j], 0.f);
-                    }
-                    if (io.out) *reinterpret_cast<float4*>(io.out + ro + c0 + q * 4) = make_float4(y[0], y[1], y[2], y[3]);
-                    if (io.out_gated) {
-                        if (gate_row) {
-                            const float4 gg = __ldg(reinterpret_cast<const float4*>(gate_row + c0 + q * 4));
-                            y[0] *= gg.x; y[1] *= gg.y; y[2] *= gg.z; y[3] *= gg.w;
-                        }
-                        *reinterpret_cast<float4*>(io.out_gated + ro + c0 + q * 4) = make_float4(y[0], y[1], y[2], y[3]);
-                    }
-                }
-            }
-        }
     } else if (warp == 4) {
         // =========================== MMA issuer ===========================
         if (lane == 0) {
             const uint32_t idesc = make_idesc(p.cout);
-            int it = 0;
-            uint32_t accumulate = 0;
-            for (uint32_t km = kmask; km; km &= km - 1) {
+            int it = 0, in_group = 0, group_idx = 0, off_idx = 0;
+            for (uint32_t km = kmask; km; km &= km - 1, ++off_idx) {
+                if (in_group == 0 && group_idx > 0) {             // previous group must be drained before TMEM is overwritten
+                    mbar_wait(acc_empty, (group_idx - 1) & 1);
+                    tc_fence_after();
+                }
                 for (int c = 0; c < p.nchunks; ++c, ++it) {
                     const int s = it % p.stages;
                     const uint32_t par = (it / p.stages) & 1;
@@ -289,18 +277,96 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc(const Params p) {
                     for (int ks = 0; ks < ksteps; ++ks) {
                         const uint64_t dah = make_desc(a_hi + ks * 32), dal = make_desc(a_lo + ks * 32);
                         const uint64_t dbh = make_desc(b_hi + ks * 32), dbl = make_desc(b_lo + ks * 32);
-                        umma(tmem_d, dah, dbh, idesc, accumulate);
-                        accumulate = 1;
+                        umma(tmem_d, dah, dbh, idesc, (in_group | c | ks) ? 1u : 0u);   // first MMA of a group overwrites
                         umma(tmem_d, dal, dbh, idesc, 1);
                         umma(tmem_d, dah, dbl, idesc, 1);
                     }
                     umma_commit(empty(s));            // frees the stage when these MMAs have read it
                 }
+                if (++in_group == p.group || off_idx == n_off - 1) {
+                    umma_commit(acc_full);            // partial sum of this group complete -> drain warps
+                    in_group = 0;
+                    ++group_idx;
+                }
             }
-            if (n_iters > 0) umma_commit(acc_full);   // accumulator complete -> epilogue
         }
         __syncwarp();
-    } else {
+    } else if (warp >= DRAIN_WARP0) {
+        // =========================== drain + epilogue (two-level accumulation) ===========================
+        const int q4 = warp & 3;                                   // TMEM lane quarter this warp may access
+        const int row = row_s[q4 * 32 + lane];
+        const long long ro = (long long)row * p.cout;
+        const float* gate_row = nullptr;
+        if (io.gate_table && row >= 0) gate_row = io.gate_table + (long long)(io.gate_idx ? __ldg(io.gate_idx + row) : 0) * p.cout;
+        const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;
+        for (int g = 0; g < max(n_groups, 1); ++g) {
+            const bool last = g >= n_groups - 1;
+            if (n_groups > 0) {
+                mbar_wait(acc_full, g & 1);
+                tc_fence_after();
+            }
+            for (int c0 = 0; c0 < p.cout; c0 += 32) {
+                float acc[32];
+                if (n_groups > 0) {
+                    uint32_t r[32];
+                    tmem_ld32(tmem_d + lane_base + (uint32_t)c0, r);
+                    if (g > 0) {
+                        uint32_t t[32];
+                        tmem_ld32(tmem_d + lane_base + (uint32_t)(p.tot_col + c0), t);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc[j] = __fadd_rn(__uint_as_float(t[j]), __uint_as_float(r[j]));
+                    } else {
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+                }
+                if (!last) {                       // running total back to TMEM
+                    uint32_t t[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) t[j] = __float_as_uint(acc[j]);
+                    tmem_st32(tmem_d + lane_base + (uint32_t)(p.tot_col + c0), t);
+                } else if (row >= 0) {             // epilogue on the final sum
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        float y[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int col = c0 + q * 4 + j;
+                            float v = acc[q * 4 + j] * out_scale;
+                            if (p.scale) v = fmaf(v, __ldg(p.scale + col), __ldg(p.shift + col));
+                            y[j] = v;
+                        }
+                        if (io.residual) {
+                            const float4 rr = __ldg(reinterpret_cast<const float4*>(io.residual + ro + c0 + q * 4));
+                            y[0] += rr.x; y[1] += rr.y; y[2] += rr.z; y[3] += rr.w;
+                        }
+                        if (p.relu) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) y[j] = fmaxf(y[j], 0.f);
+                        }
+                        if (io.out) *reinterpret_cast<float4*>(io.out + ro + c0 + q * 4) = make_float4(y[0], y[1], y[2], y[3]);
+                        if (io.out_gated) {
+                            if (gate_row) {
+                                const float4 gg = __ldg(reinterpret_cast<const float4*>(gate_row + c0 + q * 4));
+                                y[0] *= gg.x; y[1] *= gg.y; y[2] *= gg.z; y[3] *= gg.w;
+                            }
+                            *reinterpret_cast<float4*>(io.out_gated + ro + c0 + q * 4) = make_float4(y[0], y[1], y[2], y[3]);
+                        }
+                    }
+                }
+            }
+            if (!last) {
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                mbar_arrive(acc_empty);            // accumulator may be overwritten by the next group
+            }
+        }
+    } else if (warp == 5) {
         // =========================== B producer (weights) ===========================
         if (lane == 0) {
             int it = 0;
@@ -377,7 +443,7 @@ static bool shape_ok(int c1, int c2, int cout, int kvol) {
 }
 
 static size_t smem_bytes(int cout, int stages) {
-    return 1024 + (size_t)stages * (2 * A_TILE + 2 * (size_t)cout * 128) + MAX_KVOL * BM * sizeof(int) + (3 * MAX_STAGES + 1) * 8 + 16;
+    return 1024 + (size_t)stages * (2 * A_TILE + 2 * (size_t)cout * 128) + MAX_KVOL * BM * sizeof(int) + (3 * MAX_STAGES + 2) * 8 + 16 + BM * sizeof(int);
 }
 
 }  // namespace tc
@@ -410,12 +476,16 @@ int lb2_spconv_tc_launch(Lb2Handle* h, cudaStream_t s, const lb2_conv_desc* d) {
     p.c1 = d->c1; p.c2 = d->c2; p.cout = d->cout; p.kvol = d->kvol;
     p.wpacked = (const unsigned char*)d->weight_packed;
     p.scale = d->scale; p.shift = d->shift; p.relu = d->relu;
-    p.nbr = d->nbr; p.nbr_stride = d->nbr_stride; p.d_mout = d->d_mout; p.mout_cap = d->mout_cap;
+    p.nbr = d->nbr; p.nbr_stride = d->nbr_stride; p.d_mout = d->d_mout; p.mout_cap = d->mout_cap; p.row_perm = d->row_perm;
     p.nchunks = (d->c1 + d->c2 + tc::KC - 1) / tc::KC;
     int stages = tc::MAX_STAGES;
     while (stages > 1 && tc::smem_bytes(d->cout, stages) > 227 * 1024) --stages;
     p.stages = stages;
-    p.tmem_cols = d->cout <= 32 ? 32 : d->cout <= 64 ? 64 : d->cout <= 128 ? 128 : 256;
+    const int half = d->cout <= 32 ? 32 : d->cout <= 64 ? 64 : d->cout <= 128 ? 128 : 256;
+    p.tot_col = half;                          // [0, cout): MMA accumulator, [half, half + cout): running total
+    p.tmem_cols = 2 * half;
+    const int steps_per_offset = 3 * ((d->c1 + d->c2 + 15) / 16);
+    p.group = std::max(1, tc::STEP_BUDGET / steps_per_offset);
     p.io[0] = d->io[0]; p.io[1] = d->io[d->npass > 1 ? 1 : 0];
     const size_t smem = tc::smem_bytes(d->cout, stages);
     static size_t configured = 0;

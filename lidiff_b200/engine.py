@@ -20,6 +20,7 @@ order):
 from __future__ import annotations
 
 import math
+from collections import ChainMap
 
 import numpy as np
 import torch
@@ -107,6 +108,13 @@ class Geometry:
         # [9:13] transposed (out level 0..3); [13:18] row counts per level (copied from d_n)
         self.pairs = torch.zeros(18, dtype=torch.int64, device=dev)
         self.map_id = {}
+        # execution order of the output rows of each map (rows bucketed by neighbour mask, lb2_row_order)
+        self.row_mask = torch.zeros(n_cap, **i32)
+        self.ro_scratch = torch.zeros(64, dtype=torch.int64, device=dev)
+        self.perm3 = [torch.zeros(n_cap, **i32) for _ in range(levels)]
+        self.perm_dn = [None] + [torch.zeros(n_cap, **i32) for _ in range(levels - 1)]
+        self.perm_up = [torch.zeros(n_cap, **i32) for _ in range(levels - 1)] + [None] if with_up else None
+        self.perm_of = {}
 
     def build(self, coords_f: torch.Tensor, n_points: int):
         """coords_f (n_points,4) fp32 integer-valued [b,x,y,z] -> all levels and maps (async)."""
@@ -115,16 +123,20 @@ class Geometry:
         for l in range(1, self.levels):
             h.unique_build(None, self.C[l - 1], self.d_n[l - 1], N, 1 << l, self.grid[l], self.C[l], self.inv[l], self.d_n[l], self.scratch)
         self.pairs.zero_()
+
+        def one(grid, l_out, ks, step, nbr, perm, slot):
+            h.kernel_map(grid, self.C[l_out], self.d_n[l_out], N, ks, step, nbr, N, self.pairs[slot:slot + 1], self.row_mask)
+            h.row_order(self.row_mask, self.d_n[l_out], N, ks ** 3, perm, self.ro_scratch)
+            self.map_id[nbr.data_ptr()] = slot
+            self.perm_of[nbr.data_ptr()] = perm
+
         for l in range(self.levels):
-            h.kernel_map(self.grid[l], self.C[l], self.d_n[l], N, 3, 1 << l, self.nbr3[l], N, self.pairs[l:l + 1])
-            self.map_id[self.nbr3[l].data_ptr()] = l
+            one(self.grid[l], l, 3, 1 << l, self.nbr3[l], self.perm3[l], l)
         for l in range(1, self.levels):
-            h.kernel_map(self.grid[l - 1], self.C[l], self.d_n[l], N, 2, 1 << (l - 1), self.nbr_dn[l], N, self.pairs[4 + l:5 + l])
-            self.map_id[self.nbr_dn[l].data_ptr()] = 4 + l
+            one(self.grid[l - 1], l, 2, 1 << (l - 1), self.nbr_dn[l], self.perm_dn[l], 4 + l)
         if self.nbr_up is not None:
             for l in range(self.levels - 1):
-                h.kernel_map(self.grid[l + 1], self.C[l], self.d_n[l], N, 2, -(1 << l), self.nbr_up[l], N, self.pairs[9 + l:10 + l])
-                self.map_id[self.nbr_up[l].data_ptr()] = 9 + l
+                one(self.grid[l + 1], l, 2, -(1 << l), self.nbr_up[l], self.perm_up[l], 9 + l)
 
     def voxel_mean(self, feats, n_points, out):
         self.h.voxel_mean(feats, self.inv[0], n_points, feats.shape[1], self.d_n[0], self.n_cap, out, self.counts)
@@ -163,7 +175,10 @@ class DenoiseEngine:
             self.lat_2.append(Linear(sd_diff, f"latemp_{g}.2", dev))
         self.head = (Linear(sd_diff, "last.0", dev), Linear(sd_diff, "last.2", dev))
         self._bufs = {}
+        self.use_row_order = True
+        self._perm_lookup = {}
         self.geom = Geometry(h, self.N, with_up=True)
+        self._perm_lookup = self.geom.perm_of
         self.geom_cond = None
         self.part_cap = 0
         # optional instrumentation (bench.py): per-conv CUDA events + layer inventory + pair-count history
@@ -256,6 +271,8 @@ class DenoiseEngine:
         d.nbr_stride = nbr.stride(0) if nbr is not None else cap
         d.d_mout = d_m.data_ptr() if d_m is not None else None
         d.mout_cap, d.npass = cap, npass
+        perm = self._perm_lookup.get(nbr.data_ptr()) if (nbr is not None and self.use_row_order) else None
+        d.row_perm = perm.data_ptr() if perm is not None else None
         sel = lambda t, p: None if t is None else t[min(p, t.shape[0] - 1)].data_ptr()
         for p in range(npass):
             gt = gi = None
@@ -359,6 +376,7 @@ class DenoiseEngine:
         pts = scan.to(device=dev, dtype=torch.float32).contiguous()
         if self.geom_cond is None or self.geom_cond.n_cap != N:
             self.geom_cond = Geometry(self.h, N, with_up=False)
+            self._perm_lookup = ChainMap(self.geom.perm_of, self.geom_cond.perm_of)
         coords = self.buf("cond.coords", (N, 4))
         coords[:, 0] = 0
         self.h.quantize(pts, self.resolution, self.div_mode, self.buf("cond.q", (N, 3)))
@@ -369,7 +387,7 @@ class DenoiseEngine:
         g.voxel_mean(pts, N, F0[0])
         skips, _ = self._encoder(self.enc, g, F0, 1, "cenc")
         self.part_F = skips[4][0]                                      # (N cap, 256), rows valid < d_n[4]
-        self.part_C, self.part_dn = g.C[4], g.d_n[4]
+        self.part_C, self.part_dn, self.part_grid = g.C[4], g.d_n[4], g.grid[4]
         self.part_cap = N
         self.A_cond = self._part_A(self.part_F, N, self.part_dn, "c")
 
@@ -387,7 +405,7 @@ class DenoiseEngine:
         nn = []
         for l in range(5):
             ix = self.buf(f"nn{l}", (N,), torch.int32)
-            h.nn_match(g.C[l], g.d_n[l], N, self.part_C, self.part_dn, self.part_cap, 0, ix)
+            h.nn_match_grid(g.C[l], g.d_n[l], N, self.part_C, self.part_dn, self.part_cap, self.part_grid, 16, 4, ix)
             nn.append(ix)
         tabs_c = self._gate_tables(self.A_cond, self.part_cap, self.part_dn, i, "c")
         gates = [[(tabs_c[k], nn[GATE_LEVEL[k]]), (self.table_u[k][i:i + 1], None)] for k in range(8)]

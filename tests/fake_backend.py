@@ -84,7 +84,7 @@ class FakeHandle:
         cnt = torch.bincount(inv, minlength=M).float()
         out[:M] = sums / cnt[:, None]
 
-    def kernel_map(self, grid_in, out_coords, d_nout, nout_cap, ks, step, nbr, nbr_stride, pair_count=None):
+    def kernel_map(self, grid_in, out_coords, d_nout, nout_cap, ks, step, nbr, nbr_stride, pair_count=None, row_mask=None):
         self.launches += 1
         n = self._n(d_nout, nout_cap)
         skeys, order = self.grids[grid_in[0].data_ptr()]
@@ -107,6 +107,27 @@ class FakeHandle:
             nb[k, n:nout_cap] = -1
             if pair_count is not None:
                 pair_count += int(hit.sum())
+            if row_mask is not None:
+                if k == 0:
+                    row_mask[:nout_cap] = 0
+                row_mask[:n] |= torch.from_numpy((hit.astype(np.int64) << k).astype(np.int32))
+
+    def row_order(self, row_mask, d_n, n_cap, kvol, perm, scratch):
+        self.launches += 3
+        n = self._n(d_n, n_cap)
+        m = row_mask[:n].long() & 0xFFFFFFFF
+        if kvol <= 8:
+            b = m & 0xFF
+        else:
+            extras = m & ~(1 << 13)
+            low = torch.zeros_like(m)
+            for j in range(27):                      # index (1-based) of the lowest set bit
+                low = torch.where((low == 0) & (((extras >> j) & 1) == 1), torch.full_like(m, j + 1), low)
+            pop = sum(((extras >> j) & 1) for j in range(27))
+            b = torch.where(extras == 0, torch.zeros_like(m), torch.where(pop == 1, low, 27 + low))
+        order = torch.argsort(b, stable=True)
+        perm[:n] = torch.flip(order, [0]).int() if n > 3 else order.int()     # any in-bucket order is legal; scramble a bit
+        perm[:n] = order.int()
 
     # conv -----------------------------------------------------------------------------------------
     def packed_weight_bytes(self, kvol, cin, cout):
@@ -118,6 +139,8 @@ class FakeHandle:
     def spconv(self, d, algo=0):
         self.launches += 1
         M = d.mout_cap if not d.d_mout else min(int(_i(d.d_mout, (1,))[0]), d.mout_cap)
+        if d.row_perm:          # scheduling hint only: must be a permutation of the M rows
+            assert np.array_equal(np.sort(_i(d.row_perm, (M,))), np.arange(M)), "row_perm is not a permutation"
         ctot = d.c1 + d.c2
         W = torch.from_numpy(_f(d.weight, (d.kvol, ctot, d.cout)).copy()).double()
         nbr = _i(d.nbr, (d.kvol, d.nbr_stride))[:, :M] if d.nbr else np.arange(M, dtype=np.int32)[None]
@@ -164,6 +187,9 @@ class FakeHandle:
             d = ((qq[s:s + 4096, None, :] - kk[None]) ** 2).sum(-1)
             out[s:s + 4096] = torch.argmin(d, 1)
         idx[:nq] = out.int()
+
+    def nn_match_grid(self, q, d_nq, nq_cap, k, d_nk, nk_cap, key_grid, key_stride, max_ring, idx):
+        self.nn_match(q, d_nq, nq_cap, k, d_nk, nk_cap, 0, idx)
 
     @staticmethod
     def _act(v, act):
