@@ -193,14 +193,14 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- roofline of the dominant kernel (sparse convolution) ---------------------------------------------------
     peaks = measured_peaks()
-    log = eng.layer_log_done
-    nconv = len(log)
+    layers = eng.layer_log_done
+    nconv = len(layers)
     geo = eng.geom
     flops = bytes_gs = 0.0
     conv_ms = sum(a.elapsed_time(b) for a, b, _ in conv_events)
-    tc_ms = sum(a.elapsed_time(b) for a, b, j in conv_events if log[j % nconv]["tc"])
+    tc_ms = sum(a.elapsed_time(b) for a, b, j in conv_events if layers[j % nconv]["tc"])
     for step in range(K):
-        for ent in log:
+        for ent in layers:
             if ent["map"] is not None and ent["map"] in geo.map_id:
                 pairs = pair_hist[step, geo.map_id[ent["map"]]]
             else:                                   # 1x1 conv on the identity map: pairs = rows of that level

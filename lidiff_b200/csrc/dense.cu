@@ -75,12 +75,13 @@ __global__ void __launch_bounds__(256) k_nn_match_grid(const int4* __restrict__ 
     const int nq = d_nq ? min(*d_nq, nq_cap) : nq_cap;
     const int nk = d_nk ? min(*d_nk, nk_cap) : nk_cap;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nq) return;
-    const int4 c = __ldg(q + i);
+    if (blockIdx.x * blockDim.x >= nq) return;                       // whole block idle
+    const bool live = i < nq;
+    const int4 c = live ? __ldg(q + i) : make_int4(0, 0, 0, 0);
     const int cx = floor_div(c.y + ks / 2, ks), cy = floor_div(c.z + ks / 2, ks), cz = floor_div(c.w + ks / 2, ks);
     unsigned long long best = ~0ull;
     int best_j = 0x7fffffff;
-    bool settled = false;
+    bool settled = !live;
     for (int r = 0; r <= max_ring && !settled; ++r) {
         for (int dz = -r; dz <= r; ++dz) {
             for (int dy = -r; dy <= r; ++dy) {
@@ -101,17 +102,32 @@ __global__ void __launch_bounds__(256) k_nn_match_grid(const int4* __restrict__ 
         const unsigned long long bound = (unsigned long long)ks * ks * (2 * r + 1) * (2 * r + 1);   // 4 * ks^2 (r+0.5)^2
         settled = (best != ~0ull) && (4ull * best < bound);
     }
-    if (!settled) {        // far from every key: exhaustive scan (identical tie rule)
-        best = ~0ull; best_j = 0;
-        for (int j = 0; j < nk; ++j) {
+    // queries far from every key: exhaustive scan, one query at a time with the whole warp (identical tie rule)
+    unsigned pending = __ballot_sync(0xffffffffu, !settled);
+    const int lane = threadIdx.x & 31;
+    while (pending) {
+        const int src = __ffs(pending) - 1;
+        pending &= pending - 1;
+        const int qb = __shfl_sync(0xffffffffu, c.x, src), qx = __shfl_sync(0xffffffffu, c.y, src);
+        const int qy = __shfl_sync(0xffffffffu, c.z, src), qz = __shfl_sync(0xffffffffu, c.w, src);
+        unsigned long long bd = ~0ull;
+        int bj = 0x7fffffff;
+        for (int j = lane; j < nk; j += 32) {
             const int4 kc = __ldg(keys + j);
-            const long long ex = c.y - kc.y, ey = c.z - kc.z, ez = c.w - kc.w;
+            const long long ex = qx - kc.y, ey = qy - kc.z, ez = qz - kc.w;
             unsigned long long d = (unsigned long long)(ex * ex + ey * ey + ez * ez);
-            if (c.x != kc.x) d += 1ull << 62;
-            if (d < best) { best = d; best_j = j; }
+            if (qb != kc.x) d += 1ull << 62;
+            if (d < bd) { bd = d; bj = j; }                          // ascending j per lane: lowest index kept
         }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long od = __shfl_xor_sync(0xffffffffu, bd, o);
+            const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+            if (od < bd || (od == bd && oj < bj)) { bd = od; bj = oj; }
+        }
+        if (lane == src) best_j = (bj == 0x7fffffff) ? 0 : bj;
     }
-    idx[i] = best_j;
+    if (live) idx[i] = best_j;
 }
 
 extern "C" int lb2_nn_match_grid(void* handle, void* stream, const int32_t* q_coords, const int32_t* d_nq, int32_t nq_cap,

@@ -110,7 +110,7 @@ class Geometry:
         self.map_id = {}
         # execution order of the output rows of each map (rows bucketed by neighbour mask, lb2_row_order)
         self.row_mask = torch.zeros(n_cap, **i32)
-        self.ro_scratch = torch.zeros(64, dtype=torch.int64, device=dev)
+        self.ro_scratch = torch.zeros(256, **i32)            # lb2_row_order_scratch_bytes() = 1 KB
         self.perm3 = [torch.zeros(n_cap, **i32) for _ in range(levels)]
         self.perm_dn = [None] + [torch.zeros(n_cap, **i32) for _ in range(levels - 1)]
         self.perm_up = [torch.zeros(n_cap, **i32) for _ in range(levels - 1)] + [None] if with_up else None

@@ -311,7 +311,10 @@ def test_row_order_is_a_permutation_and_does_not_change_results(spread, algo):
             d.io[0] = ConvIO(x.data_ptr(), None, None, out.data_ptr(), None, None, None)
             h.spconv(d, algo)
             outs.append(out[:M].clone())
-        assert torch.equal(outs[0], outs[1]), "row order changed the result"
+        if algo == 1:
+            assert torch.equal(outs[0], outs[1]), "row order changed the result"
+        else:   # the tensor-core variant groups a tile's offsets for its two-level accumulation: same sum, other rounding
+            assert rel_err(outs[1], outs[0]) < 1e-5, "row order changed the result"
 
 
 def test_nn_match_grid_equals_brute_force():
