@@ -39,7 +39,7 @@ constexpr int PACK_HEADER = 256;     // bytes: [0] max|W| bits, [1] 2^-k output 
 constexpr int NUM_PRODUCER = 128;
 constexpr int THREADS = 320;
 constexpr int DRAIN_WARP0 = 6;        // warps 6..9
-constexpr int STEP_BUDGET = 128;      // max chained MMA steps per TMEM accumulation group
+constexpr int STEP_BUDGET = 64;       // max chained MMA steps per TMEM accumulation group
 constexpr int MAX_KVOL = 27;
 constexpr int MAX_STAGES = 4;
 
@@ -55,6 +55,7 @@ struct Params {
     int mout_cap;
     const int* row_perm;
     int stages, nchunks, tmem_cols, tot_col, group;     // tot_col: TMEM column of the running total; group: offsets per drain
+    int nbuf, acc_stride;                               // ping-pong accumulators (2 when 3 regions fit in TMEM) and their column pitch
     lb2_conv_io io[2];
 };
 
@@ -167,19 +168,18 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc(const Params p) {
     unsigned char* tail = gen + (size_t)p.stages * stage_bytes;
     int* idx_s = reinterpret_cast<int*>(tail);                       // [kvol][BM]
     uint64_t* bars = reinterpret_cast<uint64_t*>(tail + MAX_KVOL * BM * sizeof(int));
-    uint32_t* misc = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + 2);   // [0] tmem base, [1] offset mask
+    uint32_t* misc = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + 4);   // [0] tmem base, [1] offset mask
     int* row_s = reinterpret_cast<int*>(misc + 4);                             // [BM] output row of each tile slot
     const uint32_t bar0 = smem_u32(bars);
     auto full_a = [&](int s) { return bar0 + 8u * s; };
     auto full_b = [&](int s) { return bar0 + 8u * (MAX_STAGES + s); };
     auto empty = [&](int s) { return bar0 + 8u * (2 * MAX_STAGES + s); };
-    const uint32_t acc_full = bar0 + 8u * (3 * MAX_STAGES);        // MMA group complete  -> drain warps
-    const uint32_t acc_empty = bar0 + 8u * (3 * MAX_STAGES + 1);   // drain complete      -> MMA issuer
+    auto acc_full = [&](int b) { return bar0 + 8u * (3 * MAX_STAGES + b); };        // MMA group complete -> drain warps
+    auto acc_empty = [&](int b) { return bar0 + 8u * (3 * MAX_STAGES + 2 + b); };   // drain complete     -> MMA issuer
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(full_a(s), NUM_PRODUCER); mbar_init(full_b(s), 1); mbar_init(empty(s), 1); }
-        mbar_init(acc_full, 1);
-        mbar_init(acc_empty, 128);
+        for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), 128); }
         misc[1] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -261,8 +261,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc(const Params p) {
             const uint32_t idesc = make_idesc(p.cout);
             int it = 0, in_group = 0, group_idx = 0, off_idx = 0;
             for (uint32_t km = kmask; km; km &= km - 1, ++off_idx) {
-                if (in_group == 0 && group_idx > 0) {             // previous group must be drained before TMEM is overwritten
-                    mbar_wait(acc_empty, (group_idx - 1) & 1);
+                const int buf = group_idx % p.nbuf;
+                const uint32_t tmem_acc = tmem_d + (uint32_t)(buf * p.acc_stride);
+                if (in_group == 0 && group_idx >= p.nbuf) {       // this accumulator's previous group must be drained first
+                    mbar_wait(acc_empty(buf), ((group_idx / p.nbuf) - 1) & 1);
                     tc_fence_after();
                 }
                 for (int c = 0; c < p.nchunks; ++c, ++it) {
@@ -277,14 +279,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc(const Params p) {
                     for (int ks = 0; ks < ksteps; ++ks) {
                         const uint64_t dah = make_desc(a_hi + ks * 32), dal = make_desc(a_lo + ks * 32);
                         const uint64_t dbh = make_desc(b_hi + ks * 32), dbl = make_desc(b_lo + ks * 32);
-                        umma(tmem_d, dah, dbh, idesc, (in_group | c | ks) ? 1u : 0u);   // first MMA of a group overwrites
-                        umma(tmem_d, dal, dbh, idesc, 1);
-                        umma(tmem_d, dah, dbl, idesc, 1);
+                        umma(tmem_acc, dah, dbh, idesc, (in_group | c | ks) ? 1u : 0u);   // first MMA of a group overwrites
+                        umma(tmem_acc, dal, dbh, idesc, 1);
+                        umma(tmem_acc, dah, dbl, idesc, 1);
                     }
                     umma_commit(empty(s));            // frees the stage when these MMAs have read it
                 }
                 if (++in_group == p.group || off_idx == n_off - 1) {
-                    umma_commit(acc_full);            // partial sum of this group complete -> drain warps
+                    umma_commit(acc_full(buf));       // partial sum of this group complete -> drain warps
                     in_group = 0;
                     ++group_idx;
                 }
@@ -301,15 +303,17 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc(const Params p) {
         const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;
         for (int g = 0; g < max(n_groups, 1); ++g) {
             const bool last = g >= n_groups - 1;
+            const int buf = g % p.nbuf;
+            const uint32_t acc_col = (uint32_t)(buf * p.acc_stride);
             if (n_groups > 0) {
-                mbar_wait(acc_full, g & 1);
+                mbar_wait(acc_full(buf), (g / p.nbuf) & 1);
                 tc_fence_after();
             }
             for (int c0 = 0; c0 < p.cout; c0 += 32) {
                 float acc[32];
                 if (n_groups > 0) {
                     uint32_t r[32];
-                    tmem_ld32(tmem_d + lane_base + (uint32_t)c0, r);
+                    tmem_ld32(tmem_d + lane_base + acc_col + (uint32_t)c0, r);
                     if (g > 0) {
                         uint32_t t[32];
                         tmem_ld32(tmem_d + lane_base + (uint32_t)(p.tot_col + c0), t);
@@ -363,7 +367,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc(const Params p) {
             if (!last) {
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 tc_fence_before();
-                mbar_arrive(acc_empty);            // accumulator may be overwritten by the next group
+                mbar_arrive(acc_empty(buf));       // this accumulator may be overwritten by its next group
             }
         }
     } else if (warp == 5) {
@@ -443,7 +447,7 @@ static bool shape_ok(int c1, int c2, int cout, int kvol) {
 }
 
 static size_t smem_bytes(int cout, int stages) {
-    return 1024 + (size_t)stages * (2 * A_TILE + 2 * (size_t)cout * 128) + MAX_KVOL * BM * sizeof(int) + (3 * MAX_STAGES + 2) * 8 + 16 + BM * sizeof(int);
+    return 1024 + (size_t)stages * (2 * A_TILE + 2 * (size_t)cout * 128) + MAX_KVOL * BM * sizeof(int) + (3 * MAX_STAGES + 4) * 8 + 16 + BM * sizeof(int);
 }
 
 }  // namespace tc
@@ -482,8 +486,10 @@ int lb2_spconv_tc_launch(Lb2Handle* h, cudaStream_t s, const lb2_conv_desc* d) {
     while (stages > 1 && tc::smem_bytes(d->cout, stages) > 227 * 1024) --stages;
     p.stages = stages;
     const int half = d->cout <= 32 ? 32 : d->cout <= 64 ? 64 : d->cout <= 128 ? 128 : 256;
-    p.tot_col = half;                          // [0, cout): MMA accumulator, [half, half + cout): running total
-    p.tmem_cols = 2 * half;
+    p.nbuf = half <= 128 ? 2 : 1;              // ping-pong accumulators when acc0 | acc1 | total fit in 512 columns
+    p.acc_stride = half;
+    p.tot_col = p.nbuf * half;                 // [b*half, +cout): MMA accumulators, [tot_col, +cout): running fp32 total
+    { int need = (p.nbuf + 1) * half; p.tmem_cols = 32; while (p.tmem_cols < need) p.tmem_cols <<= 1; }
     const int steps_per_offset = 3 * ((d->c1 + d->c2 + 15) / 16);
     p.group = std::max(1, tc::STEP_BUDGET / steps_per_offset);
     p.io[0] = d->io[0]; p.io[1] = d->io[d->npass > 1 ? 1 : 0];

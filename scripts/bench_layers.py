@@ -40,16 +40,16 @@ def main():
     for l in range(5):
         nb = geo.nbr3[l][:, :sizes[l]]
         print(f"  L{l}: pairs {(nb >= 0).sum().item()}  avg nbrs {(nb >= 0).sum().item() / max(sizes[l], 1):.2f}")
-    print(f"{'layer':34s} {'pairs':>9s} {'GF(2p)':>8s} {'ffma ms':>8s} {'tc ms':>8s} {'tc TF/s useful':>14s} {'tc TF/s dense-eq':>16s}")
+    print(f"{'layer':34s} {'pairs':>9s} {'GF(2p)':>8s} {'ffma ms':>8s} {'tc ms':>8s} {'tc+perm':>8s} {'TF/s useful':>12s} {'TF/s dense-eq':>14s}")
     for (lvl, c1, c2, cout, kind) in LAYERS:
         if kind == "3":
-            nbr, kvol, M = geo.nbr3[lvl], 27, sizes[lvl]
+            nbr, kvol, M, perm = geo.nbr3[lvl], 27, sizes[lvl], geo.perm3[lvl]
         elif kind == "dn":
-            nbr, kvol, M = geo.nbr_dn[lvl], 8, sizes[lvl]
+            nbr, kvol, M, perm = geo.nbr_dn[lvl], 8, sizes[lvl], geo.perm_dn[lvl]
         elif kind == "up":
-            nbr, kvol, M = geo.nbr_up[lvl], 8, sizes[lvl]
+            nbr, kvol, M, perm = geo.nbr_up[lvl], 8, sizes[lvl], geo.perm_up[lvl]
         else:
-            nbr, kvol, M = None, 1, sizes[lvl]
+            nbr, kvol, M, perm = None, 1, sizes[lvl], None
         pairs = int((nbr[:, :M] >= 0).sum().item()) if nbr is not None else M
         W = torch.randn(kvol, c1 + c2, cout, device=dev) * 0.05
         Wp = h.pack_weights(W)
@@ -67,28 +67,30 @@ def main():
         for p in range(2):
             d.io[p] = ConvIO(a[p].data_ptr(), b[p].data_ptr() if b is not None else None, None, out[p].data_ptr(), None, None, None)
         res = {}
-        for algo in (1, 2):
-            if algo == 2 and Wp is None:
+        for algo in (1, 2, 3):
+            d.row_perm = perm.data_ptr() if (algo == 3 and perm is not None) else None
+            algo_ = 2 if algo == 3 else algo
+            if algo_ == 2 and Wp is None:
                 res[algo] = float("nan")
                 continue
             for _ in range(2):
-                h.spconv(d, algo)
+                h.spconv(d, algo_)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(5):
-                h.spconv(d, algo)
+                h.spconv(d, algo_)
             e1.record()
             torch.cuda.synchronize()
             res[algo] = e0.elapsed_time(e1) / 5
             if algo == 1:
                 ref = out.clone()
-            else:
+            elif algo == 2:
                 err = ((out[:, :M] - ref[:, :M]).abs().max() / ref[:, :M].abs().max()).item()
         gf = 2 * 2.0 * pairs * (c1 + c2) * cout / 1e9
         dense = 2 * 2.0 * M * kvol * (c1 + c2) * cout / 1e9
         name = f"L{lvl} {c1}+{c2}->{cout} k{kvol} {kind}"
         tcms = res[2]
-        print(f"{name:34s} {pairs:9d} {gf:8.1f} {res[1]:8.3f} {tcms:8.3f} {gf / tcms:14.1f} {dense / tcms:16.1f}   maxrel {err:.1e}")
+        print(f"{name:34s} {pairs:9d} {gf:8.1f} {res[1]:8.3f} {tcms:8.3f} {res[3]:8.3f} {gf / res[3]:12.1f} {dense / tcms:14.1f}   maxrel {err:.1e}")
 
 
 if __name__ == "__main__":
