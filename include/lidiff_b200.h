@@ -104,8 +104,8 @@ int lb2_row_order(void* h, void* stream, const uint32_t* row_mask, const int32_t
  * MinkowskiBatchNorm(eval)/MinkowskiReLU/residual-add/ME.cat/gate-multiply that follow it in
  * minkunet.py:13-80,431,464 fused as prologue/epilogue.
  *   out[o] = epi( sum_k [in1|in2][nbr[k][o]] @ W[k] )
- *   epi(y) = relu?( y*scale + shift + residual[o] );  optional second output out_gated = epi(y) *
- *   gate_table[gate_idx[o]].
+ *   epi(y) = relu?( (y + pre_add[o])*scale + shift + residual[o] );  optional second output
+ *   out_gated = epi(y) * gate_table[gate_idx[o]].
  * Up to two guidance passes (conditional/unconditional) share W and the map. */
 typedef struct {
     const float*   in1;         /* (rows_in, c1) */
@@ -115,6 +115,8 @@ typedef struct {
     const float*   gate_table;  /* (rows_g, cout) or NULL */
     const int32_t* gate_idx;    /* (m) or NULL (=> row 0 broadcast) */
     float*         out_gated;   /* (m, cout) or NULL */
+    const float*   pre_add;     /* (m, cout) or NULL: added to the raw convolution sum before the affine
+                                   (the off-centre part computed by lb2_spconv_scatter) */
 } lb2_conv_io;
 
 typedef struct {
@@ -137,6 +139,33 @@ typedef struct {
 #define LB2_ALGO_FFMA  1    /* fp32 CUDA-core implicit GEMM */
 #define LB2_ALGO_TC    2    /* tcgen05 FP16x3 split-precision implicit GEMM (needs weight_packed) */
 int lb2_spconv_forward(void* h, void* stream, const lb2_conv_desc* d, int algo);
+
+/* The same convolution in gather-GEMM-scatter form (what ME's GPU backend does per kernel offset) for levels
+ * with few neighbours per voxel: lb2_pair_list compacts the (in,out) pairs of a kernel map per offset (optionally
+ * skipping one offset, e.g. the centre 13 of a 3^3 kernel), lb2_spconv_scatter computes
+ *     out[pair_out] += in[pair_in] @ W[k]        (tensor cores, FP16x3, fp32 red.add; order-dependent last bits)
+ * into a buffer that lb2_spconv_forward then consumes as `pre_add` while it handles the skipped offset with
+ * kvol = 1.  Cout <= 128 and packed W[k] <= 96 KB (weight-stationary). */
+typedef struct {
+    int32_t        c1, c2, cout, kvol;
+    const void*    weight_packed;
+    const int32_t* pair_in;        /* [pairs] input row  */
+    const int32_t* pair_out;       /* [pairs] output row */
+    const int32_t* koff;           /* [kvol+1] first pair of each offset */
+    const int32_t* tile_off;       /* [kvol+1] first 128-pair tile of each offset */
+    int32_t        npass;
+    const float*   in1[2];
+    const float*   in2[2];
+    float*         out[2];         /* (m, cout) accumulation buffers */
+    const int32_t* d_zero_rows;    /* rows to clear first: device count (or NULL => zero_rows_cap) */
+    int32_t        zero_rows_cap;  /* 0 = caller already cleared `out` */
+} lb2_scatter_desc;
+size_t lb2_pair_list_scratch_bytes(void);
+int lb2_pair_list(void* h, void* stream, const int32_t* nbr, int64_t nbr_stride, const int32_t* d_nout,
+                  int32_t nout_cap, int32_t kvol, int32_t skip_k, int32_t* pair_in, int32_t* pair_out,
+                  int32_t* koff, int32_t* tile_off, void* scratch);
+int lb2_spconv_scatter_supported(int32_t c1, int32_t c2, int32_t cout, int32_t kvol);
+int lb2_spconv_scatter(void* h, void* stream, const lb2_scatter_desc* d);
 
 /* FP16 hi/lo split (power-of-two pre-scaled) + UMMA shared-memory image of a (kvol, cin, cout) fp32 weight
  * for LB2_ALGO_TC. */

@@ -23,7 +23,7 @@ class Grid(C.Structure):
 
 class ConvIO(C.Structure):
     _fields_ = [("in1", C.c_void_p), ("in2", C.c_void_p), ("residual", C.c_void_p), ("out", C.c_void_p),
-                ("gate_table", C.c_void_p), ("gate_idx", C.c_void_p), ("out_gated", C.c_void_p)]
+                ("gate_table", C.c_void_p), ("gate_idx", C.c_void_p), ("out_gated", C.c_void_p), ("pre_add", C.c_void_p)]
 
 
 class ConvDesc(C.Structure):
@@ -33,6 +33,14 @@ class ConvDesc(C.Structure):
                 ("nbr", C.c_void_p), ("nbr_stride", C.c_int64),
                 ("d_mout", C.c_void_p), ("mout_cap", C.c_int32), ("row_perm", C.c_void_p), ("npass", C.c_int32),
                 ("io", ConvIO * 2)]
+
+
+class ScatterDesc(C.Structure):
+    _fields_ = [("c1", C.c_int32), ("c2", C.c_int32), ("cout", C.c_int32), ("kvol", C.c_int32),
+                ("weight_packed", C.c_void_p), ("pair_in", C.c_void_p), ("pair_out", C.c_void_p),
+                ("koff", C.c_void_p), ("tile_off", C.c_void_p), ("npass", C.c_int32),
+                ("in1", C.c_void_p * 2), ("in2", C.c_void_p * 2), ("out", C.c_void_p * 2),
+                ("d_zero_rows", C.c_void_p), ("zero_rows_cap", C.c_int32)]
 
 
 class DpmCoef(C.Structure):
@@ -48,6 +56,7 @@ EXPORTS = [
     "lb2_spconv_forward", "lb2_packed_weight_bytes", "lb2_pack_weights", "lb2_nn_match", "lb2_linear",
     "lb2_gate_mul", "lb2_gather_rows", "lb2_guidance_dpm_step", "lb2_farthest_point_sample",
     "lb2_row_order", "lb2_row_order_scratch_bytes", "lb2_nn_match_grid",
+    "lb2_pair_list", "lb2_pair_list_scratch_bytes", "lb2_spconv_scatter", "lb2_spconv_scatter_supported",
 ]
 
 
@@ -91,6 +100,10 @@ class Lib:
         d.lb2_spconv_forward.argtypes = [vp, vp, C.POINTER(ConvDesc), C.c_int]
         d.lb2_pack_weights.argtypes = [vp, vp, vp, i32, i32, i32, vp]
         d.lb2_nn_match.argtypes = [vp, vp, vp, vp, i32, vp, vp, i32, i32, vp]
+        d.lb2_pair_list.argtypes = [vp, vp, vp, i64, vp, i32, i32, i32, vp, vp, vp, vp, vp]
+        d.lb2_pair_list_scratch_bytes.restype = C.c_size_t
+        d.lb2_spconv_scatter.argtypes = [vp, vp, C.POINTER(ScatterDesc)]
+        d.lb2_spconv_scatter_supported.argtypes = [i32, i32, i32, i32]
         d.lb2_nn_match_grid.argtypes = [vp, vp, vp, vp, i32, vp, vp, i32, Grid, i32, i32, vp]
         d.lb2_linear.argtypes = [vp, vp, vp, i64, vp, vp, vp, i64, i32, vp, i32, i32, i32, vp, i64,
                                  vp, i32]
@@ -176,6 +189,16 @@ class Handle:
     # -- conv ----------------------------------------------------------------------------------------
     def spconv(self, desc: ConvDesc, algo: int = ALGO_AUTO):
         self._check(self.dll.lb2_spconv_forward(self.hp, self._stream(), C.byref(desc), int(algo)), "lb2_spconv_forward")
+
+    def pair_list(self, nbr, nbr_stride, d_nout, nout_cap, kvol, skip_k, pair_in, pair_out, koff, tile_off, scratch):
+        self._check(self.dll.lb2_pair_list(self.hp, self._stream(), _ptr(nbr), int(nbr_stride), _ptr(d_nout), int(nout_cap), int(kvol), int(skip_k),
+                                           _ptr(pair_in), _ptr(pair_out), _ptr(koff), _ptr(tile_off), _ptr(scratch)), "lb2_pair_list")
+
+    def scatter_supported(self, c1, c2, cout, kvol) -> bool:
+        return bool(self.dll.lb2_spconv_scatter_supported(int(c1), int(c2), int(cout), int(kvol)))
+
+    def spconv_scatter(self, desc: "ScatterDesc"):
+        self._check(self.dll.lb2_spconv_scatter(self.hp, self._stream(), C.byref(desc)), "lb2_spconv_scatter")
 
     def packed_weight_bytes(self, kvol, cin, cout) -> int:
         return int(self.dll.lb2_packed_weight_bytes(kvol, cin, cout))

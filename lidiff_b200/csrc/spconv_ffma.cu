@@ -147,6 +147,7 @@ __global__ void __launch_bounds__(FF_THREADS) k_spconv_ffma(const FfmaParams p) 
             const int col = n0 + tx * 4 + j;
             if (col >= p.cout) continue;
             float y = acc[i][j];
+            if (io.pre_add) y += __ldg(io.pre_add + ro + col);
             if (p.scale) y = fmaf(y, __ldg(p.scale + col), __ldg(p.shift + col));
             if (io.residual) y += __ldg(io.residual + ro + col);
             if (p.relu) y = fmaxf(y, 0.f);
