@@ -26,7 +26,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import ConvDesc, ConvIO, DpmCoef
+from ._lib import ConvDesc, ConvIO, DpmCoef, ScatterDesc
 from .scheduler import DPMSolverMultistepScheduler
 
 GATE_NAMES = ("stage1", "stage2", "stage3", "stage4", "up1", "up2", "up3", "up4")
@@ -51,6 +51,11 @@ class ConvLayer:
         else:
             self.scale = self.shift = None
         self.Wp = h.pack_weights(self.W)          # tensor-core image (None when unsupported)
+        # gather-GEMM-scatter split of a 3^3 conv: off-centre offsets through lb2_spconv_scatter, centre as a 1x1 conv
+        self.Wc = self.Wpc = None
+        if self.kvol == 27 and self.Wp is not None and h.scatter_supported(self.cin, 0, self.cout, 27):
+            self.Wc = self.W[13:14].contiguous()
+            self.Wpc = h.pack_weights(self.Wc)
 
 
 class Linear:
@@ -91,9 +96,9 @@ class Geometry:
     """Device-resident coordinate manager of one point set: 5 levels of voxel rows + hash grids, the
     3^3 / 2^3-stride / transposed kernel maps, all at a fixed row capacity, row counts on device."""
 
-    def __init__(self, h, n_cap: int, with_up: bool = True, levels: int = 5):
+    def __init__(self, h, n_cap: int, with_up: bool = True, levels: int = 5, use_pairs: bool = True):
         dev = h.device
-        self.h, self.n_cap, self.levels = h, n_cap, levels
+        self.h, self.n_cap, self.levels, self.use_pairs = h, n_cap, levels, use_pairs
         i32 = dict(dtype=torch.int32, device=dev)
         self.C = [torch.zeros((n_cap, 4), **i32) for _ in range(levels)]
         self.d_n = [torch.zeros(1, **i32) for _ in range(levels)]
@@ -115,6 +120,14 @@ class Geometry:
         self.perm_dn = [None] + [torch.zeros(n_cap, **i32) for _ in range(levels - 1)]
         self.perm_up = [torch.zeros(n_cap, **i32) for _ in range(levels - 1)] + [None] if with_up else None
         self.perm_of = {}
+        # per-offset (in,out) pair lists of the 3^3 maps of the sparse levels (gather-GEMM-scatter form)
+        self.pair_levels = min(3, levels)
+        self.pairs_of = {}
+        self.pl_scratch = torch.zeros(64, **i32)
+        self.pair_in = [torch.zeros(26 * n_cap, **i32) for _ in range(self.pair_levels)]
+        self.pair_out = [torch.zeros(26 * n_cap, **i32) for _ in range(self.pair_levels)]
+        self.koff = [torch.zeros(28, **i32) for _ in range(self.pair_levels)]
+        self.tile_off = [torch.zeros(28, **i32) for _ in range(self.pair_levels)]
 
     def build(self, coords_f: torch.Tensor, n_points: int):
         """coords_f (n_points,4) fp32 integer-valued [b,x,y,z] -> all levels and maps (async)."""
@@ -132,6 +145,9 @@ class Geometry:
 
         for l in range(self.levels):
             one(self.grid[l], l, 3, 1 << l, self.nbr3[l], self.perm3[l], l)
+            if l < self.pair_levels and self.use_pairs:
+                h.pair_list(self.nbr3[l], N, self.d_n[l], N, 27, 13, self.pair_in[l], self.pair_out[l], self.koff[l], self.tile_off[l], self.pl_scratch)
+                self.pairs_of[self.nbr3[l].data_ptr()] = l
         for l in range(1, self.levels):
             one(self.grid[l - 1], l, 2, 1 << (l - 1), self.nbr_dn[l], self.perm_dn[l], 4 + l)
         if self.nbr_up is not None:
@@ -143,6 +159,17 @@ class Geometry:
 
     def sizes(self):
         return [int(d.item()) for d in self.d_n]
+
+
+class _PairLookup:
+    """nbr tensor pointer -> (geometry, level) for maps that have pair lists (the step geometry only)"""
+
+    def __init__(self, geom):
+        self.geom = geom
+
+    def get(self, ptr):
+        l = self.geom.pairs_of.get(ptr)
+        return None if l is None else (self.geom, l)
 
 
 class DenoiseEngine:
@@ -176,9 +203,11 @@ class DenoiseEngine:
         self.head = (Linear(sd_diff, "last.0", dev), Linear(sd_diff, "last.2", dev))
         self._bufs = {}
         self.use_row_order = True
+        self.use_scatter = True
         self._perm_lookup = {}
         self.geom = Geometry(h, self.N, with_up=True)
         self._perm_lookup = self.geom.perm_of
+        self._pairs_lookup = _PairLookup(self.geom)
         self.geom_cond = None
         self.part_cap = 0
         # optional instrumentation (bench.py): per-conv CUDA events + layer inventory + pair-count history
@@ -261,37 +290,64 @@ class DenoiseEngine:
         d.c1 = in1.shape[-1]
         d.c2 = in2.shape[-1] if in2 is not None else 0
         assert d.c1 + d.c2 == lay.cin, (d.c1, d.c2, lay.cin)
-        d.cout, d.kvol = lay.cout, lay.kvol
-        d.weight = lay.W.data_ptr()
-        d.weight_packed = lay.Wp.data_ptr() if lay.Wp is not None else None
+        sel = lambda t, p: None if t is None else t[min(p, t.shape[0] - 1)].data_ptr()
+        pre = None
+        geom_lvl = self._pairs_lookup.get(nbr.data_ptr()) if (nbr is not None and self.use_scatter and lay.Wpc is not None
+                                                               and self.conv_algo != _lib.ALGO_FFMA) else None
+        if geom_lvl is not None:
+            # off-centre pairs: out_scatter[pair_out] += in[pair_in] @ W[k]; the centre runs below as a 1x1 conv with pre_add
+            g, l = geom_lvl
+            pre = self.buf(f"scatter.{lay.cout}", (2, cap, lay.cout))
+            sd = ScatterDesc()
+            sd.c1, sd.c2, sd.cout, sd.kvol = d.c1, d.c2, lay.cout, 27
+            sd.weight_packed = lay.Wp.data_ptr()
+            sd.pair_in, sd.pair_out = g.pair_in[l].data_ptr(), g.pair_out[l].data_ptr()
+            sd.koff, sd.tile_off = g.koff[l].data_ptr(), g.tile_off[l].data_ptr()
+            sd.npass = npass
+            for p in range(npass):
+                sd.in1[p], sd.in2[p], sd.out[p] = sel(in1, p), sel(in2, p), pre[p].data_ptr()
+            sd.d_zero_rows, sd.zero_rows_cap = d_m.data_ptr(), cap
+        else:
+            sd = None
+        map_ptr = nbr.data_ptr() if nbr is not None else None
+        d.cout, d.kvol = lay.cout, (1 if pre is not None else lay.kvol)
+        d.weight = (lay.Wc if pre is not None else lay.W).data_ptr()
+        wp = lay.Wpc if pre is not None else lay.Wp
+        d.weight_packed = wp.data_ptr() if wp is not None else None
         d.scale = lay.scale.data_ptr() if lay.scale is not None else None
         d.shift = lay.shift.data_ptr() if lay.shift is not None else None
         d.relu = 1 if relu else 0
+        if pre is not None:
+            nbr = None                               # centre offset = identity map
         d.nbr = nbr.data_ptr() if nbr is not None else None
         d.nbr_stride = nbr.stride(0) if nbr is not None else cap
         d.d_mout = d_m.data_ptr() if d_m is not None else None
         d.mout_cap, d.npass = cap, npass
         perm = self._perm_lookup.get(nbr.data_ptr()) if (nbr is not None and self.use_row_order) else None
         d.row_perm = perm.data_ptr() if perm is not None else None
-        sel = lambda t, p: None if t is None else t[min(p, t.shape[0] - 1)].data_ptr()
         for p in range(npass):
             gt = gi = None
             if gate is not None:
                 gt = gate[p][0].data_ptr()
                 gi = gate[p][1].data_ptr() if gate[p][1] is not None else None
-            d.io[p] = ConvIO(sel(in1, p), sel(in2, p), sel(residual, p), sel(out, p), gt, gi, sel(out_gated, p))
+            d.io[p] = ConvIO(sel(in1, p), sel(in2, p), sel(residual, p), sel(out, p), gt, gi, sel(out_gated, p),
+                             pre[p].data_ptr() if pre is not None else None)
         if self.layer_log is not None:
-            self.layer_log.append(dict(map=(nbr.data_ptr() if nbr is not None else None), d_m=d_m.data_ptr() if d_m is not None else None,
+            self.layer_log.append(dict(map=map_ptr, d_m=d_m.data_ptr() if d_m is not None else None,
                                        cin=lay.cin, cout=lay.cout, kvol=lay.kvol, npass=npass,
                                        tc=bool(lay.Wp is not None and self.conv_algo != _lib.ALGO_FFMA)))
         if self.conv_events is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
+            if sd is not None:
+                self.h.spconv_scatter(sd)
             self.h.spconv(d, self.conv_algo)
             e1.record()
             self.conv_events.append((e0, e1, self._conv_counter))
             self._conv_counter += 1
         else:
+            if sd is not None:
+                self.h.spconv_scatter(sd)
             self.h.spconv(d, self.conv_algo)
 
     def _res(self, L, p, geom, lvl, in1, in2, npass, tag, gate=None, want_plain=True):
@@ -354,7 +410,7 @@ class DenoiseEngine:
         """x_uncond = all-zero points -> one voxel at the origin with zero feature; its encoder output is
         a single 256-vector that depends on the weights only (App. D.2).  Gate rows for all steps."""
         dev = self.device
-        g1 = Geometry(self.h, 16, with_up=False)
+        g1 = Geometry(self.h, 16, with_up=False, use_pairs=False)
         coords = torch.zeros((16, 4), dtype=torch.float32, device=dev)
         g1.build(coords, 16)
         F0 = torch.zeros((1, 16, 3), device=dev)
@@ -375,7 +431,7 @@ class DenoiseEngine:
         dev, N = self.device, scan.shape[0]
         pts = scan.to(device=dev, dtype=torch.float32).contiguous()
         if self.geom_cond is None or self.geom_cond.n_cap != N:
-            self.geom_cond = Geometry(self.h, N, with_up=False)
+            self.geom_cond = Geometry(self.h, N, with_up=False, use_pairs=False)
             self._perm_lookup = ChainMap(self.geom.perm_of, self.geom_cond.perm_of)
         coords = self.buf("cond.coords", (N, 4))
         coords[:, 0] = 0

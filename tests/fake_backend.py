@@ -33,6 +33,7 @@ class FakeHandle:
         self.grids = {}
         self.launches = 0
         self.status = 0
+        self.emulate_tc = False
 
     # plumbing -------------------------------------------------------------------------------------
     def launch_count(self):
@@ -134,7 +135,52 @@ class FakeHandle:
         return 0
 
     def pack_weights(self, w):
-        return None
+        # the fake keeps the fp32 weight itself as the "packed" image so the scatter path can be exercised
+        return w.detach().clone() if self.emulate_tc else None
+
+    def scatter_supported(self, c1, c2, cout, kvol):
+        return self.emulate_tc and (c1 + c2) % 16 == 0 and cout % 32 == 0 and cout <= 128
+
+    def pair_list(self, nbr, nbr_stride, d_nout, nout_cap, kvol, skip_k, pair_in, pair_out, koff, tile_off, scratch):
+        self.launches += 3
+        n = self._n(d_nout, nout_cap)
+        nb = nbr.reshape(-1)[: kvol * nbr_stride].view(kvol, nbr_stride)[:, :n]
+        a = t = 0
+        for k in range(kvol):
+            koff[k], tile_off[k] = a, t
+            if k == skip_k:
+                continue
+            o = torch.nonzero(nb[k] >= 0)[:, 0]
+            o = o[torch.randperm(o.shape[0])]                       # order inside an offset is unspecified
+            pair_in[a:a + o.shape[0]] = nb[k][o]
+            pair_out[a:a + o.shape[0]] = o.int()
+            a += o.shape[0]
+            t += (o.shape[0] + 127) // 128
+        koff[kvol], tile_off[kvol] = a, t
+
+    def spconv_scatter(self, d):
+        self.launches += 2
+        koff = _i(d.koff, (d.kvol + 1,))
+        P = int(koff[d.kvol])
+        pin, pout = _i(d.pair_in, (P,)).astype(np.int64), _i(d.pair_out, (P,)).astype(np.int64)
+        ctot = d.c1 + d.c2
+        W = torch.from_numpy(_f(d.weight_packed, (d.kvol, ctot, d.cout)).copy()).double()
+        M = min(int(_i(d.d_zero_rows, (1,))[0]), d.zero_rows_cap) if d.d_zero_rows else d.zero_rows_cap
+        rows_in = int(pin.max()) + 1 if P else 0
+        for p in range(d.npass):
+            out = _f(d.out[p], (M, d.cout))
+            if d.zero_rows_cap > 0:
+                out[:] = 0
+            x = torch.from_numpy(_f(d.in1[p], (rows_in, d.c1)).copy())
+            if d.c2:
+                x = torch.cat([x, torch.from_numpy(_f(d.in2[p], (rows_in, d.c2)).copy())], 1)
+            x = x.double()
+            acc = torch.from_numpy(out.copy()).double()
+            for k in range(d.kvol):
+                a, b = int(koff[k]), int(koff[k + 1])
+                if b > a:
+                    acc.index_add_(0, torch.from_numpy(pout[a:b]), x[torch.from_numpy(pin[a:b])] @ W[k])
+            out[:] = acc.float().numpy()
 
     def spconv(self, d, algo=0):
         self.launches += 1
@@ -156,6 +202,8 @@ class FakeHandle:
                 o = np.nonzero(nbr[k] >= 0)[0]
                 if o.size:
                     y[torch.from_numpy(o)] += x[torch.from_numpy(nbr[k][o].astype(np.int64))] @ W[k]
+            if io.pre_add:
+                y = y + torch.from_numpy(_f(io.pre_add, (M, d.cout)).copy()).double()
             if d.scale:
                 y = y * torch.from_numpy(_f(d.scale, (d.cout,)).copy()).double() + torch.from_numpy(_f(d.shift, (d.cout,)).copy()).double()
             if io.residual:
@@ -254,10 +302,11 @@ class FakeHandle:
         out_idx[:n_samples] = torch.from_numpy(sel.astype(np.int32))
 
 
-def install(monkeypatch):
+def install(monkeypatch, emulate_tc=False):
     """route the product's handle lookup to the CPU fake (host-logic tests only)"""
     from lidiff_b200 import _lib, me
     h = FakeHandle()
+    h.emulate_tc = emulate_tc
     monkeypatch.setattr(_lib, "get_handle", lambda device=None: h)
     monkeypatch.setattr(me, "_require_cuda", lambda t, what: None)
     return h

@@ -341,3 +341,65 @@ def test_nn_match_grid_equals_brute_force():
     assert torch.equal(a, b)
     ref = ome.match_part_to_full(q[:5000].cpu(), keys.cpu())
     assert torch.equal(a[:5000].long().cpu(), ref)
+
+
+@pytest.mark.parametrize("c1,c2,cout,lvl,spread", [(32, 0, 32, 0, 1.0), (96, 32, 96, 1, 0.3), (128, 64, 128, 2, 0.3), (64, 0, 64, 2, 1.0), (128, 0, 128, 0, 0.05)])
+def test_scatter_split_equals_output_stationary_conv(c1, c2, cout, lvl, spread):
+    """gather-GEMM-scatter (off-centre pairs) + centre 1x1 conv with pre_add == the plain 3^3 convolution, two passes"""
+    from lidiff_b200 import _lib
+    from lidiff_b200._lib import ConvDesc, ConvIO, ScatterDesc
+    from lidiff_b200.engine import Geometry
+    h = H()
+    pts, coords = random_field(60_000, spread, 23)
+    N = coords.shape[0]
+    g = Geometry(h, N)
+    g.build(coords.to(DEV).contiguous(), N)
+    M = g.sizes()[lvl]
+    koff = g.koff[lvl].cpu().numpy()
+    nbr = g.nbr3[lvl][:, :M].cpu().numpy()
+    # pair lists: same pair sets as the neighbour table, centre skipped
+    pin, pout = g.pair_in[lvl].cpu().numpy(), g.pair_out[lvl].cpu().numpy()
+    for k in range(27):
+        got = set(zip(pin[koff[k]:koff[k + 1]].tolist(), pout[koff[k]:koff[k + 1]].tolist()))
+        o = np.nonzero(nbr[k] >= 0)[0]
+        ref = set() if k == 13 else set(zip(nbr[k][o].tolist(), o.tolist()))
+        assert got == ref, k
+    gen = torch.Generator().manual_seed(c1 + cout)
+    ctot = c1 + c2
+    W = (torch.randn(27, ctot, cout, generator=gen) / np.sqrt(ctot * 27)).to(DEV)
+    A = torch.randn(2, N, c1, generator=gen).to(DEV)
+    B = torch.randn(2, N, c2, generator=gen).to(DEV) if c2 else None
+    sc_, sh_ = (torch.rand(cout, generator=gen) + 0.5).to(DEV), torch.randn(cout, generator=gen).to(DEV)
+    Wp, Wc = h.pack_weights(W), W[13:14].contiguous()
+    Wpc = h.pack_weights(Wc)
+
+    def conv(kvol, weight, packed, nbr_t, pre, out):
+        d = ConvDesc()
+        d.c1, d.c2, d.cout, d.kvol = c1, c2, cout, kvol
+        d.weight, d.weight_packed = weight.data_ptr(), packed.data_ptr()
+        d.scale, d.shift, d.relu = sc_.data_ptr(), sh_.data_ptr(), 1
+        d.nbr = nbr_t.data_ptr() if nbr_t is not None else None
+        d.nbr_stride, d.d_mout, d.mout_cap, d.npass = N, g.d_n[lvl].data_ptr(), N, 2
+        for p in range(2):
+            d.io[p] = ConvIO(A[p].data_ptr(), B[p].data_ptr() if B is not None else None, None, out[p].data_ptr(), None, None, None,
+                             pre[p].data_ptr() if pre is not None else None)
+        h.spconv(d, _lib.ALGO_TC)
+
+    ref = torch.zeros(2, N, cout, device=DEV)
+    conv(27, W, Wp, g.nbr3[lvl], None, ref)
+    pre = torch.full((2, N, cout), 7.0, device=DEV)               # must be cleared by the kernel
+    sd = ScatterDesc()
+    sd.c1, sd.c2, sd.cout, sd.kvol, sd.npass = c1, c2, cout, 27, 2
+    sd.weight_packed = Wp.data_ptr()
+    sd.pair_in, sd.pair_out = g.pair_in[lvl].data_ptr(), g.pair_out[lvl].data_ptr()
+    sd.koff, sd.tile_off = g.koff[lvl].data_ptr(), g.tile_off[lvl].data_ptr()
+    for p in range(2):
+        sd.in1[p], sd.in2[p], sd.out[p] = A[p].data_ptr(), (B[p].data_ptr() if B is not None else None), pre[p].data_ptr()
+    sd.d_zero_rows, sd.zero_rows_cap = g.d_n[lvl].data_ptr(), N
+    assert h.scatter_supported(c1, c2, cout, 27)
+    h.spconv_scatter(sd)
+    out = torch.zeros(2, N, cout, device=DEV)
+    conv(1, Wc, Wpc, None, pre, out)
+    e = rel_err(out[:, :M], ref[:, :M])
+    print(f"scatter split {c1}+{c2}->{cout} L{lvl}: pairs {koff[27]}, rel err vs output-stationary {e:.2e}")
+    assert e < 2e-5

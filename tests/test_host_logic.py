@@ -41,8 +41,9 @@ def test_operator_surface_networks_match_oracle(tiny, monkeypatch):
     assert rel_err(r_got, r_ref) < 1e-4
 
 
-def test_engine_orchestration_matches_oracle(tiny, monkeypatch):
-    h = fake_backend.install(monkeypatch)
+@pytest.mark.parametrize("emulate_tc", [False, True], ids=["plain", "scatter_split"])
+def test_engine_orchestration_matches_oracle(tiny, monkeypatch, emulate_tc):
+    h = fake_backend.install(monkeypatch, emulate_tc=emulate_tc)
     from lidiff_b200.engine import DenoiseEngine
     scan, sds = tiny["scan"], tiny["sds"]
     N = scan.shape[1]
