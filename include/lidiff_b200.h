@@ -117,6 +117,13 @@ typedef struct {
     float*         out_gated;   /* (m, cout) or NULL */
     const float*   pre_add;     /* (m, cout) or NULL: added to the raw convolution sum before the affine
                                    (the off-centre part computed by lb2_spconv_scatter) */
+    /* optional fp16 "split" companions (row = [C halfs hi | C halfs lo], x ~= hi + lo; same 4C bytes as fp32):
+       inputs let the tensor-core kernels gather with cp.async instead of converting in registers,
+       outputs are written by the epilogue next to the fp32 tensors. */
+    const void*    in1_h;       /* (rows_in, 2*c1) fp16 or NULL */
+    const void*    in2_h;       /* (rows_in, 2*c2) fp16 or NULL */
+    void*          out_h;       /* (m, 2*cout) fp16 or NULL */
+    void*          out_gated_h; /* (m, 2*cout) fp16 or NULL */
 } lb2_conv_io;
 
 typedef struct {
@@ -156,6 +163,8 @@ typedef struct {
     int32_t        npass;
     const float*   in1[2];
     const float*   in2[2];
+    const void*    in1_h[2];       /* fp16 split companions of in1 / in2 (or NULL), see lb2_conv_io */
+    const void*    in2_h[2];
     float*         out[2];         /* (m, cout) accumulation buffers */
     const int32_t* d_zero_rows;    /* rows to clear first: device count (or NULL => zero_rows_cap) */
     int32_t        zero_rows_cap;  /* 0 = caller already cleared `out` */
@@ -196,9 +205,10 @@ int lb2_linear(void* h, void* stream, const float* x, int64_t ldx, const float* 
                int32_t n_in, int32_t n_out, int32_t act, float* y, int64_t ldy,
                const float* prebias, int32_t pre_act);
 
-/* x * w row-gather multiply (`x0*w0`, minkunet.py:431...): out[r] = x[r] * table[idx ? idx[r] : 0] */
+/* x * w row-gather multiply (`x0*w0`, minkunet.py:431...): out[r] = x[r] * table[idx ? idx[r] : 0];
+ * out_h: optional fp16 split companion of out (see lb2_conv_io). */
 int lb2_gate_mul(void* h, void* stream, const float* x, const float* table, const int32_t* idx,
-                 const int32_t* d_m, int32_t m_cap, int32_t c, float* out);
+                 const int32_t* d_m, int32_t m_cap, int32_t c, float* out, void* out_h);
 
 /* out[i] = src[idx[i]]  (SparseTensor.slice / x_part.F[match], minkunet.py:418,497) */
 int lb2_gather_rows(void* h, void* stream, const float* src, const int32_t* idx, int32_t n, int32_t c,

@@ -23,7 +23,8 @@ class Grid(C.Structure):
 
 class ConvIO(C.Structure):
     _fields_ = [("in1", C.c_void_p), ("in2", C.c_void_p), ("residual", C.c_void_p), ("out", C.c_void_p),
-                ("gate_table", C.c_void_p), ("gate_idx", C.c_void_p), ("out_gated", C.c_void_p), ("pre_add", C.c_void_p)]
+                ("gate_table", C.c_void_p), ("gate_idx", C.c_void_p), ("out_gated", C.c_void_p), ("pre_add", C.c_void_p),
+                ("in1_h", C.c_void_p), ("in2_h", C.c_void_p), ("out_h", C.c_void_p), ("out_gated_h", C.c_void_p)]
 
 
 class ConvDesc(C.Structure):
@@ -39,7 +40,8 @@ class ScatterDesc(C.Structure):
     _fields_ = [("c1", C.c_int32), ("c2", C.c_int32), ("cout", C.c_int32), ("kvol", C.c_int32),
                 ("weight_packed", C.c_void_p), ("pair_in", C.c_void_p), ("pair_out", C.c_void_p),
                 ("koff", C.c_void_p), ("tile_off", C.c_void_p), ("npass", C.c_int32),
-                ("in1", C.c_void_p * 2), ("in2", C.c_void_p * 2), ("out", C.c_void_p * 2),
+                ("in1", C.c_void_p * 2), ("in2", C.c_void_p * 2), ("in1_h", C.c_void_p * 2), ("in2_h", C.c_void_p * 2),
+                ("out", C.c_void_p * 2),
                 ("d_zero_rows", C.c_void_p), ("zero_rows_cap", C.c_int32)]
 
 
@@ -107,7 +109,7 @@ class Lib:
         d.lb2_nn_match_grid.argtypes = [vp, vp, vp, vp, i32, vp, vp, i32, Grid, i32, i32, vp]
         d.lb2_linear.argtypes = [vp, vp, vp, i64, vp, vp, vp, i64, i32, vp, i32, i32, i32, vp, i64,
                                  vp, i32]
-        d.lb2_gate_mul.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, vp]
+        d.lb2_gate_mul.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, vp, vp]
         d.lb2_gather_rows.argtypes = [vp, vp, vp, vp, i32, i32, vp]
         d.lb2_guidance_dpm_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, DpmCoef, vp, vp, vp, vp]
         d.lb2_farthest_point_sample.argtypes = [vp, vp, vp, i32, i32, vp, vp]
@@ -225,8 +227,9 @@ class Handle:
         self._check(self.dll.lb2_linear(self.hp, self._stream(), _ptr(x), int(ldx), _ptr(w), _ptr(b), _ptr(addend), int(ld_add), int(m_cap),
                                         _ptr(d_m), int(n_in), int(n_out), int(act), _ptr(y), int(ldy), _ptr(prebias), int(pre_act)), "lb2_linear")
 
-    def gate_mul(self, x, table, idx, d_m, m_cap, c, out):
-        self._check(self.dll.lb2_gate_mul(self.hp, self._stream(), _ptr(x), _ptr(table), _ptr(idx), _ptr(d_m), int(m_cap), int(c), _ptr(out)), "lb2_gate_mul")
+    def gate_mul(self, x, table, idx, d_m, m_cap, c, out, out_h=None):
+        self._check(self.dll.lb2_gate_mul(self.hp, self._stream(), _ptr(x), _ptr(table), _ptr(idx), _ptr(d_m), int(m_cap), int(c), _ptr(out),
+                                          _ptr(out_h)), "lb2_gate_mul")
 
     def gather_rows(self, src, idx, n, c, out):
         self._check(self.dll.lb2_gather_rows(self.hp, self._stream(), _ptr(src), _ptr(idx), int(n), int(c), _ptr(out)), "lb2_gather_rows")

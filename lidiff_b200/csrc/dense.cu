@@ -7,6 +7,7 @@
 //   lb2_farthest_point_sample  open3d FPS (pipeline:97-99)
 #include "common.cuh"
 #include <float.h>
+#include "tc_common.cuh"
 
 // ---------------------------------------------------------------------------------------------------
 // nn_match: brute force, keys staged through shared memory, exact 64-bit integer distances
@@ -227,20 +228,27 @@ extern "C" int lb2_linear(void* handle, void* stream, const float* x, int64_t ld
 // gate multiply / row gather
 // ---------------------------------------------------------------------------------------------------
 __global__ void k_gate_mul(const float* __restrict__ x, const float* __restrict__ table, const int* __restrict__ idx,
-                           const int* __restrict__ d_m, int m_cap, int c, float* __restrict__ out) {
+                           const int* __restrict__ d_m, int m_cap, int c, float* __restrict__ out, __half* __restrict__ out_h) {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int M = d_m ? min(*d_m, m_cap) : m_cap;
     if (t >= (long long)M * c) return;
     const int r = (int)(t / c), j = (int)(t % c);
     const int g = idx ? __ldg(idx + r) : 0;
-    out[t] = x[t] * __ldg(table + (long long)g * c + j);
+    const float y = x[t] * __ldg(table + (long long)g * c + j);
+    out[t] = y;
+    if (out_h) {
+        __half hi, lo;
+        tc::split1(y, hi, lo);
+        out_h[(long long)r * 2 * c + j] = hi;
+        out_h[(long long)r * 2 * c + c + j] = lo;
+    }
 }
 
 extern "C" int lb2_gate_mul(void* handle, void* stream, const float* x, const float* table, const int32_t* idx,
-                            const int32_t* d_m, int32_t m_cap, int32_t c, float* out) {
+                            const int32_t* d_m, int32_t m_cap, int32_t c, float* out, void* out_h) {
     Lb2Handle* h = (Lb2Handle*)handle;
     LB2_REQUIRE(h, h && x && table && out && m_cap > 0 && c > 0, "gate_mul");
-    k_gate_mul<<<cdiv((long long)m_cap * c, 256), 256, 0, (cudaStream_t)stream>>>(x, table, idx, d_m, m_cap, c, out);
+    k_gate_mul<<<cdiv((long long)m_cap * c, 256), 256, 0, (cudaStream_t)stream>>>(x, table, idx, d_m, m_cap, c, out, (__half*)out_h);
     LB2_POST_LAUNCH(h, "k_gate_mul");
     return LB2_OK;
 }

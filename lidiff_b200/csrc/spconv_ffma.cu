@@ -11,6 +11,7 @@
 // Stands behind ME.MinkowskiConvolution / MinkowskiConvolutionTranspose forward
 // (/root/reference/lidiff/models/minkunet.py:17-24,36-42,53-74) — semantics SURVEY.md App. A.4/A.5.
 #include "common.cuh"
+#include "tc_common.cuh"
 
 #define FF_BM 64
 #define FF_BN 64
@@ -142,6 +143,7 @@ __global__ void __launch_bounds__(FF_THREADS) k_spconv_ffma(const FfmaParams p) 
         const long long ro = (long long)row * p.cout;
         const float* gate_row = nullptr;
         if (io.gate_table) gate_row = io.gate_table + (long long)(io.gate_idx ? __ldg(io.gate_idx + row) : 0) * p.cout;
+        float yv[4] = {0.f, 0.f, 0.f, 0.f}, gv[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int col = n0 + tx * 4 + j;
@@ -151,8 +153,14 @@ __global__ void __launch_bounds__(FF_THREADS) k_spconv_ffma(const FfmaParams p) 
             if (p.scale) y = fmaf(y, __ldg(p.scale + col), __ldg(p.shift + col));
             if (io.residual) y += __ldg(io.residual + ro + col);
             if (p.relu) y = fmaxf(y, 0.f);
+            yv[j] = y;
+            gv[j] = gate_row ? y * __ldg(gate_row + col) : y;
             if (io.out) io.out[ro + col] = y;
-            if (io.out_gated) io.out_gated[ro + col] = gate_row ? y * __ldg(gate_row + col) : y;
+            if (io.out_gated) io.out_gated[ro + col] = gv[j];
+        }
+        if (n0 + tx * 4 + 3 < p.cout) {         // fp16 split companions (only for cout % 4 == 0 layers)
+            if (io.out_h) tc::store_split4(io.out_h, row, p.cout, n0 + tx * 4, yv);
+            if (io.out_gated_h) tc::store_split4(io.out_gated_h, row, p.cout, n0 + tx * 4, gv);
         }
     }
 }

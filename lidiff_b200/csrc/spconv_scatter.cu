@@ -36,6 +36,8 @@ struct Params {
     const int* tile_off;    // [kvol+1]
     const float* in1[2];
     const float* in2[2];
+    const void* in1_h[2];
+    const void* in2_h[2];
     float* out[2];
     int acc_stride, tmem_cols;
 };
@@ -98,10 +100,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_scatter(const Params p) {
     if (warp < 4) {
         // =========================== A producers ===========================
         const int sub = threadIdx.x & 7, rbase = threadIdx.x >> 3;
-        int it = 0;
+        const int D = p.stages - 1;
+        int it = 0, arrived = 0;
+        bool any_h = false;
         for (int T = t_begin; T < t_end; ++T) {
             int pass, k, pbase, cnt;
             decode(T, pass, k, pbase, cnt);
+            const bool use_h = (p.in1_h[pass] != nullptr) && (p.c2 == 0 || p.in2_h[pass] != nullptr);
+            any_h |= use_h;
             int src[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) { const int r = rbase + 16 * j; src[j] = r < cnt ? __ldg(p.pair_in + pbase + r) : -1; }
@@ -109,38 +115,29 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_scatter(const Params p) {
                 const int s = it % p.stages;
                 mbar_wait(empty_a(s), ((it / p.stages) & 1) ^ 1);
                 unsigned char* a_hi = a_gen + (size_t)s * a_stage;
-                unsigned char* a_lo = a_hi + A_TILE;
+                const uint32_t a_hi_u = a_base + (uint32_t)s * a_stage;
                 const int ch = c * KC + sub * 8;
                 if (ch < ctot) {
                     const bool first = ch < p.c1;
-                    const float* srcp = first ? p.in1[pass] : p.in2[pass];
                     const int cw = first ? p.c1 : p.c2;
                     const int co = first ? ch : ch - p.c1;
-                    float4 va[8], vb[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        if (src[j] >= 0) {
-                            const float4* rp = reinterpret_cast<const float4*>(srcp + (long long)src[j] * cw + co);
-                            va[j] = __ldg(rp);
-                            vb[j] = __ldg(rp + 1);
-                        } else {
-                            va[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            vb[j] = va[j];
-                        }
-                    }
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        uint4 hi, lo;
-                        split8(va[j], vb[j], hi, lo);
-                        const uint32_t off = sw128(rbase + 16 * j, sub);
-                        *reinterpret_cast<uint4*>(a_hi + off) = hi;
-                        *reinterpret_cast<uint4*>(a_lo + off) = lo;
-                    }
+                    if (use_h) produce_a_split(reinterpret_cast<const __half*>(first ? p.in1_h[pass] : p.in2_h[pass]), cw, co, src, a_hi_u, a_hi_u + A_TILE, rbase, sub);
+                    else produce_a_f32(first ? p.in1[pass] : p.in2[pass], cw, co, src, a_hi, a_hi + A_TILE, rbase, sub);
                 }
-                fence_proxy_async();
-                mbar_arrive(full_a(s));
+                // one protocol for both paths: a cp.async group per stage (empty for the fp32 path), arrive D stages later
+                cp_async_commit();
+                if (it >= D) {
+                    cp_async_wait_dyn(D);
+                    fence_proxy_async();
+                    mbar_arrive(full_a(arrived % p.stages));
+                    ++arrived;
+                }
             }
         }
+        cp_async_wait<0>();
+        fence_proxy_async();
+        for (; arrived < it; ++arrived) mbar_arrive(full_a(arrived % p.stages));
+        (void)any_h;
     } else if (warp == 4) {
         // =========================== MMA issuer ===========================
         if (lane == 0) {
@@ -294,7 +291,7 @@ static bool shape_ok(int c1, int c2, int cout, int kvol) {
     if (kvol < 1 || kvol > MAX_KVOL || ctot % 16 || ctot < 16) return false;
     if (c2 > 0 && (c1 % 8 || c2 % 8)) return false;
     if (cout % 32 || cout < 32 || cout > 128) return false;
-    return smem_bytes(ctot, cout, 2) <= 227 * 1024;
+    return smem_bytes(ctot, cout, 2) <= 227 * 1024 - 256;
 }
 
 }  // namespace sc
@@ -337,9 +334,10 @@ extern "C" int lb2_spconv_scatter(void* handle, void* stream, const lb2_scatter_
         const int j = d->npass > 1 ? i : 0;
         LB2_REQUIRE(h, d->in1[j] && d->out[j] && ((d->c2 > 0) == (d->in2[j] != nullptr)), "spconv_scatter io");
         p.in1[i] = d->in1[j]; p.in2[i] = d->in2[j]; p.out[i] = d->out[j];
+        p.in1_h[i] = d->in1_h[j]; p.in2_h[i] = d->in2_h[j];
     }
     int stages = sc::MAX_STAGES;
-    while (stages > 2 && sc::smem_bytes(d->c1 + d->c2, d->cout, stages) > 227 * 1024) --stages;
+    while (stages > 2 && sc::smem_bytes(d->c1 + d->c2, d->cout, stages) > 227 * 1024 - 256) --stages;
     p.stages = stages;
     const int half = d->cout <= 32 ? 32 : d->cout <= 64 ? 64 : 128;
     p.acc_stride = half; p.tmem_cols = 2 * half;
@@ -351,7 +349,7 @@ extern "C" int lb2_spconv_scatter(void* handle, void* stream, const lb2_scatter_
     }
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(sc::k_spconv_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+        cudaError_t e = cudaFuncSetAttribute(sc::k_spconv_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024 - 256));   // 224 B of static smem
         if (e != cudaSuccess) return lb2_fail(h, LB2_ERR_CUDA, "k_spconv_scatter smem attribute: %s", cudaGetErrorString(e));
         configured = true;
     }

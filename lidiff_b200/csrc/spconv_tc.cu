@@ -120,46 +120,46 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc(const Params p) {
         // =========================== A producers ===========================
         const int sub = threadIdx.x & 7;           // 8-channel group inside the 64-channel chunk
         const int rbase = threadIdx.x >> 3;        // 0..15
-        int it = 0;
+        const bool use_h = (io.in1_h != nullptr) && (p.c2 == 0 || io.in2_h != nullptr);   // fp16 split inputs: cp.async gather
+        const int D = p.stages - 1;                // cp.async lookahead: stages still landing while the next is issued
+        int it = 0, arrived = 0;
         for (uint32_t km = kmask; km; km &= km - 1) {
             const int k = __ffs(km) - 1;
             const int* idxk = idx_s + k * BM;
+            int src[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) src[j] = idxk[rbase + 16 * j];
             for (int c = 0; c < p.nchunks; ++c, ++it) {
                 const int s = it % p.stages;
                 mbar_wait(empty(s), ((it / p.stages) & 1) ^ 1);
                 unsigned char* a_hi = gen + (size_t)s * stage_bytes;
-                unsigned char* a_lo = a_hi + A_TILE;
+                const uint32_t a_hi_u = base + (uint32_t)s * stage_bytes;
                 const int ch = c * KC + sub * 8;
                 if (ch < ctot) {
                     const bool first = ch < p.c1;
-                    const float* srcp = first ? io.in1 : io.in2;
                     const int cw = first ? p.c1 : p.c2;
                     const int co = first ? ch : ch - p.c1;
-                    float4 va[8], vb[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int src = idxk[rbase + 16 * j];
-                        if (src >= 0) {
-                            const float4* rp = reinterpret_cast<const float4*>(srcp + (long long)src * cw + co);
-                            va[j] = __ldg(rp);
-                            vb[j] = __ldg(rp + 1);
-                        } else {
-                            va[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            vb[j] = va[j];
-                        }
-                    }
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        uint4 hi, lo;
-                        split8(va[j], vb[j], hi, lo);
-                        const uint32_t off = sw128(rbase + 16 * j, sub);
-                        *reinterpret_cast<uint4*>(a_hi + off) = hi;
-                        *reinterpret_cast<uint4*>(a_lo + off) = lo;
-                    }
+                    if (use_h) produce_a_split(reinterpret_cast<const __half*>(first ? io.in1_h : io.in2_h), cw, co, src, a_hi_u, a_hi_u + A_TILE, rbase, sub);
+                    else produce_a_f32(first ? io.in1 : io.in2, cw, co, src, a_hi, a_hi + A_TILE, rbase, sub);
                 }
-                fence_proxy_async();
-                mbar_arrive(full_a(s));
+                if (use_h) {
+                    cp_async_commit();
+                    if (it >= D) {                 // the copies of iteration it-D have landed
+                        cp_async_wait_dyn(D);
+                        fence_proxy_async();
+                        mbar_arrive(full_a(arrived % p.stages));
+                        ++arrived;
+                    }
+                } else {
+                    fence_proxy_async();
+                    mbar_arrive(full_a(s));
+                }
             }
+        }
+        if (use_h) {
+            cp_async_wait<0>();
+            fence_proxy_async();
+            for (; arrived < it; ++arrived) mbar_arrive(full_a(arrived % p.stages));
         }
     } else if (warp == 4) {
         // =========================== MMA issuer ===========================
@@ -263,12 +263,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc(const Params p) {
                             for (int j = 0; j < 4; ++j) y[j] = fmaxf(y[j], 0.f);
                         }
                         if (io.out) *reinterpret_cast<float4*>(io.out + ro + c0 + q * 4) = make_float4(y[0], y[1], y[2], y[3]);
-                        if (io.out_gated) {
+                        if (io.out_h) store_split4(io.out_h, row, p.cout, c0 + q * 4, y);
+                        if (io.out_gated || io.out_gated_h) {
                             if (gate_row) {
                                 const float4 gg = __ldg(reinterpret_cast<const float4*>(gate_row + c0 + q * 4));
                                 y[0] *= gg.x; y[1] *= gg.y; y[2] *= gg.z; y[3] *= gg.w;
                             }
-                            *reinterpret_cast<float4*>(io.out_gated + ro + c0 + q * 4) = make_float4(y[0], y[1], y[2], y[3]);
+                            if (io.out_gated) *reinterpret_cast<float4*>(io.out_gated + ro + c0 + q * 4) = make_float4(y[0], y[1], y[2], y[3]);
+                            if (io.out_gated_h) store_split4(io.out_gated_h, row, p.cout, c0 + q * 4, y);
                         }
                     }
                 }

@@ -102,4 +102,74 @@ __device__ __forceinline__ void split8(const float4& a, const float4& b, uint4& 
 }
 
 
+// fp32 -> (hi, lo) fp16 pair, saturating at the fp16 range
+__device__ __forceinline__ void split1(float x, __half& hi, __half& lo) {
+    x = fminf(fmaxf(x, -65504.f), 65504.f);
+    hi = __float2half_rn(x);
+    lo = __float2half_rn(x - __half2float(hi));
+}
+// write 4 consecutive channels of a split companion row: hi halfs at row[col], lo halfs at row[c + col]
+__device__ __forceinline__ void store_split4(void* base, long long row, int c, int col, const float (&y)[4]) {
+    __half h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) split1(y[j], h[j], l[j]);
+    __half* rp = reinterpret_cast<__half*>(base) + row * 2 * c;
+    uint2 uh, ul;
+    uh.x = (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16);
+    uh.y = (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16);
+    ul.x = (uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16);
+    ul.y = (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16);
+    *reinterpret_cast<uint2*>(rp + col) = uh;
+    *reinterpret_cast<uint2*>(rp + c + col) = ul;
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void cp_async_wait_dyn(int n) {      // n in [0, 3]
+    if (n <= 0) cp_async_wait<0>(); else if (n == 1) cp_async_wait<1>(); else if (n == 2) cp_async_wait<2>(); else cp_async_wait<3>();
+}
+
+// One producer thread's share of an A stage (8 rows x one 8-channel group, hi and lo tile).
+//  * split path  (src_h != nullptr): two 16-byte cp.async per row straight into the swizzled image (zero-fill for
+//    missing rows); completion is tracked by the caller with commit/wait groups;
+//  * fp32 path: 2 x LDG.128 per row, hi/lo split in registers, 2 x STS.128.
+__device__ __forceinline__ void produce_a_split(const __half* __restrict__ src_h, int cw, int co, const int (&src)[8],
+                                                uint32_t a_hi, uint32_t a_lo, int rbase, int sub) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint32_t off = sw128(rbase + 16 * j, sub);
+        const bool ok = src[j] >= 0;
+        const __half* rp = src_h + (ok ? ((long long)src[j] * 2 * cw + co) : 0);
+        cp_async16(a_hi + off, rp, ok ? 16u : 0u);
+        cp_async16(a_lo + off, rp + (ok ? cw : 0), ok ? 16u : 0u);
+    }
+}
+__device__ __forceinline__ void produce_a_f32(const float* __restrict__ srcp, int cw, int co, const int (&src)[8],
+                                              unsigned char* a_hi, unsigned char* a_lo, int rbase, int sub) {
+    float4 va[8], vb[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        if (src[j] >= 0) {
+            const float4* rp = reinterpret_cast<const float4*>(srcp + (long long)src[j] * cw + co);
+            va[j] = __ldg(rp);
+            vb[j] = __ldg(rp + 1);
+        } else {
+            va[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            vb[j] = va[j];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        uint4 hi, lo;
+        split8(va[j], vb[j], hi, lo);
+        const uint32_t off = sw128(rbase + 16 * j, sub);
+        *reinterpret_cast<uint4*>(a_hi + off) = hi;
+        *reinterpret_cast<uint4*>(a_lo + off) = lo;
+    }
+}
+
 }  // namespace tc

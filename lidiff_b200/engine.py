@@ -204,6 +204,8 @@ class DenoiseEngine:
         self._bufs = {}
         self.use_row_order = True
         self.use_scatter = True
+        self.use_split = True            # fp16 hi/lo companions + cp.async gathers in the tensor-core kernels
+        self._h_of = {}
         self._perm_lookup = {}
         self.geom = Geometry(h, self.N, with_up=True)
         self._perm_lookup = self.geom.perm_of
@@ -235,6 +237,18 @@ class DenoiseEngine:
             t = torch.zeros(shape, dtype=dtype, device=self.device)
             self._bufs[name] = t
         return t
+
+    # ---- fp16 split companions of activations consumed by tensor-core convolutions ----------------------
+    def _companion(self, t: torch.Tensor, create: bool):
+        """(P, cap, 2C) fp16 buffer paired with the fp32 activation `t` (row = [hi | lo]); None when unused"""
+        if t is None or not self.use_split or self.conv_algo == _lib.ALGO_FFMA or t.shape[-1] % 8:
+            return None
+        key = t.data_ptr()
+        hbuf = self._h_of.get(key)
+        if hbuf is None and create:
+            hbuf = torch.zeros(tuple(t.shape[:-1]) + (2 * t.shape[-1],), dtype=torch.float16, device=self.device)
+            self._h_of[key] = hbuf
+        return hbuf
 
     # ---- small dense helpers ------------------------------------------------------------------------
     def _linear(self, x, lin: Linear, out, act=0, m_cap=None, d_m=None, prebias=None, pre_act=0, bias=True):
@@ -291,6 +305,8 @@ class DenoiseEngine:
         d.c2 = in2.shape[-1] if in2 is not None else 0
         assert d.c1 + d.c2 == lay.cin, (d.c1, d.c2, lay.cin)
         sel = lambda t, p: None if t is None else t[min(p, t.shape[0] - 1)].data_ptr()
+        in1_h, in2_h = self._companion(in1, False), self._companion(in2, False)
+        out_h, outg_h = self._companion(out, True), self._companion(out_gated, True)
         pre = None
         geom_lvl = self._pairs_lookup.get(nbr.data_ptr()) if (nbr is not None and self.use_scatter and lay.Wpc is not None
                                                                and self.conv_algo != _lib.ALGO_FFMA) else None
@@ -306,6 +322,7 @@ class DenoiseEngine:
             sd.npass = npass
             for p in range(npass):
                 sd.in1[p], sd.in2[p], sd.out[p] = sel(in1, p), sel(in2, p), pre[p].data_ptr()
+                sd.in1_h[p], sd.in2_h[p] = sel(in1_h, p), sel(in2_h, p)
             sd.d_zero_rows, sd.zero_rows_cap = d_m.data_ptr(), cap
         else:
             sd = None
@@ -331,7 +348,8 @@ class DenoiseEngine:
                 gt = gate[p][0].data_ptr()
                 gi = gate[p][1].data_ptr() if gate[p][1] is not None else None
             d.io[p] = ConvIO(sel(in1, p), sel(in2, p), sel(residual, p), sel(out, p), gt, gi, sel(out_gated, p),
-                             pre[p].data_ptr() if pre is not None else None)
+                             pre[p].data_ptr() if pre is not None else None,
+                             sel(in1_h, p), sel(in2_h, p), sel(out_h, p), sel(outg_h, p))
         if self.layer_log is not None:
             self.layer_log.append(dict(map=map_ptr, d_m=d_m.data_ptr() if d_m is not None else None,
                                        cin=lay.cin, cout=lay.cout, kvol=lay.kvol, npass=npass,
@@ -377,9 +395,10 @@ class DenoiseEngine:
         skips = [x0]
         if gates is not None:
             cur = self.buf(f"{tag}.x0g", (npass, cap, 32))
+            cur_h = self._companion(cur, True)
             for p in range(npass):
                 tb, ix = gates[0][p]
-                self.h.gate_mul(x0[0], tb, ix, geom.d_n[0], cap, 32, cur[p])
+                self.h.gate_mul(x0[0], tb, ix, geom.d_n[0], cap, 32, cur[p], cur_h[p] if cur_h is not None else None)
         else:
             cur = x0
         for n in range(1, 5):

@@ -256,7 +256,7 @@ class FakeHandle:
             v = v + torch.as_strided(addend, (M, n_out), (ld_add, 1)).double()
         torch.as_strided(y, (M, n_out), (ldy, 1)).copy_(self._act(v, act).float())
 
-    def gate_mul(self, x, table, idx, d_m, m_cap, c, out):
+    def gate_mul(self, x, table, idx, d_m, m_cap, c, out, out_h=None):
         self.launches += 1
         M = self._n(d_m, m_cap)
         g = table[idx[:M].long()] if idx is not None else table[0:1]

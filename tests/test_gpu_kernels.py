@@ -403,3 +403,50 @@ def test_scatter_split_equals_output_stationary_conv(c1, c2, cout, lvl, spread):
     e = rel_err(out[:, :M], ref[:, :M])
     print(f"scatter split {c1}+{c2}->{cout} L{lvl}: pairs {koff[27]}, rel err vs output-stationary {e:.2e}")
     assert e < 2e-5
+
+
+@pytest.mark.parametrize("c1,c2,cout", [(64, 0, 64), (96, 32, 96), (256, 128, 256)])
+def test_split_companion_inputs_give_identical_results(c1, c2, cout):
+    """fp16 hi/lo companions + cp.async gather == fp32 inputs split in registers (same rounding), and the epilogue's
+    out_h is the split of its fp32 output"""
+    from lidiff_b200 import _lib
+    from lidiff_b200._lib import ConvDesc, ConvIO
+    from lidiff_b200.engine import Geometry
+    h = H()
+    pts, coords = random_field(30_000, 0.4, 29)
+    N = coords.shape[0]
+    g = Geometry(h, N)
+    g.build(coords.to(DEV).contiguous(), N)
+    M = g.sizes()[0]
+    gen = torch.Generator().manual_seed(3)
+    W = (torch.randn(27, c1 + c2, cout, generator=gen) * 0.05).to(DEV)
+    Wp = h.pack_weights(W)
+    ones = torch.ones(1, max(c1, c2, 1), device=DEV)
+    xs, xh = [], []
+    for c in (c1, c2):
+        if c == 0:
+            xs.append(None); xh.append(None); continue
+        x = (torch.randn(N, c, generator=gen) * 3).to(DEV)
+        y, yh = torch.empty_like(x), torch.zeros(N, 2 * c, dtype=torch.float16, device=DEV)
+        h.gate_mul(x, ones[:, :c].contiguous(), None, None, N, c, y, yh)            # y = x * 1, yh = split(y)
+        assert torch.equal(y, x)
+        hi, lo = yh[:, :c].float(), yh[:, c:].float()
+        assert torch.equal(hi, x.half().float()) and (hi + lo - x).abs().max() <= 2e-6 * x.abs().max()
+        xs.append(x); xh.append(yh)
+    outs = []
+    for use_h in (False, True):
+        out = torch.zeros(N, cout, device=DEV)
+        out_h = torch.zeros(N, 2 * cout, dtype=torch.float16, device=DEV)
+        d = ConvDesc()
+        d.c1, d.c2, d.cout, d.kvol = c1, c2, cout, 27
+        d.weight, d.weight_packed = W.data_ptr(), Wp.data_ptr()
+        d.nbr, d.nbr_stride, d.d_mout, d.mout_cap, d.npass = g.nbr3[0].data_ptr(), N, g.d_n[0].data_ptr(), N, 1
+        d.io[0] = ConvIO(xs[0].data_ptr(), xs[1].data_ptr() if xs[1] is not None else None, None, out.data_ptr(), None, None, None, None,
+                         xh[0].data_ptr() if use_h else None, (xh[1].data_ptr() if (use_h and xh[1] is not None) else None),
+                         out_h.data_ptr(), None)
+        h.spconv(d, _lib.ALGO_TC)
+        outs.append((out[:M].clone(), out_h[:M].clone()))
+    assert torch.equal(outs[0][0], outs[1][0]), "cp.async split path differs from the register path"
+    o, oh = outs[1]
+    assert torch.equal(oh[:, :cout].float(), o.half().float())
+    assert (oh[:, :cout].float() + oh[:, cout:].float() - o).abs().max() <= 2e-6 * o.abs().max()
