@@ -211,9 +211,13 @@ def run_ours(args, rank, world, local_rank):
     n_launch = len(conv_events)
     avg_ms = conv_ms / max(n_launch, 1)
     achieved_tf = flops / n_launch / (avg_ms * 1e-3) / 1e12
-    roofline = {"kernel": "k_spconv_tc / k_spconv_ffma (sparse conv, all layers)", "bound": "tensor",
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_conv_dram_traffic.json")
+    if os.path.exists(tpath):                         # dram__bytes_read+write per conv launch from the committed ncu capture
+        traffic = json.load(open(tpath)).get("traffic_bytes_per_launch")
+    roofline = {"kernel": "k_spconv_tc (+k_spconv_scatter, k_spconv_ffma): sparse convolution, all layers", "bound": "tensor",
                 "achieved": round(achieved_tf, 2), "peak": peaks["tf"], "unit": "TFLOP/s", "frac": round(achieved_tf / peaks["tf"], 4),
-                "traffic": None, "peak_source": peaks["src"],
+                "traffic": traffic, "traffic_unit": "DRAM bytes per conv launch (ncu, profiles/r01_conv_dram_traffic.json)", "peak_source": peaks["src"],
                 "algorithmic_flops_per_launch": flops / n_launch, "avg_launch_ms": round(avg_ms, 4),
                 "conv_share_of_step": round(conv_ms / ms, 3), "tc_share_of_conv_time": round(tc_ms / max(conv_ms, 1e-9), 3),
                 "gather_scatter_model_GBps": round(bytes_gs / (conv_ms * 1e-3) / 1e9, 1), "hbm_peak_GBps": peaks["hbm_gbs"],

@@ -202,11 +202,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc(const Params p) {
     } else if (warp >= DRAIN_WARP0) {
         // =========================== drain + epilogue (two-level accumulation) ===========================
         const int q4 = warp & 3;                                   // TMEM lane quarter this warp may access
-        const int row = row_s[q4 * 32 + lane];
-        const long long ro = (long long)row * p.cout;
-        const float* gate_row = nullptr;
-        if (io.gate_table && row >= 0) gate_row = io.gate_table + (long long)(io.gate_idx ? __ldg(io.gate_idx + row) : 0) * p.cout;
         const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;
+        float* stage_c = reinterpret_cast<float*>(gen);            // [BM][pitch] fp32, reuses the (then idle) stage ring
+        const int pitch = p.cout + 4;                              // +4 floats: conflict-free 16-byte row writes
         for (int g = 0; g < max(n_groups, 1); ++g) {
             const bool last = g >= n_groups - 1;
             const int buf = g % p.nbuf;
@@ -240,45 +238,61 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc(const Params p) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) t[j] = __float_as_uint(acc[j]);
                     tmem_st32(tmem_d + lane_base + (uint32_t)(p.tot_col + c0), t);
-                } else if (row >= 0) {             // epilogue on the final sum
+                } else {                           // final sum -> shared-memory staging tile (the stage ring is idle now)
+                    float* srow = stage_c + (size_t)(q4 * 32 + lane) * pitch + c0;
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        float y[4];
-                        float4 pa = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (io.pre_add) pa = __ldg(reinterpret_cast<const float4*>(io.pre_add + ro + c0 + q * 4));
-                        const float pav[4] = {pa.x, pa.y, pa.z, pa.w};
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int col = c0 + q * 4 + j;
-                            float v = acc[q * 4 + j] * out_scale + pav[j];
-                            if (p.scale) v = fmaf(v, __ldg(p.scale + col), __ldg(p.shift + col));
-                            y[j] = v;
-                        }
-                        if (io.residual) {
-                            const float4 rr = __ldg(reinterpret_cast<const float4*>(io.residual + ro + c0 + q * 4));
-                            y[0] += rr.x; y[1] += rr.y; y[2] += rr.z; y[3] += rr.w;
-                        }
-                        if (p.relu) {
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) y[j] = fmaxf(y[j], 0.f);
-                        }
-                        if (io.out) *reinterpret_cast<float4*>(io.out + ro + c0 + q * 4) = make_float4(y[0], y[1], y[2], y[3]);
-                        if (io.out_h) store_split4(io.out_h, row, p.cout, c0 + q * 4, y);
-                        if (io.out_gated || io.out_gated_h) {
-                            if (gate_row) {
-                                const float4 gg = __ldg(reinterpret_cast<const float4*>(gate_row + c0 + q * 4));
-                                y[0] *= gg.x; y[1] *= gg.y; y[2] *= gg.z; y[3] *= gg.w;
-                            }
-                            if (io.out_gated) *reinterpret_cast<float4*>(io.out_gated + ro + c0 + q * 4) = make_float4(y[0], y[1], y[2], y[3]);
-                            if (io.out_gated_h) store_split4(io.out_gated_h, row, p.cout, c0 + q * 4, y);
-                        }
-                    }
+                    for (int q = 0; q < 8; ++q)
+                        *reinterpret_cast<float4*>(srow + q * 4) = make_float4(acc[q * 4] * out_scale, acc[q * 4 + 1] * out_scale,
+                                                                               acc[q * 4 + 2] * out_scale, acc[q * 4 + 3] * out_scale);
                 }
             }
             if (!last) {
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 tc_fence_before();
                 mbar_arrive(acc_empty(buf));       // this accumulator may be overwritten by its next group
+            }
+        }
+        // ---- epilogue, coalesced: one warp per output row, lanes along the channels ---------------------------------
+        asm volatile("bar.sync 1, 128;" ::: "memory");          // the 4 drain warps: staging tile complete
+        const int nv = p.cout >> 2;                              // float4 per row
+        for (int rr = q4; rr < BM; rr += 4) {
+            const int orow = row_s[rr];
+            if (orow < 0) continue;
+            const long long ro = (long long)orow * p.cout;
+            const float* grow = nullptr;
+            if (io.gate_table) grow = io.gate_table + (long long)(io.gate_idx ? __ldg(io.gate_idx + orow) : 0) * p.cout;
+            const float* srow = stage_c + (size_t)rr * pitch;
+            for (int v4 = lane; v4 < nv; v4 += 32) {
+                const int col = v4 * 4;
+                const float4 a4 = *reinterpret_cast<const float4*>(srow + col);
+                float y[4] = {a4.x, a4.y, a4.z, a4.w};
+                if (io.pre_add) {
+                    const float4 t4 = __ldg(reinterpret_cast<const float4*>(io.pre_add + ro + col));
+                    y[0] += t4.x; y[1] += t4.y; y[2] += t4.z; y[3] += t4.w;
+                }
+                if (p.scale) {
+                    const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.scale + col));
+                    const float4 h4 = __ldg(reinterpret_cast<const float4*>(p.shift + col));
+                    y[0] = fmaf(y[0], s4.x, h4.x); y[1] = fmaf(y[1], s4.y, h4.y); y[2] = fmaf(y[2], s4.z, h4.z); y[3] = fmaf(y[3], s4.w, h4.w);
+                }
+                if (io.residual) {
+                    const float4 t4 = __ldg(reinterpret_cast<const float4*>(io.residual + ro + col));
+                    y[0] += t4.x; y[1] += t4.y; y[2] += t4.z; y[3] += t4.w;
+                }
+                if (p.relu) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) y[j] = fmaxf(y[j], 0.f);
+                }
+                if (io.out) *reinterpret_cast<float4*>(io.out + ro + col) = make_float4(y[0], y[1], y[2], y[3]);
+                if (io.out_h) store_split4(io.out_h, orow, p.cout, col, y);
+                if (io.out_gated || io.out_gated_h) {
+                    if (grow) {
+                        const float4 g4 = __ldg(reinterpret_cast<const float4*>(grow + col));
+                        y[0] *= g4.x; y[1] *= g4.y; y[2] *= g4.z; y[3] *= g4.w;
+                    }
+                    if (io.out_gated) *reinterpret_cast<float4*>(io.out_gated + ro + col) = make_float4(y[0], y[1], y[2], y[3]);
+                    if (io.out_gated_h) store_split4(io.out_gated_h, orow, p.cout, col, y);
+                }
             }
         }
     } else if (warp == 5) {

@@ -43,6 +43,7 @@ class ConvLayer:
             W = W[None]
         self.W = W.contiguous()
         self.kvol, self.cin, self.cout = self.W.shape
+        self.name = pconv
         if pbn is not None:
             g = lambda k: sd[f"{pbn}.bn.{k}"].detach().to(device=device, dtype=torch.float32)
             scale = g("weight") / torch.sqrt(g("running_var") + BN_EPS)
@@ -351,7 +352,7 @@ class DenoiseEngine:
                              pre[p].data_ptr() if pre is not None else None,
                              sel(in1_h, p), sel(in2_h, p), sel(out_h, p), sel(outg_h, p))
         if self.layer_log is not None:
-            self.layer_log.append(dict(map=map_ptr, d_m=d_m.data_ptr() if d_m is not None else None,
+            self.layer_log.append(dict(name=lay.name, scatter=sd is not None, map=map_ptr, d_m=d_m.data_ptr() if d_m is not None else None,
                                        cin=lay.cin, cout=lay.cout, kvol=lay.kvol, npass=npass,
                                        tc=bool(lay.Wp is not None and self.conv_algo != _lib.ALGO_FFMA)))
         if self.conv_events is not None:
