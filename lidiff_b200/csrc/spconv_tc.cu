@@ -28,6 +28,7 @@
 // Stands behind ME.MinkowskiConvolution(+Transpose) forward, /root/reference/lidiff/models/minkunet.py:17-24,36-42,53-74.
 #include "common.cuh"
 #include <algorithm>
+#include <stdlib.h>
 #include "tc_common.cuh"
 
 namespace tc {
@@ -51,7 +52,8 @@ struct Params {
     int mout_cap;
     const int* row_perm;
     int stages, nchunks, tmem_cols, tot_col, group;     // tot_col: TMEM column of the running total; group: offsets per drain
-    int nbuf, acc_stride;                               // ping-pong accumulators (2 when 3 regions fit in TMEM) and their column pitch
+    int nbuf, acc_stride;
+    int ncta;                                           // output channels handled by one CTA (cout or cout/2): blockIdx.z picks the slice                               // ping-pong accumulators (2 when 3 regions fit in TMEM) and their column pitch
     lb2_conv_io io[2];
 };
 
@@ -61,6 +63,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc(const Params p) {
     const int m0 = blockIdx.x * BM;
     if (m0 >= M) return;
     const lb2_conv_io io = p.io[blockIdx.y];
+    const int n0 = blockIdx.z * p.ncta;              // first output channel of this CTA
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ctot = p.c1 + p.c2;
 
@@ -68,7 +71,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc(const Params p) {
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     unsigned char* gen = smem_raw + (base - raw);
-    const uint32_t b_tile = (uint32_t)p.cout * 128u;                 // one fp16 B tile (hi or lo)
+    const uint32_t b_tile = (uint32_t)p.ncta * 128u;                 // one fp16 B tile (hi or lo) of this CTA's channels
+    const uint32_t b_full = (uint32_t)p.cout * 128u;                 // the same tile over all cout channels (packed layout)
     const float out_scale = __ldg(reinterpret_cast<const float*>(p.wpacked) + 1);     // 2^-k of the packed weights
     const uint32_t stage_bytes = 2u * A_TILE + 2u * b_tile;
     unsigned char* tail = gen + (size_t)p.stages * stage_bytes;
@@ -164,7 +168,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc(const Params p) {
     } else if (warp == 4) {
         // =========================== MMA issuer ===========================
         if (lane == 0) {
-            const uint32_t idesc = make_idesc(p.cout);
+            const uint32_t idesc = make_idesc(p.ncta);
             int it = 0, in_group = 0, group_idx = 0, off_idx = 0;
             for (uint32_t km = kmask; km; km &= km - 1, ++off_idx) {
                 const int buf = group_idx % p.nbuf;
@@ -204,7 +208,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc(const Params p) {
         const int q4 = warp & 3;                                   // TMEM lane quarter this warp may access
         const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;
         float* stage_c = reinterpret_cast<float*>(gen);            // [BM][pitch] fp32, reuses the (then idle) stage ring
-        const int pitch = p.cout + 4;                              // +4 floats: conflict-free 16-byte row writes
+        const int pitch = p.ncta + 4;                              // +4 floats: conflict-free 16-byte row writes
         for (int g = 0; g < max(n_groups, 1); ++g) {
             const bool last = g >= n_groups - 1;
             const int buf = g % p.nbuf;
@@ -213,7 +217,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc(const Params p) {
                 mbar_wait(acc_full(buf), (g / p.nbuf) & 1);
                 tc_fence_after();
             }
-            for (int c0 = 0; c0 < p.cout; c0 += 32) {
+            for (int c0 = 0; c0 < p.ncta; c0 += 32) {
                 float acc[32];
                 if (n_groups > 0) {
                     uint32_t r[32];
@@ -252,47 +256,46 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc(const Params p) {
                 mbar_arrive(acc_empty(buf));       // this accumulator may be overwritten by its next group
             }
         }
-        // ---- epilogue, coalesced: one warp per output row, lanes along the channels ---------------------------------
+        // ---- epilogue, coalesced: each drain warp owns 32 tile rows and walks their (row, 4-channel) elements with
+        //      consecutive lanes on consecutive channels, so every global access is a contiguous row segment ----------
         asm volatile("bar.sync 1, 128;" ::: "memory");          // the 4 drain warps: staging tile complete
-        const int nv = p.cout >> 2;                              // float4 per row
-        for (int rr = q4; rr < BM; rr += 4) {
+        const int nv = p.ncta >> 2;                              // float4 per row (this CTA's channels)
+        for (int e = lane; e < 32 * nv; e += 32) {
+            const int rr = q4 + 4 * (e / nv);
+            const int lcol = (e % nv) * 4;
+            const int col = n0 + lcol;
             const int orow = row_s[rr];
             if (orow < 0) continue;
             const long long ro = (long long)orow * p.cout;
-            const float* grow = nullptr;
-            if (io.gate_table) grow = io.gate_table + (long long)(io.gate_idx ? __ldg(io.gate_idx + orow) : 0) * p.cout;
-            const float* srow = stage_c + (size_t)rr * pitch;
-            for (int v4 = lane; v4 < nv; v4 += 32) {
-                const int col = v4 * 4;
-                const float4 a4 = *reinterpret_cast<const float4*>(srow + col);
-                float y[4] = {a4.x, a4.y, a4.z, a4.w};
-                if (io.pre_add) {
-                    const float4 t4 = __ldg(reinterpret_cast<const float4*>(io.pre_add + ro + col));
-                    y[0] += t4.x; y[1] += t4.y; y[2] += t4.z; y[3] += t4.w;
-                }
-                if (p.scale) {
-                    const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.scale + col));
-                    const float4 h4 = __ldg(reinterpret_cast<const float4*>(p.shift + col));
-                    y[0] = fmaf(y[0], s4.x, h4.x); y[1] = fmaf(y[1], s4.y, h4.y); y[2] = fmaf(y[2], s4.z, h4.z); y[3] = fmaf(y[3], s4.w, h4.w);
-                }
-                if (io.residual) {
-                    const float4 t4 = __ldg(reinterpret_cast<const float4*>(io.residual + ro + col));
-                    y[0] += t4.x; y[1] += t4.y; y[2] += t4.z; y[3] += t4.w;
-                }
-                if (p.relu) {
+            const float4 a4 = *reinterpret_cast<const float4*>(stage_c + (size_t)rr * pitch + lcol);
+            float y[4] = {a4.x, a4.y, a4.z, a4.w};
+            if (io.pre_add) {
+                const float4 t4 = __ldg(reinterpret_cast<const float4*>(io.pre_add + ro + col));
+                y[0] += t4.x; y[1] += t4.y; y[2] += t4.z; y[3] += t4.w;
+            }
+            if (p.scale) {
+                const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.scale + col));
+                const float4 h4 = __ldg(reinterpret_cast<const float4*>(p.shift + col));
+                y[0] = fmaf(y[0], s4.x, h4.x); y[1] = fmaf(y[1], s4.y, h4.y); y[2] = fmaf(y[2], s4.z, h4.z); y[3] = fmaf(y[3], s4.w, h4.w);
+            }
+            if (io.residual) {
+                const float4 t4 = __ldg(reinterpret_cast<const float4*>(io.residual + ro + col));
+                y[0] += t4.x; y[1] += t4.y; y[2] += t4.z; y[3] += t4.w;
+            }
+            if (p.relu) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) y[j] = fmaxf(y[j], 0.f);
+                for (int j = 0; j < 4; ++j) y[j] = fmaxf(y[j], 0.f);
+            }
+            if (io.out) *reinterpret_cast<float4*>(io.out + ro + col) = make_float4(y[0], y[1], y[2], y[3]);
+            if (io.out_h) store_split4(io.out_h, orow, p.cout, col, y);
+            if (io.out_gated || io.out_gated_h) {
+                if (io.gate_table) {
+                    const long long g = io.gate_idx ? __ldg(io.gate_idx + orow) : 0;
+                    const float4 g4 = __ldg(reinterpret_cast<const float4*>(io.gate_table + g * p.cout + col));
+                    y[0] *= g4.x; y[1] *= g4.y; y[2] *= g4.z; y[3] *= g4.w;
                 }
-                if (io.out) *reinterpret_cast<float4*>(io.out + ro + col) = make_float4(y[0], y[1], y[2], y[3]);
-                if (io.out_h) store_split4(io.out_h, orow, p.cout, col, y);
-                if (io.out_gated || io.out_gated_h) {
-                    if (grow) {
-                        const float4 g4 = __ldg(reinterpret_cast<const float4*>(grow + col));
-                        y[0] *= g4.x; y[1] *= g4.y; y[2] *= g4.z; y[3] *= g4.w;
-                    }
-                    if (io.out_gated) *reinterpret_cast<float4*>(io.out_gated + ro + col) = make_float4(y[0], y[1], y[2], y[3]);
-                    if (io.out_gated_h) store_split4(io.out_gated_h, orow, p.cout, col, y);
-                }
+                if (io.out_gated) *reinterpret_cast<float4*>(io.out_gated + ro + col) = make_float4(y[0], y[1], y[2], y[3]);
+                if (io.out_gated_h) store_split4(io.out_gated_h, orow, p.cout, col, y);
             }
         }
     } else if (warp == 5) {
@@ -305,9 +308,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc(const Params p) {
                     const int s = it % p.stages;
                     mbar_wait(empty(s), ((it / p.stages) & 1) ^ 1);
                     const uint32_t dst = base + (uint32_t)s * stage_bytes + 2u * A_TILE;
-                    const unsigned char* src = p.wpacked + PACK_HEADER + ((size_t)k * p.nchunks + c) * (2u * b_tile);
+                    const unsigned char* src = p.wpacked + PACK_HEADER + ((size_t)k * p.nchunks + c) * (2u * b_full) + (size_t)n0 * 128u;
                     mbar_expect_tx(full_b(s), 2u * b_tile);
-                    bulk_g2s(dst, src, 2u * b_tile, full_b(s));
+                    bulk_g2s(dst, src, b_tile, full_b(s));                       // hi rows n0 .. n0+ncta
+                    bulk_g2s(dst + b_tile, src + b_full, b_tile, full_b(s));     // lo rows
                 }
             }
         }
@@ -400,6 +404,12 @@ extern "C" int lb2_pack_weights(void* handle, void* stream, const float* weight,
     return LB2_OK;
 }
 
+static bool tc_nsplit_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("LB2_TC_NSPLIT"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
+
 int lb2_spconv_tc_launch(Lb2Handle* h, cudaStream_t s, const lb2_conv_desc* d) {
     tc::Params p;
     p.c1 = d->c1; p.c2 = d->c2; p.cout = d->cout; p.kvol = d->kvol;
@@ -407,10 +417,12 @@ int lb2_spconv_tc_launch(Lb2Handle* h, cudaStream_t s, const lb2_conv_desc* d) {
     p.scale = d->scale; p.shift = d->shift; p.relu = d->relu;
     p.nbr = d->nbr; p.nbr_stride = d->nbr_stride; p.d_mout = d->d_mout; p.mout_cap = d->mout_cap; p.row_perm = d->row_perm;
     p.nchunks = (d->c1 + d->c2 + tc::KC - 1) / tc::KC;
+    const int nsplit = (d->cout == 256 && tc_nsplit_enabled()) ? 2 : 1;     // 256 channels: two CTAs of 128 (drain overlap, 3 stages)
+    p.ncta = d->cout / nsplit;
     int stages = tc::MAX_STAGES;
-    while (stages > 1 && tc::smem_bytes(d->cout, stages) > 227 * 1024) --stages;
+    while (stages > 1 && tc::smem_bytes(p.ncta, stages) > 227 * 1024) --stages;
     p.stages = stages;
-    const int half = d->cout <= 32 ? 32 : d->cout <= 64 ? 64 : d->cout <= 128 ? 128 : 256;
+    const int half = p.ncta <= 32 ? 32 : p.ncta <= 64 ? 64 : p.ncta <= 128 ? 128 : 256;
     p.nbuf = half <= 128 ? 2 : 1;              // ping-pong accumulators when acc0 | acc1 | total fit in 512 columns
     p.acc_stride = half;
     p.tot_col = p.nbuf * half;                 // [b*half, +cout): MMA accumulators, [tot_col, +cout): running fp32 total
@@ -418,14 +430,14 @@ int lb2_spconv_tc_launch(Lb2Handle* h, cudaStream_t s, const lb2_conv_desc* d) {
     const int steps_per_offset = 3 * ((d->c1 + d->c2 + 15) / 16);
     p.group = std::max(1, tc::STEP_BUDGET / steps_per_offset);
     p.io[0] = d->io[0]; p.io[1] = d->io[d->npass > 1 ? 1 : 0];
-    const size_t smem = tc::smem_bytes(d->cout, stages);
+    const size_t smem = tc::smem_bytes(p.ncta, stages);
     static size_t configured = 0;
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(tc::k_spconv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
         if (e != cudaSuccess) return lb2_fail(h, LB2_ERR_CUDA, "k_spconv_tc smem attribute: %s", cudaGetErrorString(e));
         configured = 227 * 1024;
     }
-    dim3 grid(cdiv(d->mout_cap, tc::BM), d->npass);
+    dim3 grid(cdiv(d->mout_cap, tc::BM), d->npass, nsplit);
     tc::k_spconv_tc<<<grid, tc::THREADS, smem, s>>>(p);
     LB2_POST_LAUNCH(h, "k_spconv_tc");
     return LB2_OK;
