@@ -144,7 +144,8 @@ typedef struct {
 
 #define LB2_ALGO_AUTO  0
 #define LB2_ALGO_FFMA  1    /* fp32 CUDA-core implicit GEMM */
-#define LB2_ALGO_TC    2    /* tcgen05 FP16x3 split-precision implicit GEMM (needs weight_packed) */
+#define LB2_ALGO_TC    2    /* tcgen05 FP16x3 split-precision implicit GEMM (needs weight_packed), persistent CTAs */
+#define LB2_ALGO_TC_TILE 3  /* same math, one CTA per 128-row tile (non-persistent reference variant) */
 int lb2_spconv_forward(void* h, void* stream, const lb2_conv_desc* d, int algo);
 
 /* The same convolution in gather-GEMM-scatter form (what ME's GPU backend does per kernel offset) for levels

@@ -14,7 +14,7 @@ import torch
 
 _SO = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_C", "liblidiff_b200.so")
 
-ALGO_AUTO, ALGO_FFMA, ALGO_TC = 0, 1, 2
+ALGO_AUTO, ALGO_FFMA, ALGO_TC, ALGO_TC_TILE = 0, 1, 2, 3
 
 
 class Grid(C.Structure):

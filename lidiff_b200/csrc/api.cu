@@ -2,7 +2,7 @@
 #include "common.cuh"
 
 int lb2_spconv_ffma_launch(Lb2Handle* h, cudaStream_t s, const lb2_conv_desc* d);
-int lb2_spconv_tc_launch(Lb2Handle* h, cudaStream_t s, const lb2_conv_desc* d);
+int lb2_spconv_tc_launch(Lb2Handle* h, cudaStream_t s, const lb2_conv_desc* d, bool persistent);
 bool lb2_spconv_tc_supported(const lb2_conv_desc* d);
 
 extern "C" int lb2_spconv_forward(void* handle, void* stream, const lb2_conv_desc* d, int algo) {
@@ -21,11 +21,11 @@ extern "C" int lb2_spconv_forward(void* handle, void* stream, const lb2_conv_des
     }
     LB2_REQUIRE(h, d->c2 == 0 || d->c1 % 16 == 0, "c1 must be a multiple of 16 when in2 is given");
     cudaStream_t s = (cudaStream_t)stream;
-    if (algo == LB2_ALGO_TC) {
+    if (algo == LB2_ALGO_TC || algo == LB2_ALGO_TC_TILE) {
         if (!d->weight_packed || !lb2_spconv_tc_supported(d))
             return lb2_fail(h, LB2_ERR_UNSUP, "tensor-core variant does not support this layer%s", "");
-        return lb2_spconv_tc_launch(h, s, d);
+        return lb2_spconv_tc_launch(h, s, d, algo == LB2_ALGO_TC);
     }
-    if (algo == LB2_ALGO_AUTO && d->weight_packed && lb2_spconv_tc_supported(d)) return lb2_spconv_tc_launch(h, s, d);
+    if (algo == LB2_ALGO_AUTO && d->weight_packed && lb2_spconv_tc_supported(d)) return lb2_spconv_tc_launch(h, s, d, true);
     return lb2_spconv_ffma_launch(h, s, d);
 }

@@ -410,7 +410,11 @@ static bool tc_nsplit_enabled() {
     return v == 1;
 }
 
-int lb2_spconv_tc_launch(Lb2Handle* h, cudaStream_t s, const lb2_conv_desc* d) {
+int lb2_spconv_tc2_launch(Lb2Handle* h, cudaStream_t s, const lb2_conv_desc* d, int step_budget);
+bool lb2_tc_persistent_enabled();
+
+int lb2_spconv_tc_launch(Lb2Handle* h, cudaStream_t s, const lb2_conv_desc* d, bool persistent) {
+    if (persistent && lb2_tc_persistent_enabled()) return lb2_spconv_tc2_launch(h, s, d, tc::STEP_BUDGET);
     tc::Params p;
     p.c1 = d->c1; p.c2 = d->c2; p.cout = d->cout; p.kvol = d->kvol;
     p.wpacked = (const unsigned char*)d->weight_packed;

@@ -1,0 +1,379 @@
+// K4 (variant B, persistent) — the output-stationary tcgen05 sparse convolution of spconv_tc.cu restructured as a
+// persistent kernel: one CTA per SM walks the (pass, 128-row tile) work items round-robin and keeps every pipeline
+// running ACROSS tiles, so the latency chain of a tile (neighbour-index fetch -> first gather -> MMA -> drain ->
+// epilogue) overlaps with its neighbours instead of being paid ~20 times per SM and launch (measured: 22 us per tile
+// on the 96-channel level-0 layers against a 5 us bandwidth floor).
+//
+//   warps 0-3  A producers: per tile fetch row ids (execution order) + the K neighbour rows of each, publish the
+//              tile's non-empty-offset mask (meta_full), then stream the gathered rows of every (offset, chunk)
+//              through the stage ring (cp.async from the fp16 split companions, or fp32 -> split in registers)
+//   warp 4     MMA issuer (FP16x3, accumulator groups of <= STEP_BUDGET chained steps, ping-pong TMEM when it fits)
+//   warp 5     weight loader (one cp.async.bulk pair per stage)
+//   warps 6-9  drain: two-level accumulation (RN fp32 running total in TMEM) and the fused epilogue, coalesced
+//              through a per-warp 32x32 shared-memory slab; outputs fp32 and/or fp16 split companions
+//
+// Same math, same parameters and the same results as k_spconv_tc (tests compare them).
+#include "common.cuh"
+#include <algorithm>
+#include <stdlib.h>
+#include "tc_common.cuh"
+
+namespace tc2 {
+using namespace tc;
+
+constexpr int THREADS = 320;
+constexpr int MAX_KVOL = 27;
+constexpr int MAX_STAGES = 4;
+constexpr int SLAB_PITCH = 36;                        // floats per slab row (32 + 4: conflict-free 16-byte accesses)
+constexpr int SLAB_BYTES = BM * SLAB_PITCH * 4;       // 4 warps x 32 rows
+
+struct Params {
+    int c1, c2, cout, kvol;
+    const unsigned char* wpacked;
+    const float* scale;
+    const float* shift;
+    int relu;
+    const int* nbr;
+    long long nbr_stride;
+    const int* d_mout;
+    int mout_cap;
+    const int* row_perm;
+    int stages, nchunks, tmem_cols, tot_col, group, nbuf, acc_stride, npass;
+    lb2_conv_io io[2];
+};
+
+__global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_persist(const Params p) {
+    extern __shared__ unsigned char smem_raw[];
+    const int M = p.d_mout ? min(*p.d_mout, p.mout_cap) : p.mout_cap;
+    const int n_tiles = (M + BM - 1) / BM;
+    const int total = n_tiles * p.npass;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ctot = p.c1 + p.c2;
+
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    unsigned char* gen = smem_raw + (base - raw);
+    const uint32_t b_tile = (uint32_t)p.cout * 128u;
+    const uint32_t stage_bytes = 2u * A_TILE + 2u * b_tile;
+    unsigned char* tail = gen + (size_t)p.stages * stage_bytes;
+    float* slab = reinterpret_cast<float*>(tail);                                   // [4 warps][32][SLAB_PITCH]
+    int* idx_s = reinterpret_cast<int*>(tail + SLAB_BYTES);                          // [kvol][BM] (producer private)
+    int* row_s = idx_s + MAX_KVOL * BM;                                              // [2][BM]
+    uint32_t* wmask = reinterpret_cast<uint32_t*>(row_s + 2 * BM);                   // [2][4] per-warp offset masks
+    uint64_t* bars = reinterpret_cast<uint64_t*>(wmask + 8);
+    uint32_t* misc = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + 8);
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_a = [&](int s) { return bar0 + 8u * s; };
+    auto full_b = [&](int s) { return bar0 + 8u * (MAX_STAGES + s); };
+    auto empty = [&](int s) { return bar0 + 8u * (2 * MAX_STAGES + s); };
+    auto acc_full = [&](int b) { return bar0 + 8u * (3 * MAX_STAGES + b); };
+    auto acc_empty = [&](int b) { return bar0 + 8u * (3 * MAX_STAGES + 2 + b); };
+    auto meta_full = [&](int b) { return bar0 + 8u * (3 * MAX_STAGES + 4 + b); };
+    auto meta_empty = [&](int b) { return bar0 + 8u * (3 * MAX_STAGES + 6 + b); };
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(full_a(s), 128); mbar_init(full_b(s), 1); mbar_init(empty(s), 1); }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), 128);
+            mbar_init(meta_full(b), 1); mbar_init(meta_empty(b), 130);           // MMA + loader + 128 drain threads
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&misc[0])), "r"((uint32_t)p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = misc[0];
+    const float out_scale = __ldg(reinterpret_cast<const float*>(p.wpacked) + 1);
+
+    auto tile_kmask = [&](int b) { return wmask[b * 4] | wmask[b * 4 + 1] | wmask[b * 4 + 2] | wmask[b * 4 + 3]; };
+
+    if (warp < 4) {
+        // =========================== A producers ===========================
+        const int t = threadIdx.x;
+        const int sub = t & 7, rbase = t >> 3;
+        const int D = p.stages - 1;
+        int it = 0, arrived = 0, j = 0;
+        for (int item = blockIdx.x; item < total; item += gridDim.x, ++j) {
+            const int b = j & 1;
+            const int pass = item / n_tiles, tile = item - pass * n_tiles;
+            const lb2_conv_io io = p.io[pass];
+            if (j >= 2) mbar_wait(meta_empty(b), ((j >> 1) - 1) & 1);
+            asm volatile("bar.sync 2, 128;" ::: "memory");              // everybody is done reading the previous tile's idx_s
+            {
+                const int slot = tile * BM + t;
+                const int row = (slot < M) ? (p.row_perm ? __ldg(p.row_perm + slot) : slot) : -1;
+                row_s[b * BM + t] = row;
+                uint32_t mymask = 0;
+                for (int k = 0; k < p.kvol; ++k) {
+                    int v = -1;
+                    if (row >= 0) v = p.nbr ? __ldg(p.nbr + (long long)k * p.nbr_stride + row) : row;
+                    idx_s[k * BM + t] = v;
+                    if (__any_sync(0xffffffffu, v >= 0)) mymask |= 1u << k;
+                }
+                if (lane == 0) wmask[b * 4 + warp] = mymask;
+            }
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+            if (t == 0) mbar_arrive(meta_full(b));
+            const uint32_t kmask = tile_kmask(b);
+            const bool use_h = (io.in1_h != nullptr) && (p.c2 == 0 || io.in2_h != nullptr);
+            for (uint32_t km = kmask; km; km &= km - 1) {
+                const int k = __ffs(km) - 1;
+                const int* idxk = idx_s + k * BM;
+                int src[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) src[q] = idxk[rbase + 16 * q];
+                for (int c = 0; c < p.nchunks; ++c, ++it) {
+                    const int s = it % p.stages;
+                    mbar_wait(empty(s), ((it / p.stages) & 1) ^ 1);
+                    unsigned char* a_hi = gen + (size_t)s * stage_bytes;
+                    const uint32_t a_hi_u = base + (uint32_t)s * stage_bytes;
+                    const int ch = c * KC + sub * 8;
+                    if (ch < ctot) {
+                        const bool first = ch < p.c1;
+                        const int cw = first ? p.c1 : p.c2;
+                        const int co = first ? ch : ch - p.c1;
+                        if (use_h) produce_a_split(reinterpret_cast<const __half*>(first ? io.in1_h : io.in2_h), cw, co, src, a_hi_u, a_hi_u + A_TILE, rbase, sub);
+                        else produce_a_f32(first ? io.in1 : io.in2, cw, co, src, a_hi, a_hi + A_TILE, rbase, sub);
+                    }
+                    cp_async_commit();                                  // (empty group on the fp32 path)
+                    if (it >= D) {
+                        cp_async_wait_dyn(D);
+                        fence_proxy_async();
+                        mbar_arrive(full_a(arrived % p.stages));
+                        ++arrived;
+                    }
+                }
+            }
+        }
+        cp_async_wait<0>();
+        fence_proxy_async();
+        for (; arrived < it; ++arrived) mbar_arrive(full_a(arrived % p.stages));
+    } else if (warp == 4) {
+        // =========================== MMA issuer ===========================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(p.cout);
+            int it = 0, gcount = 0, j = 0;
+            for (int item = blockIdx.x; item < total; item += gridDim.x, ++j) {
+                const int b = j & 1;
+                mbar_wait(meta_full(b), (j >> 1) & 1);
+                const uint32_t kmask = tile_kmask(b);
+                const int n_off = __popc(kmask);
+                int in_group = 0, off_idx = 0;
+                for (uint32_t km = kmask; km; km &= km - 1, ++off_idx) {
+                    const int buf = gcount % p.nbuf;
+                    const uint32_t tmem_acc = tmem_d + (uint32_t)(buf * p.acc_stride);
+                    if (in_group == 0 && gcount >= p.nbuf) {
+                        mbar_wait(acc_empty(buf), ((gcount / p.nbuf) - 1) & 1);
+                        tc_fence_after();
+                    }
+                    for (int c = 0; c < p.nchunks; ++c, ++it) {
+                        const int s = it % p.stages;
+                        const uint32_t par = (it / p.stages) & 1;
+                        mbar_wait(full_b(s), par);
+                        mbar_wait(full_a(s), par);
+                        tc_fence_after();
+                        const uint32_t a_hi = base + (uint32_t)s * stage_bytes, a_lo = a_hi + A_TILE;
+                        const uint32_t b_hi = a_lo + A_TILE, b_lo = b_hi + b_tile;
+                        const int ksteps = min(KC, ctot - c * KC) >> 4;
+                        for (int ks = 0; ks < ksteps; ++ks) {
+                            const uint64_t dah = make_desc(a_hi + ks * 32), dal = make_desc(a_lo + ks * 32);
+                            const uint64_t dbh = make_desc(b_hi + ks * 32), dbl = make_desc(b_lo + ks * 32);
+                            umma(tmem_acc, dah, dbh, idesc, (in_group | c | ks) ? 1u : 0u);
+                            umma(tmem_acc, dal, dbh, idesc, 1);
+                            umma(tmem_acc, dah, dbl, idesc, 1);
+                        }
+                        umma_commit(empty(s));
+                    }
+                    if (++in_group == p.group || off_idx == n_off - 1) {
+                        umma_commit(acc_full(buf));
+                        in_group = 0;
+                        ++gcount;
+                    }
+                }
+                mbar_arrive(meta_empty(b));
+            }
+        }
+        __syncwarp();
+    } else if (warp == 5) {
+        // =========================== weight loader ===========================
+        if (lane == 0) {
+            int it = 0, j = 0;
+            for (int item = blockIdx.x; item < total; item += gridDim.x, ++j) {
+                const int b = j & 1;
+                mbar_wait(meta_full(b), (j >> 1) & 1);
+                const uint32_t kmask = tile_kmask(b);
+                for (uint32_t km = kmask; km; km &= km - 1) {
+                    const int k = __ffs(km) - 1;
+                    for (int c = 0; c < p.nchunks; ++c, ++it) {
+                        const int s = it % p.stages;
+                        mbar_wait(empty(s), ((it / p.stages) & 1) ^ 1);
+                        const uint32_t dst = base + (uint32_t)s * stage_bytes + 2u * A_TILE;
+                        const unsigned char* src = p.wpacked + PACK_HEADER + ((size_t)k * p.nchunks + c) * (2u * b_tile);
+                        mbar_expect_tx(full_b(s), 2u * b_tile);
+                        bulk_g2s(dst, src, 2u * b_tile, full_b(s));
+                    }
+                }
+                mbar_arrive(meta_empty(b));
+            }
+        }
+        __syncwarp();
+    } else {
+        // =========================== drain + epilogue ===========================
+        const int q4 = warp & 3;
+        const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;
+        float* myslab = slab + (size_t)q4 * 32 * SLAB_PITCH;
+        int gcount = 0, j = 0;
+        for (int item = blockIdx.x; item < total; item += gridDim.x, ++j) {
+            const int b = j & 1;
+            const int pass = item / n_tiles;
+            const lb2_conv_io io = p.io[pass];
+            mbar_wait(meta_full(b), (j >> 1) & 1);
+            const uint32_t kmask = tile_kmask(b);
+            const int n_off = __popc(kmask);
+            const int n_groups = (n_off + p.group - 1) / p.group;
+            const int* rows = row_s + b * BM + q4 * 32;                 // this warp's 32 output rows
+            for (int g = 0; g < max(n_groups, 1); ++g) {
+                const bool last = g >= n_groups - 1;
+                const int buf = gcount % p.nbuf;
+                const uint32_t acc_col = (uint32_t)(buf * p.acc_stride);
+                if (n_groups > 0) {
+                    mbar_wait(acc_full(buf), (gcount / p.nbuf) & 1);
+                    tc_fence_after();
+                }
+                for (int c0 = 0; c0 < p.cout; c0 += 32) {
+                    float acc[32];
+                    if (n_groups > 0) {
+                        uint32_t r[32];
+                        tmem_ld32(tmem_d + lane_base + acc_col + (uint32_t)c0, r);
+                        if (g > 0) {
+                            uint32_t tt[32];
+                            tmem_ld32(tmem_d + lane_base + (uint32_t)(p.tot_col + c0), tt);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int q = 0; q < 32; ++q) acc[q] = __fadd_rn(__uint_as_float(tt[q]), __uint_as_float(r[q]));
+                        } else {
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int q = 0; q < 32; ++q) acc[q] = __uint_as_float(r[q]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) acc[q] = 0.f;
+                    }
+                    if (!last) {
+                        uint32_t tt[32];
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) tt[q] = __float_as_uint(acc[q]);
+                        tmem_st32(tmem_d + lane_base + (uint32_t)(p.tot_col + c0), tt);
+                    } else {
+                        // ---- epilogue of this 32-column slab: transpose through the warp's slab, then lanes run along channels
+                        __syncwarp();
+                        float* srow = myslab + lane * SLAB_PITCH;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            *reinterpret_cast<float4*>(srow + q * 4) = make_float4(acc[q * 4] * out_scale, acc[q * 4 + 1] * out_scale,
+                                                                                   acc[q * 4 + 2] * out_scale, acc[q * 4 + 3] * out_scale);
+                        __syncwarp();
+#pragma unroll 2
+                        for (int e = lane; e < 256; e += 32) {
+                            const int rr = e >> 3;
+                            const int col = c0 + (e & 7) * 4;
+                            const int orow = rows[rr];
+                            if (orow < 0) continue;
+                            const long long ro = (long long)orow * p.cout;
+                            const float4 a4 = *reinterpret_cast<const float4*>(myslab + rr * SLAB_PITCH + (e & 7) * 4);
+                            float y[4] = {a4.x, a4.y, a4.z, a4.w};
+                            if (io.pre_add) {
+                                const float4 t4 = __ldg(reinterpret_cast<const float4*>(io.pre_add + ro + col));
+                                y[0] += t4.x; y[1] += t4.y; y[2] += t4.z; y[3] += t4.w;
+                            }
+                            if (p.scale) {
+                                const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.scale + col));
+                                const float4 h4 = __ldg(reinterpret_cast<const float4*>(p.shift + col));
+                                y[0] = fmaf(y[0], s4.x, h4.x); y[1] = fmaf(y[1], s4.y, h4.y); y[2] = fmaf(y[2], s4.z, h4.z); y[3] = fmaf(y[3], s4.w, h4.w);
+                            }
+                            if (io.residual) {
+                                const float4 t4 = __ldg(reinterpret_cast<const float4*>(io.residual + ro + col));
+                                y[0] += t4.x; y[1] += t4.y; y[2] += t4.z; y[3] += t4.w;
+                            }
+                            if (p.relu) {
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) y[q] = fmaxf(y[q], 0.f);
+                            }
+                            if (io.out) *reinterpret_cast<float4*>(io.out + ro + col) = make_float4(y[0], y[1], y[2], y[3]);
+                            if (io.out_h) store_split4(io.out_h, orow, p.cout, col, y);
+                            if (io.out_gated || io.out_gated_h) {
+                                if (io.gate_table) {
+                                    const long long gi = io.gate_idx ? __ldg(io.gate_idx + orow) : 0;
+                                    const float4 g4 = __ldg(reinterpret_cast<const float4*>(io.gate_table + gi * p.cout + col));
+                                    y[0] *= g4.x; y[1] *= g4.y; y[2] *= g4.z; y[3] *= g4.w;
+                                }
+                                if (io.out_gated) *reinterpret_cast<float4*>(io.out_gated + ro + col) = make_float4(y[0], y[1], y[2], y[3]);
+                                if (io.out_gated_h) store_split4(io.out_gated_h, orow, p.cout, col, y);
+                            }
+                        }
+                    }
+                }
+                if (n_groups > 0) {
+                    if (!last) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    tc_fence_before();
+                    mbar_arrive(acc_empty(buf));            // persistent: always release (the next tile reuses it)
+                    ++gcount;
+                }
+            }
+            mbar_arrive(meta_empty(b));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)p.tmem_cols) : "memory");
+}
+
+static size_t smem_bytes(int cout, int stages) {
+    return 1024 + (size_t)stages * (2 * A_TILE + 2 * (size_t)cout * 128) + SLAB_BYTES + MAX_KVOL * BM * sizeof(int) + 2 * BM * sizeof(int) +
+           8 * sizeof(uint32_t) + (3 * MAX_STAGES + 8) * 8 + 64;
+}
+
+}  // namespace tc2
+
+bool lb2_tc_persistent_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("LB2_TC_PERSISTENT"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
+
+int lb2_spconv_tc2_launch(Lb2Handle* h, cudaStream_t s, const lb2_conv_desc* d, int step_budget) {
+    tc2::Params p;
+    p.c1 = d->c1; p.c2 = d->c2; p.cout = d->cout; p.kvol = d->kvol; p.npass = d->npass;
+    p.wpacked = (const unsigned char*)d->weight_packed;
+    p.scale = d->scale; p.shift = d->shift; p.relu = d->relu;
+    p.nbr = d->nbr; p.nbr_stride = d->nbr_stride; p.d_mout = d->d_mout; p.mout_cap = d->mout_cap; p.row_perm = d->row_perm;
+    p.nchunks = (d->c1 + d->c2 + tc::KC - 1) / tc::KC;
+    int stages = tc2::MAX_STAGES;
+    while (stages > 1 && tc2::smem_bytes(d->cout, stages) > 227 * 1024) --stages;
+    p.stages = stages;
+    const int half = d->cout <= 32 ? 32 : d->cout <= 64 ? 64 : d->cout <= 128 ? 128 : 256;
+    p.nbuf = half <= 128 ? 2 : 1;
+    p.acc_stride = half;
+    p.tot_col = p.nbuf * half;
+    { int need = (p.nbuf + 1) * half; p.tmem_cols = 32; while (p.tmem_cols < need) p.tmem_cols <<= 1; }
+    const int steps_per_offset = 3 * ((d->c1 + d->c2 + 15) / 16);
+    p.group = std::max(1, step_budget / steps_per_offset);
+    p.io[0] = d->io[0]; p.io[1] = d->io[d->npass > 1 ? 1 : 0];
+    const size_t smem = tc2::smem_bytes(d->cout, stages);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(tc2::k_spconv_tc_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+        if (e != cudaSuccess) return lb2_fail(h, LB2_ERR_CUDA, "k_spconv_tc_persist smem attribute: %s", cudaGetErrorString(e));
+        configured = true;
+    }
+    const long long tiles_cap = (long long)cdiv(d->mout_cap, tc::BM) * d->npass;
+    const unsigned grid = (unsigned)std::min<long long>(h->num_sms, tiles_cap);
+    tc2::k_spconv_tc_persist<<<grid, tc2::THREADS, smem, s>>>(p);
+    LB2_POST_LAUNCH(h, "k_spconv_tc_persist");
+    return LB2_OK;
+}

@@ -450,3 +450,49 @@ def test_split_companion_inputs_give_identical_results(c1, c2, cout):
     o, oh = outs[1]
     assert torch.equal(oh[:, :cout].float(), o.half().float())
     assert (oh[:, :cout].float() + oh[:, cout:].float() - o).abs().max() <= 2e-6 * o.abs().max()
+
+
+@pytest.mark.parametrize("c1,c2,cout,lvl,kind", [(32, 0, 32, 0, "3"), (96, 32, 96, 1, "3"), (128, 0, 128, 2, "3"), (256, 128, 256, 3, "3"),
+                                                    (256, 0, 256, 3, "up"), (128, 0, 128, 4, "dn"), (384, 0, 256, 3, "1")])
+def test_persistent_kernel_equals_per_tile_kernel(c1, c2, cout, lvl, kind):
+    """LB2_ALGO_TC (persistent, cross-tile pipelined) and LB2_ALGO_TC_TILE (one CTA per tile) run the same math in the
+    same order: identical results, with row order, two passes, fused epilogue and split outputs"""
+    from lidiff_b200 import _lib
+    from lidiff_b200._lib import ConvDesc, ConvIO
+    from lidiff_b200.engine import Geometry
+    h = H()
+    pts, coords = random_field(70_000, 1.0 if lvl >= 3 else 0.3, 31)
+    N = coords.shape[0]
+    g = Geometry(h, N)
+    g.build(coords.to(DEV).contiguous(), N)
+    M = g.sizes()[lvl]
+    nbr, perm, kvol = {"3": (g.nbr3[lvl], g.perm3[lvl], 27), "up": (g.nbr_up[lvl], g.perm_up[lvl], 8),
+                       "dn": (g.nbr_dn[lvl], g.perm_dn[lvl], 8), "1": (None, None, 1)}[kind]
+    gen = torch.Generator().manual_seed(c1 + cout + lvl)
+    W = (torch.randn(kvol, c1 + c2, cout, generator=gen) / np.sqrt((c1 + c2) * kvol)).to(DEV)
+    Wp = h.pack_weights(W)
+    A = torch.randn(2, N, c1, generator=gen).to(DEV)
+    B = torch.randn(2, N, c2, generator=gen).to(DEV) if c2 else None
+    R = torch.randn(2, N, cout, generator=gen).to(DEV)
+    sc_, sh_ = (torch.rand(cout, generator=gen) + 0.5).to(DEV), torch.randn(cout, generator=gen).to(DEV)
+    tab = torch.randn(40, cout, generator=gen).to(DEV)
+    gi = torch.randint(0, 40, (N,), generator=gen, dtype=torch.int32).to(DEV)
+    res = []
+    for algo in (_lib.ALGO_TC_TILE, _lib.ALGO_TC):
+        out, outg = torch.zeros(2, N, cout, device=DEV), torch.zeros(2, N, cout, device=DEV)
+        out_h = torch.zeros(2, N, 2 * cout, dtype=torch.float16, device=DEV)
+        d = ConvDesc()
+        d.c1, d.c2, d.cout, d.kvol = c1, c2, cout, kvol
+        d.weight, d.weight_packed = W.data_ptr(), Wp.data_ptr()
+        d.scale, d.shift, d.relu = sc_.data_ptr(), sh_.data_ptr(), 1
+        d.nbr = nbr.data_ptr() if nbr is not None else None
+        d.nbr_stride, d.d_mout, d.mout_cap, d.npass = N, g.d_n[lvl].data_ptr(), N, 2
+        d.row_perm = perm.data_ptr() if perm is not None else None
+        for p_ in range(2):
+            d.io[p_] = ConvIO(A[p_].data_ptr(), B[p_].data_ptr() if B is not None else None, R[p_].data_ptr(), out[p_].data_ptr(),
+                              tab.data_ptr(), gi.data_ptr() if p_ == 0 else None, outg[p_].data_ptr(), None, None, None, out_h[p_].data_ptr(), None)
+        h.spconv(d, algo)
+        res.append((out[:, :M].clone(), outg[:, :M].clone(), out_h[:, :M].clone()))
+    for a, b in zip(res[0], res[1]):
+        assert torch.equal(a, b)
+    assert res[0][0].abs().sum() > 0
