@@ -373,11 +373,102 @@ __global__ void __launch_bounds__(FPS_THREADS) k_fps(const double* __restrict__ 
     }
 }
 
+// ---- multi-CTA variant: every SM owns a slice of the points in REGISTERS; one grid barrier per sample ------------
+struct FpsBest { double d; int idx; int pad; };
+#define FPS_PPT 4
+
+__global__ void __launch_bounds__(FPS_THREADS, 1) k_fps_coop(const double* __restrict__ pts, int n, int n_samples, int* __restrict__ out_idx,
+                                                              FpsBest* blk_best /* [2][gridDim.x] */, unsigned* counter) {
+    __shared__ double s_val[FPS_THREADS / 32];
+    __shared__ int s_idx[FPS_THREADS / 32];
+    __shared__ int s_cur;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int G = gridDim.x * FPS_THREADS, gtid = blockIdx.x * FPS_THREADS + t;
+    double px[FPS_PPT], py[FPS_PPT], pz[FPS_PPT], dist[FPS_PPT];
+#pragma unroll
+    for (int q = 0; q < FPS_PPT; ++q) {
+        const long long j = (long long)gtid + (long long)q * G;
+        const bool ok = j < n;
+        px[q] = ok ? pts[3 * j] : 0.0; py[q] = ok ? pts[3 * j + 1] : 0.0; pz[q] = ok ? pts[3 * j + 2] : 0.0;
+        dist[q] = ok ? DBL_MAX : -1.0;                 // -1: slot unused, can never win
+    }
+    int cur = 0;
+    for (int it = 0; it < n_samples; ++it) {
+        if (gtid == 0) out_idx[it] = cur;
+        const double cx = __ldg(pts + 3 * (long long)cur), cy = __ldg(pts + 3 * (long long)cur + 1), cz = __ldg(pts + 3 * (long long)cur + 2);
+        double bv = -1.0; int bi = 0x7fffffff;
+#pragma unroll
+        for (int q = 0; q < FPS_PPT; ++q) {
+            if (dist[q] >= 0.0) {
+                const double dx = px[q] - cx, dy = py[q] - cy, dz = pz[q] - cz;
+                const double d = fmin(dist[q], __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+                dist[q] = d;
+                if (d > bv) { bv = d; bi = gtid + q * G; }       // ascending index per thread
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) { s_val[w] = bv; s_idx[w] = bi; }
+        __syncthreads();
+        FpsBest* slot = blk_best + (size_t)(it & 1) * gridDim.x;
+        if (w == 0) {
+            bv = s_val[lane]; bi = s_idx[lane];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            }
+            if (lane == 0) {
+                slot[blockIdx.x].d = bv; slot[blockIdx.x].idx = bi;
+                __threadfence();
+                atomicAdd(counter, 1u);
+                const unsigned target = (unsigned)(it + 1) * gridDim.x;
+                while (*(volatile unsigned*)counter < target) { }      // grid barrier (all CTAs co-resident: cooperative launch)
+                __threadfence();
+            }
+            __syncwarp();
+            bv = -1.0; bi = 0x7fffffff;
+            for (int b = lane; b < (int)gridDim.x; b += 32) {
+                const double ov = __ldcg(&slot[b].d);
+                const int oi = __ldcg(&slot[b].idx);
+                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            }
+            if (lane == 0) s_cur = bi;
+        }
+        __syncthreads();
+        cur = s_cur;
+    }
+}
+
 extern "C" int lb2_farthest_point_sample(void* handle, void* stream, const double* pts, int32_t n, int32_t n_samples,
                                          int32_t* out_idx, double* dist_scratch) {
     Lb2Handle* h = (Lb2Handle*)handle;
     LB2_REQUIRE(h, h && pts && out_idx && dist_scratch && n > 0 && n_samples > 0 && n_samples <= n, "fps");
-    k_fps<<<1, FPS_THREADS, 0, (cudaStream_t)stream>>>(pts, n, n_samples, out_idx, dist_scratch);
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long coop_cap = (long long)h->num_sms * FPS_THREADS * FPS_PPT;
+    const size_t need = 2 * (size_t)h->num_sms * sizeof(FpsBest) + 64;
+    if (n >= 8192 && n <= coop_cap && (size_t)n * sizeof(double) >= need && (long long)n_samples * h->num_sms < 0x7fffffffLL) {
+        // cooperative multi-CTA kernel; scratch: [counter | pad][2][num_sms] FpsBest, carved from dist_scratch
+        unsigned* counter = (unsigned*)dist_scratch;
+        FpsBest* best = (FpsBest*)((char*)dist_scratch + 64);
+        if (cudaMemsetAsync(counter, 0, 64, s) != cudaSuccess) return lb2_fail(h, LB2_ERR_CUDA, "fps memset%s", "");
+        void* args[] = {(void*)&pts, (void*)&n, (void*)&n_samples, (void*)&out_idx, (void*)&best, (void*)&counter};
+        cudaError_t e = cudaLaunchCooperativeKernel((const void*)k_fps_coop, dim3(h->num_sms), dim3(FPS_THREADS), args, 0, s);
+        if (e == cudaSuccess) { h->launches++; return LB2_OK; }
+        (void)cudaGetLastError();                      // cooperative launch unavailable: fall through to the single-CTA kernel
+    }
+    k_fps<<<1, FPS_THREADS, 0, s>>>(pts, n, n_samples, out_idx, dist_scratch);
     LB2_POST_LAUNCH(h, "k_fps");
     return LB2_OK;
 }

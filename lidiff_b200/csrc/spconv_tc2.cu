@@ -26,6 +26,10 @@ constexpr int MAX_KVOL = 27;
 constexpr int MAX_STAGES = 4;
 constexpr int SLAB_PITCH = 36;                        // floats per slab row (32 + 4: conflict-free 16-byte accesses)
 constexpr int SLAB_BYTES = BM * SLAB_PITCH * 4;       // 4 warps x 32 rows
+constexpr int META = 4;                               // ring of per-tile metadata (row ids, offset masks).  Must exceed the cp.async
+                                                      // lookahead D <= MAX_STAGES-1: a tile's last full_a arrival is issued up to D
+                                                      // stage-iterations (= up to D tiles) later, while re-using a slot waits for the
+                                                      // tile META positions back to be completely drained.
 
 struct Params {
     int c1, c2, cout, kvol;
@@ -58,10 +62,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_persist(const Params p
     unsigned char* tail = gen + (size_t)p.stages * stage_bytes;
     float* slab = reinterpret_cast<float*>(tail);                                   // [4 warps][32][SLAB_PITCH]
     int* idx_s = reinterpret_cast<int*>(tail + SLAB_BYTES);                          // [kvol][BM] (producer private)
-    int* row_s = idx_s + MAX_KVOL * BM;                                              // [2][BM]
-    uint32_t* wmask = reinterpret_cast<uint32_t*>(row_s + 2 * BM);                   // [2][4] per-warp offset masks
-    uint64_t* bars = reinterpret_cast<uint64_t*>(wmask + 8);
-    uint32_t* misc = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + 8);
+    int* row_s = idx_s + MAX_KVOL * BM;                                              // [META][BM]
+    uint32_t* wmask = reinterpret_cast<uint32_t*>(row_s + META * BM);                // [META][4] per-warp offset masks
+    uint64_t* bars = reinterpret_cast<uint64_t*>(wmask + 4 * META);
+    uint32_t* misc = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + 4 + 2 * META);
     const uint32_t bar0 = smem_u32(bars);
     auto full_a = [&](int s) { return bar0 + 8u * s; };
     auto full_b = [&](int s) { return bar0 + 8u * (MAX_STAGES + s); };
@@ -69,14 +73,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_persist(const Params p
     auto acc_full = [&](int b) { return bar0 + 8u * (3 * MAX_STAGES + b); };
     auto acc_empty = [&](int b) { return bar0 + 8u * (3 * MAX_STAGES + 2 + b); };
     auto meta_full = [&](int b) { return bar0 + 8u * (3 * MAX_STAGES + 4 + b); };
-    auto meta_empty = [&](int b) { return bar0 + 8u * (3 * MAX_STAGES + 6 + b); };
+    auto meta_empty = [&](int b) { return bar0 + 8u * (3 * MAX_STAGES + 4 + META + b); };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(full_a(s), 128); mbar_init(full_b(s), 1); mbar_init(empty(s), 1); }
-        for (int b = 0; b < 2; ++b) {
-            mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), 128);
-            mbar_init(meta_full(b), 1); mbar_init(meta_empty(b), 130);           // MMA + loader + 128 drain threads
-        }
+        for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), 128); }
+        for (int b = 0; b < META; ++b) { mbar_init(meta_full(b), 1); mbar_init(meta_empty(b), 130); }   // MMA + loader + 128 drain threads
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 4) {
@@ -98,10 +100,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_persist(const Params p
         const int D = p.stages - 1;
         int it = 0, arrived = 0, j = 0;
         for (int item = blockIdx.x; item < total; item += gridDim.x, ++j) {
-            const int b = j & 1;
+            const int b = j % META;
             const int pass = item / n_tiles, tile = item - pass * n_tiles;
             const lb2_conv_io io = p.io[pass];
-            if (j >= 2) mbar_wait(meta_empty(b), ((j >> 1) - 1) & 1);
+            if (j >= META) mbar_wait(meta_empty(b), ((j / META) - 1) & 1);
             asm volatile("bar.sync 2, 128;" ::: "memory");              // everybody is done reading the previous tile's idx_s
             {
                 const int slot = tile * BM + t;
@@ -158,8 +160,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_persist(const Params p
             const uint32_t idesc = make_idesc(p.cout);
             int it = 0, gcount = 0, j = 0;
             for (int item = blockIdx.x; item < total; item += gridDim.x, ++j) {
-                const int b = j & 1;
-                mbar_wait(meta_full(b), (j >> 1) & 1);
+                const int b = j % META;
+                mbar_wait(meta_full(b), (j / META) & 1);
                 const uint32_t kmask = tile_kmask(b);
                 const int n_off = __popc(kmask);
                 int in_group = 0, off_idx = 0;
@@ -203,8 +205,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_persist(const Params p
         if (lane == 0) {
             int it = 0, j = 0;
             for (int item = blockIdx.x; item < total; item += gridDim.x, ++j) {
-                const int b = j & 1;
-                mbar_wait(meta_full(b), (j >> 1) & 1);
+                const int b = j % META;
+                mbar_wait(meta_full(b), (j / META) & 1);
                 const uint32_t kmask = tile_kmask(b);
                 for (uint32_t km = kmask; km; km &= km - 1) {
                     const int k = __ffs(km) - 1;
@@ -228,10 +230,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_persist(const Params p
         float* myslab = slab + (size_t)q4 * 32 * SLAB_PITCH;
         int gcount = 0, j = 0;
         for (int item = blockIdx.x; item < total; item += gridDim.x, ++j) {
-            const int b = j & 1;
+            const int b = j % META;
             const int pass = item / n_tiles;
             const lb2_conv_io io = p.io[pass];
-            mbar_wait(meta_full(b), (j >> 1) & 1);
+            mbar_wait(meta_full(b), (j / META) & 1);
             const uint32_t kmask = tile_kmask(b);
             const int n_off = __popc(kmask);
             const int n_groups = (n_off + p.group - 1) / p.group;
@@ -334,8 +336,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_persist(const Params p
 }
 
 static size_t smem_bytes(int cout, int stages) {
-    return 1024 + (size_t)stages * (2 * A_TILE + 2 * (size_t)cout * 128) + SLAB_BYTES + MAX_KVOL * BM * sizeof(int) + 2 * BM * sizeof(int) +
-           8 * sizeof(uint32_t) + (3 * MAX_STAGES + 8) * 8 + 64;
+    return 1024 + (size_t)stages * (2 * A_TILE + 2 * (size_t)cout * 128) + SLAB_BYTES + MAX_KVOL * BM * sizeof(int) + META * BM * sizeof(int) +
+           4 * META * sizeof(uint32_t) + (3 * MAX_STAGES + 4 + 2 * META) * 8 + 64;
 }
 
 }  // namespace tc2
