@@ -26,6 +26,8 @@ using namespace tc;
 constexpr int THREADS = 320;
 constexpr int MAX_STAGES = 4;
 constexpr int MAX_KVOL = 27;
+constexpr int SLAB_PITCH = 36;
+constexpr int SLAB_BYTES = BM * SLAB_PITCH * 4;
 
 struct Params {
     int c1, c2, cout, kvol, nchunks, stages, npass;
@@ -58,7 +60,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_scatter(const Params p) {
     const uint32_t a_stage = 2u * A_TILE;
     unsigned char* a_gen = gen + w_bytes;
     const uint32_t a_base = base + w_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(a_gen + (size_t)p.stages * a_stage);
+    float* slab = reinterpret_cast<float*>(a_gen + (size_t)p.stages * a_stage);         // [4 warps][32][SLAB_PITCH] epilogue transpose
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(slab) + SLAB_BYTES);
     uint32_t* misc = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 6);
     const uint32_t bar0 = smem_u32(bars);
     auto full_a = [&](int s) { return bar0 + 8u * s; };
@@ -200,9 +203,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_scatter(const Params p) {
         __syncwarp();
     } else {
         // =========================== scatter epilogue ===========================
+        // per 32-column slab: TMEM -> registers -> the warp's smem slab (transpose) -> lanes along channels, so each
+        // red.global.add.v4.f32 instruction covers 4 rows x 128 contiguous bytes (full sectors) instead of 32 rows x 16 B
         const int q4 = warp & 3;
         const float out_scale = __ldg(reinterpret_cast<const float*>(p.wpacked) + 1);
         const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;
+        float* myslab = slab + (size_t)q4 * 32 * SLAB_PITCH;
         int j = 0;
         for (int T = t_begin; T < t_end; ++T, ++j) {
             int pass, k, pbase, cnt;
@@ -212,17 +218,25 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_scatter(const Params p) {
             const int buf = j & 1;
             mbar_wait(acc_full(buf), (j >> 1) & 1);
             tc_fence_after();
-            float* dst = p.out[pass] + (long long)max(orow, 0) * p.cout;
             for (int c0 = 0; c0 < p.cout; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld32(tmem_d + lane_base + (uint32_t)(buf * p.acc_stride + c0), v);
                 tmem_ld_wait();
-                if (orow >= 0) {
+                __syncwarp();
+                float* srow = myslab + lane * SLAB_PITCH;
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c0 + q * 4),
-                                     "f"(__uint_as_float(v[q * 4]) * out_scale), "f"(__uint_as_float(v[q * 4 + 1]) * out_scale),
-                                     "f"(__uint_as_float(v[q * 4 + 2]) * out_scale), "f"(__uint_as_float(v[q * 4 + 3]) * out_scale) : "memory");
+                for (int q = 0; q < 8; ++q)
+                    *reinterpret_cast<float4*>(srow + q * 4) = make_float4(__uint_as_float(v[q * 4]) * out_scale, __uint_as_float(v[q * 4 + 1]) * out_scale,
+                                                                           __uint_as_float(v[q * 4 + 2]) * out_scale, __uint_as_float(v[q * 4 + 3]) * out_scale);
+                __syncwarp();
+#pragma unroll
+                for (int e = lane; e < 256; e += 32) {
+                    const int rr = e >> 3, c4 = (e & 7) * 4;
+                    const int dst_row = __shfl_sync(0xffffffffu, orow, rr);
+                    if (dst_row >= 0) {
+                        const float4 a4 = *reinterpret_cast<const float4*>(myslab + rr * SLAB_PITCH + c4);
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.out[pass] + (long long)dst_row * p.cout + c0 + c4),
+                                     "f"(a4.x), "f"(a4.y), "f"(a4.z), "f"(a4.w) : "memory");
                     }
                 }
             }
@@ -283,7 +297,7 @@ __global__ void k_zero_rows(float* __restrict__ buf, const int* __restrict__ d_n
 
 static size_t smem_bytes(int cin, int cout, int stages) {
     const int nchunks = (cin + tc::KC - 1) / tc::KC;
-    return 1024 + (size_t)nchunks * 2 * cout * 128 + (size_t)stages * 2 * tc::A_TILE + (2 * MAX_STAGES + 6) * 8 + 64;
+    return 1024 + (size_t)nchunks * 2 * cout * 128 + (size_t)stages * 2 * tc::A_TILE + SLAB_BYTES + (2 * MAX_STAGES + 6) * 8 + 64;
 }
 
 static bool shape_ok(int c1, int c2, int cout, int kvol) {

@@ -20,6 +20,7 @@ order):
 from __future__ import annotations
 
 import math
+import os
 from collections import ChainMap
 
 import numpy as np
@@ -123,6 +124,7 @@ class Geometry:
         self.perm_of = {}
         # per-offset (in,out) pair lists of the 3^3 maps of the sparse levels (gather-GEMM-scatter form)
         self.pair_levels = min(3, levels)
+        self.pair_level_set = set(int(c) for c in os.environ.get("LB2_SCATTER_LEVELS", "012") if c.isdigit())
         self.pairs_of = {}
         self.pl_scratch = torch.zeros(64, **i32)
         self.pair_in = [torch.zeros(26 * n_cap, **i32) for _ in range(self.pair_levels)]
@@ -146,7 +148,7 @@ class Geometry:
 
         for l in range(self.levels):
             one(self.grid[l], l, 3, 1 << l, self.nbr3[l], self.perm3[l], l)
-            if l < self.pair_levels and self.use_pairs:
+            if l < self.pair_levels and self.use_pairs and l in self.pair_level_set:
                 h.pair_list(self.nbr3[l], N, self.d_n[l], N, 27, 13, self.pair_in[l], self.pair_out[l], self.koff[l], self.tile_off[l], self.pl_scratch)
                 self.pairs_of[self.nbr3[l].data_ptr()] = l
         for l in range(1, self.levels):
