@@ -104,11 +104,22 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc(const Params p) {
         const int row = (slot < M) ? (p.row_perm ? __ldg(p.row_perm + slot) : slot) : -1;
         row_s[threadIdx.x] = row;
         uint32_t mymask = 0;
-        for (int k = 0; k < p.kvol; ++k) {
-            int v = -1;
-            if (row >= 0) v = p.nbr ? __ldg(p.nbr + (long long)k * p.nbr_stride + row) : row;
-            idx_s[k * BM + threadIdx.x] = v;
-            if (__any_sync(0xffffffffu, v >= 0)) mymask |= 1u << k;
+        for (int k0 = 0; k0 < p.kvol; k0 += 9) {        // 9 independent loads in flight, then the votes
+            int v[9];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) {
+                const int k = k0 + q;
+                v[q] = -1;
+                if (k < p.kvol && row >= 0) v[q] = p.nbr ? __ldg(p.nbr + (long long)k * p.nbr_stride + row) : row;
+            }
+#pragma unroll
+            for (int q = 0; q < 9; ++q) {
+                const int k = k0 + q;
+                if (k < p.kvol) {
+                    idx_s[k * BM + threadIdx.x] = v[q];
+                    if (__any_sync(0xffffffffu, v[q] >= 0)) mymask |= 1u << k;
+                }
+            }
         }
         if (lane == 0 && mymask) atomicOr(&misc[1], mymask);
     }

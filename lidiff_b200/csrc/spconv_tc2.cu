@@ -99,22 +99,40 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_persist(const Params p
         const int sub = t & 7, rbase = t >> 3;
         const int D = p.stages - 1;
         int it = 0, arrived = 0, j = 0;
+        auto fetch_row = [&](int item) {                                // output row of this thread's slot in work item `item`
+            if (item >= total) return -1;
+            const int tile = item % n_tiles;
+            const int slot = tile * BM + t;
+            return (slot < M) ? (p.row_perm ? __ldg(p.row_perm + slot) : slot) : -1;
+        };
+        int next_row = fetch_row(blockIdx.x);
         for (int item = blockIdx.x; item < total; item += gridDim.x, ++j) {
             const int b = j % META;
-            const int pass = item / n_tiles, tile = item - pass * n_tiles;
+            const int pass = item / n_tiles;
             const lb2_conv_io io = p.io[pass];
             if (j >= META) mbar_wait(meta_empty(b), ((j / META) - 1) & 1);
             asm volatile("bar.sync 2, 128;" ::: "memory");              // everybody is done reading the previous tile's idx_s
             {
-                const int slot = tile * BM + t;
-                const int row = (slot < M) ? (p.row_perm ? __ldg(p.row_perm + slot) : slot) : -1;
+                const int row = next_row;
+                next_row = fetch_row(item + gridDim.x);                 // prefetch: its latency hides behind this tile's gathers
                 row_s[b * BM + t] = row;
                 uint32_t mymask = 0;
-                for (int k = 0; k < p.kvol; ++k) {
-                    int v = -1;
-                    if (row >= 0) v = p.nbr ? __ldg(p.nbr + (long long)k * p.nbr_stride + row) : row;
-                    idx_s[k * BM + t] = v;
-                    if (__any_sync(0xffffffffu, v >= 0)) mymask |= 1u << k;
+                for (int k0 = 0; k0 < p.kvol; k0 += 9) {        // 9 independent loads in flight, then the votes
+                    int v[9];
+#pragma unroll
+                    for (int q = 0; q < 9; ++q) {
+                        const int k = k0 + q;
+                        v[q] = -1;
+                        if (k < p.kvol && row >= 0) v[q] = p.nbr ? __ldg(p.nbr + (long long)k * p.nbr_stride + row) : row;
+                    }
+#pragma unroll
+                    for (int q = 0; q < 9; ++q) {
+                        const int k = k0 + q;
+                        if (k < p.kvol) {
+                            idx_s[k * BM + t] = v[q];
+                            if (__any_sync(0xffffffffu, v[q] >= 0)) mymask |= 1u << k;
+                        }
+                    }
                 }
                 if (lane == 0) wmask[b * 4 + warp] = mymask;
             }

@@ -124,7 +124,7 @@ class Geometry:
         self.perm_of = {}
         # per-offset (in,out) pair lists of the 3^3 maps of the sparse levels (gather-GEMM-scatter form)
         self.pair_levels = min(3, levels)
-        self.pair_level_set = set(int(c) for c in os.environ.get("LB2_SCATTER_LEVELS", "012") if c.isdigit())
+        self.pair_level_set = set(int(c) for c in os.environ.get("LB2_SCATTER_LEVELS", "2") if c.isdigit())
         self.pairs_of = {}
         self.pl_scratch = torch.zeros(64, **i32)
         self.pair_in = [torch.zeros(26 * n_cap, **i32) for _ in range(self.pair_levels)]
