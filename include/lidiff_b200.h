@@ -196,6 +196,15 @@ int lb2_nn_match_grid(void* h, void* stream, const int32_t* q_coords, const int3
                       const int32_t* k_coords, const int32_t* d_nk, int32_t nk_cap, lb2_grid key_grid,
                       int32_t key_stride, int32_t max_ring, int32_t* idx);
 
+/* Variant with the key lattice in shared memory: lb2_nn_table_build re-hashes the (<= 8192) keys once per scan into
+ * a compact table (`table`: lb2_nn_table_bytes() bytes), lb2_nn_match_table probes it from shared memory.  If the
+ * keys do not fit the table is marked overflowing and every query takes the exhaustive path (still exact). */
+size_t lb2_nn_table_bytes(void);
+int lb2_nn_table_build(void* h, void* stream, const int32_t* k_coords, const int32_t* d_nk, int32_t nk_cap, void* table);
+int lb2_nn_match_table(void* h, void* stream, const int32_t* q_coords, const int32_t* d_nq, int32_t nq_cap,
+                       const int32_t* k_coords, const int32_t* d_nk, int32_t nk_cap, const void* table,
+                       int32_t key_stride, int32_t max_ring, int32_t* idx);
+
 /* ---- small dense layers — torch.nn.Linear (+LeakyReLU) of the gate / head MLPs
  * (minkunet.py:165-181,376-380): y = act(x @ W^T + b [+ addend]); W is (n_out, n_in) torch layout.
  * act: 0 none, 1 LeakyReLU(0.1), 2 tanh.  rows read from d_m if non-NULL.

@@ -58,6 +58,7 @@ EXPORTS = [
     "lb2_spconv_forward", "lb2_packed_weight_bytes", "lb2_pack_weights", "lb2_nn_match", "lb2_linear",
     "lb2_gate_mul", "lb2_gather_rows", "lb2_guidance_dpm_step", "lb2_farthest_point_sample",
     "lb2_row_order", "lb2_row_order_scratch_bytes", "lb2_nn_match_grid",
+    "lb2_nn_table_bytes", "lb2_nn_table_build", "lb2_nn_match_table",
     "lb2_pair_list", "lb2_pair_list_scratch_bytes", "lb2_spconv_scatter", "lb2_spconv_scatter_supported",
 ]
 
@@ -106,6 +107,9 @@ class Lib:
         d.lb2_pair_list_scratch_bytes.restype = C.c_size_t
         d.lb2_spconv_scatter.argtypes = [vp, vp, C.POINTER(ScatterDesc)]
         d.lb2_spconv_scatter_supported.argtypes = [i32, i32, i32, i32]
+        d.lb2_nn_table_bytes.restype = C.c_size_t
+        d.lb2_nn_table_build.argtypes = [vp, vp, vp, vp, i32, vp]
+        d.lb2_nn_match_table.argtypes = [vp, vp, vp, vp, i32, vp, vp, i32, vp, i32, i32, vp]
         d.lb2_nn_match_grid.argtypes = [vp, vp, vp, vp, i32, vp, vp, i32, Grid, i32, i32, vp]
         d.lb2_linear.argtypes = [vp, vp, vp, i64, vp, vp, vp, i64, i32, vp, i32, i32, i32, vp, i64,
                                  vp, i32]
@@ -222,6 +226,16 @@ class Handle:
     def nn_match_grid(self, q, d_nq, nq_cap, k, d_nk, nk_cap, key_grid, key_stride, max_ring, idx):
         self._check(self.dll.lb2_nn_match_grid(self.hp, self._stream(), _ptr(q), _ptr(d_nq), int(nq_cap), _ptr(k), _ptr(d_nk), int(nk_cap),
                                                self._grid(key_grid), int(key_stride), int(max_ring), _ptr(idx)), "lb2_nn_match_grid")
+
+    def nn_table(self, k, d_nk, nk_cap):
+        """compact hash table of the key voxels for nn_match_table (one per conditioning scan)"""
+        t = torch.empty(int(self.dll.lb2_nn_table_bytes()), dtype=torch.uint8, device=self.device)
+        self._check(self.dll.lb2_nn_table_build(self.hp, self._stream(), _ptr(k), _ptr(d_nk), int(nk_cap), _ptr(t)), "lb2_nn_table_build")
+        return t
+
+    def nn_match_table(self, q, d_nq, nq_cap, k, d_nk, nk_cap, table, key_stride, max_ring, idx):
+        self._check(self.dll.lb2_nn_match_table(self.hp, self._stream(), _ptr(q), _ptr(d_nq), int(nq_cap), _ptr(k), _ptr(d_nk), int(nk_cap),
+                                                _ptr(table), int(key_stride), int(max_ring), _ptr(idx)), "lb2_nn_match_table")
 
     def linear(self, x, ldx, w, b, addend, ld_add, m_cap, d_m, n_in, n_out, act, y, ldy, prebias=None, pre_act=0):
         self._check(self.dll.lb2_linear(self.hp, self._stream(), _ptr(x), int(ldx), _ptr(w), _ptr(b), _ptr(addend), int(ld_add), int(m_cap),

@@ -7,6 +7,7 @@
 //   lb2_farthest_point_sample  open3d FPS (pipeline:97-99)
 #include "common.cuh"
 #include <float.h>
+#include <algorithm>
 #include "tc_common.cuh"
 
 // ---------------------------------------------------------------------------------------------------
@@ -141,6 +142,143 @@ extern "C" int lb2_nn_match_grid(void* handle, void* stream, const int32_t* q_co
         (const int4*)q_coords, d_nq, nq_cap, (const int4*)k_coords, d_nk, nk_cap, (const unsigned long long*)key_grid.keys,
         key_grid.vals + key_grid.cap_table, (unsigned)key_grid.cap_table - 1u, key_stride, max_ring, idx);
     LB2_POST_LAUNCH(h, "k_nn_match_grid");
+    return LB2_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// nn_match with the key lattice in SHARED memory: the <= 8192 keys of the partial scan are re-hashed once per scan
+// into a compact 16384-slot table (128 KB keys + 64 KB rows) that every CTA copies into its shared memory, so the
+// 27-125 probes of a query are smem accesses instead of L2 round trips.  Same shell search and tie rule as above.
+// ---------------------------------------------------------------------------------------------------
+#define NNT_SLOTS 16384
+#define NNT_THREADS 1024
+
+__global__ void k_nn_table_build(const int4* __restrict__ keys, const int* __restrict__ d_nk, int nk_cap,
+                                 unsigned long long* __restrict__ tkeys, int* __restrict__ trows, int* __restrict__ overflow) {
+    const int nk = d_nk ? min(*d_nk, nk_cap) : nk_cap;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j == 0) *overflow = (nk > NNT_SLOTS / 2) ? 1 : 0;
+    if (j >= nk || nk > NNT_SLOTS / 2) return;
+    const int4 c = __ldg(keys + j);
+    unsigned long long key;
+    if (!lb2_pack_key(c.x, c.y, c.z, c.w, key)) return;            // out-of-range keys can never be probed
+    unsigned slot = lb2_hash(key) & (NNT_SLOTS - 1);
+    while (true) {
+        const unsigned long long prev = atomicCAS(tkeys + slot, (unsigned long long)LB2_KEY_EMPTY, key);
+        if (prev == LB2_KEY_EMPTY || prev == key) break;
+        slot = (slot + 1) & (NNT_SLOTS - 1);
+    }
+    atomicMin(trows + slot, j);                                    // duplicate coordinates: lowest row wins (tie rule)
+}
+
+__global__ void __launch_bounds__(NNT_THREADS, 1) k_nn_match_table(const int4* __restrict__ q, const int* __restrict__ d_nq, int nq_cap,
+                                                                   const int4* __restrict__ keys, const int* __restrict__ d_nk, int nk_cap,
+                                                                   const unsigned long long* __restrict__ tkeys, const int* __restrict__ trows,
+                                                                   int ks, int max_ring, int* __restrict__ idx) {
+    extern __shared__ unsigned char nnt_smem[];
+    unsigned long long* sk = reinterpret_cast<unsigned long long*>(nnt_smem);
+    int* sr = reinterpret_cast<int*>(sk + NNT_SLOTS);
+    for (int i = threadIdx.x; i < NNT_SLOTS / 2; i += NNT_THREADS) reinterpret_cast<ulonglong2*>(sk)[i] = __ldg(reinterpret_cast<const ulonglong2*>(tkeys) + i);
+    for (int i = threadIdx.x; i < NNT_SLOTS / 4; i += NNT_THREADS) reinterpret_cast<int4*>(sr)[i] = __ldg(reinterpret_cast<const int4*>(trows) + i);
+    __syncthreads();
+    const int nq = d_nq ? min(*d_nq, nq_cap) : nq_cap;
+    const int nk = d_nk ? min(*d_nk, nk_cap) : nk_cap;
+    const int lane = threadIdx.x & 31;
+    for (int i0 = blockIdx.x * NNT_THREADS; i0 < nq; i0 += gridDim.x * NNT_THREADS) {
+        const int i = i0 + threadIdx.x;
+        const bool live = i < nq;
+        const int4 c = live ? __ldg(q + i) : make_int4(0, 0, 0, 0);
+        const int cx = floor_div(c.y + ks / 2, ks), cy = floor_div(c.z + ks / 2, ks), cz = floor_div(c.w + ks / 2, ks);
+        unsigned long long best = ~0ull;
+        int best_j = 0x7fffffff;
+        bool settled = !live;
+        for (int r = 0; r <= max_ring && !settled; ++r) {
+            for (int dz = -r; dz <= r; ++dz) {
+                for (int dy = -r; dy <= r; ++dy) {
+                    const bool face = (abs(dz) == r) || (abs(dy) == r);
+                    const int step = face ? 1 : max(2 * r, 1);
+                    for (int dx = -r; dx <= r; dx += step) {
+                        const int kx = (cx + dx) * ks, ky = (cy + dy) * ks, kz = (cz + dz) * ks;
+                        unsigned long long key;
+                        if (!lb2_pack_key(c.x, kx, ky, kz, key)) continue;
+                        unsigned slot = lb2_hash(key) & (NNT_SLOTS - 1);
+                        int j = -1;
+                        while (true) {
+                            const unsigned long long kk = sk[slot];
+                            if (kk == key) { j = sr[slot]; break; }
+                            if (kk == LB2_KEY_EMPTY) break;
+                            slot = (slot + 1) & (NNT_SLOTS - 1);
+                        }
+                        if (j < 0) continue;
+                        const long long ex = c.y - kx, ey = c.z - ky, ez = c.w - kz;
+                        const unsigned long long d = (unsigned long long)(ex * ex + ey * ey + ez * ez);
+                        if (d < best || (d == best && j < best_j)) { best = d; best_j = j; }
+                    }
+                }
+            }
+            const unsigned long long bound = (unsigned long long)ks * ks * (2 * r + 1) * (2 * r + 1);
+            settled = (best != ~0ull) && (4ull * best < bound);
+        }
+        unsigned pending = __ballot_sync(0xffffffffu, !settled);
+        while (pending) {
+            const int src = __ffs(pending) - 1;
+            pending &= pending - 1;
+            const int qb = __shfl_sync(0xffffffffu, c.x, src), qx = __shfl_sync(0xffffffffu, c.y, src);
+            const int qy = __shfl_sync(0xffffffffu, c.z, src), qz = __shfl_sync(0xffffffffu, c.w, src);
+            unsigned long long bd = ~0ull;
+            int bj = 0x7fffffff;
+            for (int j = lane; j < nk; j += 32) {
+                const int4 kc = __ldg(keys + j);
+                const long long ex = qx - kc.y, ey = qy - kc.z, ez = qz - kc.w;
+                unsigned long long d = (unsigned long long)(ex * ex + ey * ey + ez * ez);
+                if (qb != kc.x) d += 1ull << 62;
+                if (d < bd) { bd = d; bj = j; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const unsigned long long od = __shfl_xor_sync(0xffffffffu, bd, o);
+                const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+                if (od < bd || (od == bd && oj < bj)) { bd = od; bj = oj; }
+            }
+            if (lane == src) best_j = (bj == 0x7fffffff) ? 0 : bj;
+        }
+        if (live) idx[i] = best_j;
+    }
+}
+
+extern "C" size_t lb2_nn_table_bytes(void) { return (size_t)NNT_SLOTS * 12 + 16; }
+
+extern "C" int lb2_nn_table_build(void* handle, void* stream, const int32_t* k_coords, const int32_t* d_nk, int32_t nk_cap, void* table) {
+    Lb2Handle* h = (Lb2Handle*)handle;
+    LB2_REQUIRE(h, h && k_coords && table && nk_cap > 0, "nn_table_build");
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned long long* tk = (unsigned long long*)table;
+    int* tr = (int*)(tk + NNT_SLOTS);
+    if (cudaMemsetAsync(tk, 0xFF, (size_t)NNT_SLOTS * 8, s) != cudaSuccess || cudaMemsetAsync(tr, 0x7F, (size_t)NNT_SLOTS * 4, s) != cudaSuccess)
+        return lb2_fail(h, LB2_ERR_CUDA, "nn_table memset%s", "");
+    k_nn_table_build<<<cdiv(nk_cap, 256), 256, 0, s>>>((const int4*)k_coords, d_nk, nk_cap, tk, tr, tr + NNT_SLOTS);
+    LB2_POST_LAUNCH(h, "k_nn_table_build");
+    return LB2_OK;
+}
+
+extern "C" int lb2_nn_match_table(void* handle, void* stream, const int32_t* q_coords, const int32_t* d_nq, int32_t nq_cap,
+                                  const int32_t* k_coords, const int32_t* d_nk, int32_t nk_cap, const void* table,
+                                  int32_t key_stride, int32_t max_ring, int32_t* idx) {
+    Lb2Handle* h = (Lb2Handle*)handle;
+    LB2_REQUIRE(h, h && q_coords && k_coords && idx && table && nq_cap > 0 && nk_cap > 0, "nn_match_table");
+    LB2_REQUIRE(h, key_stride > 0 && key_stride % 2 == 0 && max_ring >= 0 && max_ring <= 16, "nn_match_table stride/ring");
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_nn_match_table, cudaFuncAttributeMaxDynamicSharedMemorySize, NNT_SLOTS * 12);
+        if (e != cudaSuccess) return lb2_fail(h, LB2_ERR_CUDA, "k_nn_match_table smem attribute: %s", cudaGetErrorString(e));
+        configured = true;
+    }
+    const unsigned long long* tk = (const unsigned long long*)table;
+    const int* tr = (const int*)(tk + NNT_SLOTS);
+    const unsigned grid = std::min<unsigned>(h->num_sms, cdiv(nq_cap, NNT_THREADS));
+    k_nn_match_table<<<grid, NNT_THREADS, NNT_SLOTS * 12, (cudaStream_t)stream>>>((const int4*)q_coords, d_nq, nq_cap, (const int4*)k_coords, d_nk, nk_cap,
+                                                                                  tk, tr, key_stride, max_ring, idx);
+    LB2_POST_LAUNCH(h, "k_nn_match_table");
     return LB2_OK;
 }
 

@@ -256,6 +256,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_persist(const Params p
             const int n_off = __popc(kmask);
             const int n_groups = (n_off + p.group - 1) / p.group;
             const int* rows = row_s + b * BM + q4 * 32;                 // this warp's 32 output rows
+            int orows[8], gidx[8];                                      // the 8 rows this lane serves in the epilogue + their gate rows
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                orows[i] = rows[(lane >> 3) + 4 * i];
+                gidx[i] = (io.gate_table && io.gate_idx && orows[i] >= 0) ? __ldg(io.gate_idx + orows[i]) : 0;
+            }
             for (int g = 0; g < max(n_groups, 1); ++g) {
                 const bool last = g >= n_groups - 1;
                 const int buf = gcount % p.nbuf;
@@ -298,41 +304,41 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_persist(const Params p
                             *reinterpret_cast<float4*>(srow + q * 4) = make_float4(acc[q * 4] * out_scale, acc[q * 4 + 1] * out_scale,
                                                                                    acc[q * 4 + 2] * out_scale, acc[q * 4 + 3] * out_scale);
                         __syncwarp();
-#pragma unroll 2
-                        for (int e = lane; e < 256; e += 32) {
-                            const int rr = e >> 3;
-                            const int col = c0 + (e & 7) * 4;
-                            const int orow = rows[rr];
+                        // all global loads of this slab first (8 rows per lane: memory-level parallelism), then the math + stores
+                        const int lc4 = (lane & 7) * 4;
+                        const int col = c0 + lc4;
+                        float4 pre[8], res[8], gat[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            pre[i] = make_float4(0.f, 0.f, 0.f, 0.f); res[i] = pre[i]; gat[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+                            if (orows[i] >= 0) {
+                                const long long ro = (long long)orows[i] * p.cout + col;
+                                if (io.pre_add) pre[i] = __ldg(reinterpret_cast<const float4*>(io.pre_add + ro));
+                                if (io.residual) res[i] = __ldg(reinterpret_cast<const float4*>(io.residual + ro));
+                                if (io.gate_table) gat[i] = __ldg(reinterpret_cast<const float4*>(io.gate_table + (long long)gidx[i] * p.cout + col));
+                            }
+                        }
+                        float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f), h4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (p.scale) { s4 = __ldg(reinterpret_cast<const float4*>(p.scale + col)); h4 = __ldg(reinterpret_cast<const float4*>(p.shift + col)); }
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int orow = orows[i];
                             if (orow < 0) continue;
-                            const long long ro = (long long)orow * p.cout;
-                            const float4 a4 = *reinterpret_cast<const float4*>(myslab + rr * SLAB_PITCH + (e & 7) * 4);
-                            float y[4] = {a4.x, a4.y, a4.z, a4.w};
-                            if (io.pre_add) {
-                                const float4 t4 = __ldg(reinterpret_cast<const float4*>(io.pre_add + ro + col));
-                                y[0] += t4.x; y[1] += t4.y; y[2] += t4.z; y[3] += t4.w;
-                            }
-                            if (p.scale) {
-                                const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.scale + col));
-                                const float4 h4 = __ldg(reinterpret_cast<const float4*>(p.shift + col));
-                                y[0] = fmaf(y[0], s4.x, h4.x); y[1] = fmaf(y[1], s4.y, h4.y); y[2] = fmaf(y[2], s4.z, h4.z); y[3] = fmaf(y[3], s4.w, h4.w);
-                            }
-                            if (io.residual) {
-                                const float4 t4 = __ldg(reinterpret_cast<const float4*>(io.residual + ro + col));
-                                y[0] += t4.x; y[1] += t4.y; y[2] += t4.z; y[3] += t4.w;
-                            }
+                            const int rr = (lane >> 3) + 4 * i;
+                            const long long ro = (long long)orow * p.cout + col;
+                            const float4 a4 = *reinterpret_cast<const float4*>(myslab + rr * SLAB_PITCH + lc4);
+                            float y[4] = {a4.x + pre[i].x, a4.y + pre[i].y, a4.z + pre[i].z, a4.w + pre[i].w};
+                            y[0] = fmaf(y[0], s4.x, h4.x) + res[i].x; y[1] = fmaf(y[1], s4.y, h4.y) + res[i].y;
+                            y[2] = fmaf(y[2], s4.z, h4.z) + res[i].z; y[3] = fmaf(y[3], s4.w, h4.w) + res[i].w;
                             if (p.relu) {
 #pragma unroll
                                 for (int q = 0; q < 4; ++q) y[q] = fmaxf(y[q], 0.f);
                             }
-                            if (io.out) *reinterpret_cast<float4*>(io.out + ro + col) = make_float4(y[0], y[1], y[2], y[3]);
+                            if (io.out) *reinterpret_cast<float4*>(io.out + ro) = make_float4(y[0], y[1], y[2], y[3]);
                             if (io.out_h) store_split4(io.out_h, orow, p.cout, col, y);
                             if (io.out_gated || io.out_gated_h) {
-                                if (io.gate_table) {
-                                    const long long gi = io.gate_idx ? __ldg(io.gate_idx + orow) : 0;
-                                    const float4 g4 = __ldg(reinterpret_cast<const float4*>(io.gate_table + gi * p.cout + col));
-                                    y[0] *= g4.x; y[1] *= g4.y; y[2] *= g4.z; y[3] *= g4.w;
-                                }
-                                if (io.out_gated) *reinterpret_cast<float4*>(io.out_gated + ro + col) = make_float4(y[0], y[1], y[2], y[3]);
+                                y[0] *= gat[i].x; y[1] *= gat[i].y; y[2] *= gat[i].z; y[3] *= gat[i].w;
+                                if (io.out_gated) *reinterpret_cast<float4*>(io.out_gated + ro) = make_float4(y[0], y[1], y[2], y[3]);
                                 if (io.out_gated_h) store_split4(io.out_gated_h, orow, p.cout, col, y);
                             }
                         }

@@ -239,6 +239,12 @@ class FakeHandle:
     def nn_match_grid(self, q, d_nq, nq_cap, k, d_nk, nk_cap, key_grid, key_stride, max_ring, idx):
         self.nn_match(q, d_nq, nq_cap, k, d_nk, nk_cap, 0, idx)
 
+    def nn_table(self, k, d_nk, nk_cap):
+        return torch.zeros(16, dtype=torch.uint8)
+
+    def nn_match_table(self, q, d_nq, nq_cap, k, d_nk, nk_cap, table, key_stride, max_ring, idx):
+        self.nn_match(q, d_nq, nq_cap, k, d_nk, nk_cap, 0, idx)
+
     @staticmethod
     def _act(v, act):
         return torch.nn.functional.leaky_relu(v, 0.1) if act == 1 else (torch.tanh(v) if act == 2 else v)

@@ -323,13 +323,13 @@ def test_nn_match_grid_equals_brute_force():
     h = H()
     g = torch.Generator().manual_seed(4)
     # keys: occupied stride-16 cells of a noisy "scan"; queries: near, on ties, and far outside
-    base = torch.randn(30_000, 3, generator=g) * torch.tensor([400.0, 400.0, 40.0])
+    base = torch.randn(7_000, 3, generator=g) * torch.tensor([400.0, 400.0, 40.0])        # <= 8192 key cells: table path
     kc = torch.cat([torch.zeros(base.shape[0], 1), torch.round(base)], 1)
     geo = Geometry(h, kc.shape[0], with_up=False)
     geo.build(kc.to(DEV).contiguous(), kc.shape[0])
     nk = geo.sizes()[4]
     keys = geo.C[4][:nk]
-    q_near = torch.round(base[:20_000] + torch.randn(20_000, 3, generator=g) * 20)
+    q_near = torch.round(base[:7_000].repeat(3, 1) + torch.randn(21_000, 3, generator=g) * 20)
     q_tie = keys[:2_000, 1:].cpu().float() + 8.0                         # exactly between lattice cells
     q_far = torch.round(torch.randn(3_000, 3, generator=g) * 3000)
     q = torch.cat([q_near, q_tie, q_far], 0)
@@ -339,6 +339,10 @@ def test_nn_match_grid_equals_brute_force():
     h.nn_match(q, None, q.shape[0], keys, geo.d_n[4], kc.shape[0], 0, a)
     h.nn_match_grid(q, None, q.shape[0], geo.C[4], geo.d_n[4], kc.shape[0], geo.grid[4], 16, 4, b)
     assert torch.equal(a, b)
+    c = torch.empty_like(a)
+    tab = h.nn_table(geo.C[4], geo.d_n[4], kc.shape[0])
+    h.nn_match_table(q, None, q.shape[0], geo.C[4], geo.d_n[4], kc.shape[0], tab, 16, 4, c)
+    assert torch.equal(a, c), "shared-memory table variant"
     ref = ome.match_part_to_full(q[:5000].cpu(), keys.cpu())
     assert torch.equal(a[:5000].long().cpu(), ref)
 
