@@ -466,7 +466,6 @@ class DenoiseEngine:
         skips, _ = self._encoder(self.enc, g, F0, 1, "cenc")
         self.part_F = skips[4][0]                                      # (N cap, 256), rows valid < d_n[4]
         self.part_C, self.part_dn, self.part_grid = g.C[4], g.d_n[4], g.grid[4]
-        self.part_table = self.h.nn_table(self.part_C, self.part_dn, N)
         self.part_cap = N
         self.A_cond = self._part_A(self.part_F, N, self.part_dn, "c")
 
@@ -484,7 +483,8 @@ class DenoiseEngine:
         nn = []
         for l in range(5):
             ix = self.buf(f"nn{l}", (N,), torch.int32)
-            h.nn_match_table(g.C[l], g.d_n[l], N, self.part_C, self.part_dn, self.part_cap, self.part_table, 16, 4, ix)
+            # (the shared-memory-table variant lb2_nn_match_table measured slower: 2.1 vs 1.7 ms for the 5 levels)
+            h.nn_match_grid(g.C[l], g.d_n[l], N, self.part_C, self.part_dn, self.part_cap, self.part_grid, 16, 4, ix)
             nn.append(ix)
         tabs_c = self._gate_tables(self.A_cond, self.part_cap, self.part_dn, i, "c")
         gates = [[(tabs_c[k], nn[GATE_LEVEL[k]]), (self.table_u[k][i:i + 1], None)] for k in range(8)]

@@ -63,7 +63,7 @@ def main():
     g_.build(ca, N)
     marks[1].record()
     for l in range(5):
-        eng.h.nn_match_table(g_.C[l], g_.d_n[l], N, eng.part_C, eng.part_dn, eng.part_cap, eng.part_table, 16, 4, eng.buf(f"nn{l}", (N,), torch.int32))
+        eng.h.nn_match_grid(g_.C[l], g_.d_n[l], N, eng.part_C, eng.part_dn, eng.part_cap, eng.part_grid, 16, 4, eng.buf(f"nn{l}", (N,), torch.int32))
     marks[2].record()
     eng._gate_tables(eng.A_cond, eng.part_cap, eng.part_dn, 0, "c")
     marks[3].record()

@@ -348,8 +348,9 @@ def test_nn_match_grid_equals_brute_force():
 
 
 @pytest.mark.parametrize("c1,c2,cout,lvl,spread", [(32, 0, 32, 0, 1.0), (96, 32, 96, 1, 0.3), (128, 64, 128, 2, 0.3), (64, 0, 64, 2, 1.0), (128, 0, 128, 0, 0.05)])
-def test_scatter_split_equals_output_stationary_conv(c1, c2, cout, lvl, spread):
+def test_scatter_split_equals_output_stationary_conv(c1, c2, cout, lvl, spread, monkeypatch):
     """gather-GEMM-scatter (off-centre pairs) + centre 1x1 conv with pre_add == the plain 3^3 convolution, two passes"""
+    monkeypatch.setenv("LB2_SCATTER_LEVELS", "012")            # pair lists for every sparse level in this test
     from lidiff_b200 import _lib
     from lidiff_b200._lib import ConvDesc, ConvIO, ScatterDesc
     from lidiff_b200.engine import Geometry
