@@ -1,0 +1,391 @@
+// K4 (variant B, persistent, 256 output channels) — specialisation of spconv_tc2.cu for Cout = 256, the layers that hold most
+// of the FLOPs (L3 decoder, L4).  With N = 256 the accumulator alone fills half of TMEM, so the generic kernel has to
+// keep the fp32 running total of the two-level accumulation in the other half and can neither ping-pong accumulators
+// nor overlap drains/epilogue with the next MMAs (measured: ~25 % of these layers' time).  Here the running total lives
+// in the REGISTERS of eight drain warps instead (setmaxnreg: producer / MMA warpgroups shrink to 56 registers, the two
+// drain warpgroups grow to 200), TMEM holds two 256-column accumulators in ping-pong, and a group's drain as well as the
+// whole epilogue overlap with the tensor-core work of the next group / tile.
+//   WG0 warps 0-3   A producers (cp.async from the fp16 split companions only; neighbour rows re-read per offset)
+//   WG1 warp 4 MMA issuer, warp 5 weight loader (warps 6,7 idle)
+//   WG2 warps 8-11  drain + epilogue of output channels   0..127        WG3 warps 12-15: channels 128..255
+// Same math and results as k_spconv_tc / k_spconv_tc_n256 (tests compare them).
+#include "common.cuh"
+#include <algorithm>
+#include <stdlib.h>
+#include "tc_common.cuh"
+
+namespace tc3 {
+using namespace tc;
+
+constexpr int THREADS = 512;
+constexpr int NCOLS = 256;
+constexpr int MAX_KVOL = 27;
+constexpr int MAX_STAGES = 4;
+constexpr int SLAB_COLS = 16;
+constexpr int SLAB_PITCH = SLAB_COLS + 4;             // floats per slab row
+constexpr int SLAB_BYTES = 8 * 32 * SLAB_PITCH * 4;   // 8 drain warps x 32 rows
+constexpr int META = 4;                               // ring of per-tile metadata (row ids, offset masks).  Must exceed the cp.async
+                                                      // lookahead D <= MAX_STAGES-1: a tile's last full_a arrival is issued up to D
+                                                      // stage-iterations (= up to D tiles) later, while re-using a slot waits for the
+                                                      // tile META positions back to be completely drained.
+
+struct Params {
+    int c1, c2, cout, kvol;
+    const unsigned char* wpacked;
+    const float* scale;
+    const float* shift;
+    int relu;
+    const int* nbr;
+    long long nbr_stride;
+    const int* d_mout;
+    int mout_cap;
+    const int* row_perm;
+    int stages, nchunks, tmem_cols, tot_col, group, nbuf, acc_stride, npass;
+    lb2_conv_io io[2];
+};
+
+__global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_n256(const Params p) {
+    extern __shared__ unsigned char smem_raw[];
+    const int M = p.d_mout ? min(*p.d_mout, p.mout_cap) : p.mout_cap;
+    const int n_tiles = (M + BM - 1) / BM;
+    const int total = n_tiles * p.npass;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ctot = p.c1 + p.c2;
+
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    unsigned char* gen = smem_raw + (base - raw);
+    const uint32_t b_tile = (uint32_t)NCOLS * 128u;
+    const uint32_t stage_bytes = 2u * A_TILE + 2u * b_tile;
+    unsigned char* tail = gen + (size_t)p.stages * stage_bytes;
+    float* slab = reinterpret_cast<float*>(tail);                                   // [8 warps][32][SLAB_PITCH]
+    int* row_s = reinterpret_cast<int*>(tail + SLAB_BYTES);                          // [META][BM]
+    uint32_t* wmask = reinterpret_cast<uint32_t*>(row_s + META * BM);                // [META][4] per-warp offset masks
+    uint64_t* bars = reinterpret_cast<uint64_t*>(wmask + 4 * META);
+    uint32_t* misc = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + 4 + 2 * META);
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_a = [&](int s) { return bar0 + 8u * s; };
+    auto full_b = [&](int s) { return bar0 + 8u * (MAX_STAGES + s); };
+    auto empty = [&](int s) { return bar0 + 8u * (2 * MAX_STAGES + s); };
+    auto acc_full = [&](int b) { return bar0 + 8u * (3 * MAX_STAGES + b); };
+    auto acc_empty = [&](int b) { return bar0 + 8u * (3 * MAX_STAGES + 2 + b); };
+    auto meta_full = [&](int b) { return bar0 + 8u * (3 * MAX_STAGES + 4 + b); };
+    auto meta_empty = [&](int b) { return bar0 + 8u * (3 * MAX_STAGES + 4 + META + b); };
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(full_a(s), 128); mbar_init(full_b(s), 1); mbar_init(empty(s), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), 256); }        // 8 drain warps
+        for (int b = 0; b < META; ++b) { mbar_init(meta_full(b), 1); mbar_init(meta_empty(b), 258); }   // MMA + loader + 256 drain threads
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&misc[0])), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = misc[0];
+    const float out_scale = __ldg(reinterpret_cast<const float*>(p.wpacked) + 1);
+    auto tile_kmask = [&](int b) { return wmask[b * 4] | wmask[b * 4 + 1] | wmask[b * 4 + 2] | wmask[b * 4 + 3]; };
+
+    if (warp < 4) {
+        // =========================== WG0: A producers ===========================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        const int t = threadIdx.x;
+        const int sub = t & 7, rbase = t >> 3;
+        const int D = p.stages - 1;
+        int it = 0, arrived = 0, j = 0;
+        auto fetch_row = [&](int item) {
+            if (item >= total) return -1;
+            const int slot = (item % n_tiles) * BM + t;
+            return (slot < M) ? (p.row_perm ? __ldg(p.row_perm + slot) : slot) : -1;
+        };
+        int next_row = fetch_row(blockIdx.x);
+        for (int item = blockIdx.x; item < total; item += gridDim.x, ++j) {
+            const int b = j % META;
+            const int pass = item / n_tiles;
+            const lb2_conv_io io = p.io[pass];
+            if (j >= META) mbar_wait(meta_empty(b), ((j / META) - 1) & 1);
+            {
+                const int row = next_row;
+                next_row = fetch_row(item + gridDim.x);
+                row_s[b * BM + t] = row;
+                uint32_t mymask = 0;
+                for (int k0 = 0; k0 < p.kvol; k0 += 9) {
+                    int v[9];
+#pragma unroll
+                    for (int q = 0; q < 9; ++q) {
+                        const int k = k0 + q;
+                        v[q] = -1;
+                        if (k < p.kvol && row >= 0) v[q] = p.nbr ? __ldg(p.nbr + (long long)k * p.nbr_stride + row) : row;
+                    }
+#pragma unroll
+                    for (int q = 0; q < 9; ++q)
+                        if (k0 + q < p.kvol && __any_sync(0xffffffffu, v[q] >= 0)) mymask |= 1u << (k0 + q);
+                }
+                if (lane == 0) wmask[b * 4 + warp] = mymask;
+            }
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+            if (t == 0) mbar_arrive(meta_full(b));
+            const uint32_t kmask = tile_kmask(b);
+            int myrows[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) myrows[q] = row_s[b * BM + rbase + 16 * q];
+            auto load_src = [&](int k, int (&dst)[8]) {              // neighbour rows of this thread's 8 tile rows at offset k
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    dst[q] = -1;
+                    if (myrows[q] >= 0) dst[q] = p.nbr ? __ldg(p.nbr + (long long)k * p.nbr_stride + myrows[q]) : myrows[q];
+                }
+            };
+            int src[8], nxt[8];
+            uint32_t km = kmask;
+            if (km) load_src(__ffs(km) - 1, src);
+            while (km) {
+                km &= km - 1;
+                if (km) load_src(__ffs(km) - 1, nxt);                 // prefetch the next offset's rows behind this offset's copies
+                for (int c = 0; c < p.nchunks; ++c, ++it) {
+                    const int s = it % p.stages;
+                    mbar_wait(empty(s), ((it / p.stages) & 1) ^ 1);
+                    const uint32_t a_hi_u = base + (uint32_t)s * stage_bytes;
+                    const int ch = c * KC + sub * 8;
+                    if (ch < ctot) {
+                        const bool first = ch < p.c1;
+                        const int cw = first ? p.c1 : p.c2;
+                        const int co = first ? ch : ch - p.c1;
+                        produce_a_split(reinterpret_cast<const __half*>(first ? io.in1_h : io.in2_h), cw, co, src, a_hi_u, a_hi_u + A_TILE, rbase, sub);
+                    }
+                    cp_async_commit();
+                    if (it >= D) {
+                        cp_async_wait_dyn(D);
+                        fence_proxy_async();
+                        mbar_arrive(full_a(arrived % p.stages));
+                        ++arrived;
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) src[q] = nxt[q];
+            }
+        }
+        cp_async_wait<0>();
+        fence_proxy_async();
+        for (; arrived < it; ++arrived) mbar_arrive(full_a(arrived % p.stages));
+    } else if (warp < 8) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        if (warp == 4 && lane == 0) {
+            // =========================== MMA issuer ===========================
+            const uint32_t idesc = make_idesc(NCOLS);
+            int it = 0, gcount = 0, j = 0;
+            for (int item = blockIdx.x; item < total; item += gridDim.x, ++j) {
+                const int b = j % META;
+                mbar_wait(meta_full(b), (j / META) & 1);
+                const uint32_t kmask = tile_kmask(b);
+                const int n_off = __popc(kmask);
+                int in_group = 0, off_idx = 0;
+                for (uint32_t km = kmask; km; km &= km - 1, ++off_idx) {
+                    const int buf = gcount & 1;
+                    const uint32_t tmem_acc = tmem_d + (uint32_t)(buf * NCOLS);
+                    if (in_group == 0 && gcount >= 2) {
+                        mbar_wait(acc_empty(buf), ((gcount >> 1) - 1) & 1);
+                        tc_fence_after();
+                    }
+                    for (int c = 0; c < p.nchunks; ++c, ++it) {
+                        const int s = it % p.stages;
+                        const uint32_t par = (it / p.stages) & 1;
+                        mbar_wait(full_b(s), par);
+                        mbar_wait(full_a(s), par);
+                        tc_fence_after();
+                        const uint32_t a_hi = base + (uint32_t)s * stage_bytes, a_lo = a_hi + A_TILE;
+                        const uint32_t b_hi = a_lo + A_TILE, b_lo = b_hi + b_tile;
+                        const int ksteps = min(KC, ctot - c * KC) >> 4;
+                        for (int ks = 0; ks < ksteps; ++ks) {
+                            const uint64_t dah = make_desc(a_hi + ks * 32), dal = make_desc(a_lo + ks * 32);
+                            const uint64_t dbh = make_desc(b_hi + ks * 32), dbl = make_desc(b_lo + ks * 32);
+                            umma(tmem_acc, dah, dbh, idesc, (in_group | c | ks) ? 1u : 0u);
+                            umma(tmem_acc, dal, dbh, idesc, 1);
+                            umma(tmem_acc, dah, dbl, idesc, 1);
+                        }
+                        umma_commit(empty(s));
+                    }
+                    if (++in_group == p.group || off_idx == n_off - 1) {
+                        umma_commit(acc_full(buf));
+                        in_group = 0;
+                        ++gcount;
+                    }
+                }
+                mbar_arrive(meta_empty(b));
+            }
+        } else if (warp == 5 && lane == 0) {
+            // =========================== weight loader ===========================
+            int it = 0, j = 0;
+            for (int item = blockIdx.x; item < total; item += gridDim.x, ++j) {
+                const int b = j % META;
+                mbar_wait(meta_full(b), (j / META) & 1);
+                const uint32_t kmask = tile_kmask(b);
+                for (uint32_t km = kmask; km; km &= km - 1) {
+                    const int k = __ffs(km) - 1;
+                    for (int c = 0; c < p.nchunks; ++c, ++it) {
+                        const int s = it % p.stages;
+                        mbar_wait(empty(s), ((it / p.stages) & 1) ^ 1);
+                        const uint32_t dst = base + (uint32_t)s * stage_bytes + 2u * A_TILE;
+                        const unsigned char* src = p.wpacked + PACK_HEADER + ((size_t)k * p.nchunks + c) * (2u * b_tile);
+                        mbar_expect_tx(full_b(s), 2u * b_tile);
+                        bulk_g2s(dst, src, 2u * b_tile, full_b(s));
+                    }
+                }
+                mbar_arrive(meta_empty(b));
+            }
+        }
+        __syncwarp();
+    } else {
+        // =========================== WG2 / WG3: drain (register-resident fp32 total) + epilogue ===========================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+        const int q4 = warp & 3;                                   // TMEM lane quarter
+        const int cb = (warp >= 12) ? 128 : 0;                     // this warpgroup's first output channel
+        const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;
+        float* myslab = slab + (size_t)(warp - 8) * 32 * SLAB_PITCH;
+        float tot[128];
+        int gcount = 0, j = 0;
+        for (int item = blockIdx.x; item < total; item += gridDim.x, ++j) {
+            const int b = j % META;
+            const int pass = item / n_tiles;
+            const lb2_conv_io io = p.io[pass];
+            mbar_wait(meta_full(b), (j / META) & 1);
+            const uint32_t kmask = tile_kmask(b);
+            const int n_off = __popc(kmask);
+            const int n_groups = (n_off + p.group - 1) / p.group;
+            const int* rows = row_s + b * BM + q4 * 32;
+            int orows[4], gidx[4];                                  // the 4 rows this lane serves in the epilogue
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                orows[i] = rows[(lane >> 2) + 8 * i];
+                gidx[i] = (io.gate_table && io.gate_idx && orows[i] >= 0) ? __ldg(io.gate_idx + orows[i]) : 0;
+            }
+            if (n_groups == 0) {
+#pragma unroll
+                for (int q = 0; q < 128; ++q) tot[q] = 0.f;
+            }
+            for (int g = 0; g < n_groups; ++g) {
+                const int buf = gcount & 1;
+                mbar_wait(acc_full(buf), (gcount >> 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    uint32_t r[32];
+                    tmem_ld32(tmem_d + lane_base + (uint32_t)(buf * NCOLS + cb + cc * 32), r);
+                    tmem_ld_wait();
+                    if (g == 0) {
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) tot[cc * 32 + q] = __uint_as_float(r[q]);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) tot[cc * 32 + q] = __fadd_rn(tot[cc * 32 + q], __uint_as_float(r[q]));
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(acc_empty(buf));                       // accumulator free again: the MMA warp runs on while we finish
+                ++gcount;
+            }
+            // ---- epilogue from registers, 16 channels at a time through the warp's slab (coalesced global accesses) ----
+            const int lc4 = (lane & 3) * 4;
+#pragma unroll
+            for (int cs = 0; cs < 8; ++cs) {
+                __syncwarp();
+                float* srow = myslab + lane * SLAB_PITCH;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    *reinterpret_cast<float4*>(srow + q * 4) = make_float4(tot[cs * 16 + q * 4] * out_scale, tot[cs * 16 + q * 4 + 1] * out_scale,
+                                                                           tot[cs * 16 + q * 4 + 2] * out_scale, tot[cs * 16 + q * 4 + 3] * out_scale);
+                __syncwarp();
+                const int col = cb + cs * 16 + lc4;
+                float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f), h4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.scale) { s4 = __ldg(reinterpret_cast<const float4*>(p.scale + col)); h4 = __ldg(reinterpret_cast<const float4*>(p.shift + col)); }
+#pragma unroll
+                for (int i0 = 0; i0 < 4; i0 += 2) {                 // two rows per batch: loads first, then math + stores
+                    float4 pre[2], res[2], gat[2];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int i = i0 + u;
+                        pre[u] = make_float4(0.f, 0.f, 0.f, 0.f); res[u] = pre[u]; gat[u] = make_float4(1.f, 1.f, 1.f, 1.f);
+                        if (orows[i] >= 0) {
+                            const long long ro = (long long)orows[i] * NCOLS + col;
+                            if (io.pre_add) pre[u] = __ldg(reinterpret_cast<const float4*>(io.pre_add + ro));
+                            if (io.residual) res[u] = __ldg(reinterpret_cast<const float4*>(io.residual + ro));
+                            if (io.gate_table) gat[u] = __ldg(reinterpret_cast<const float4*>(io.gate_table + (long long)gidx[i] * NCOLS + col));
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int i = i0 + u;
+                        const int orow = orows[i];
+                        if (orow < 0) continue;
+                        const int rr = (lane >> 2) + 8 * i;
+                        const long long ro = (long long)orow * NCOLS + col;
+                        const float4 a4 = *reinterpret_cast<const float4*>(myslab + rr * SLAB_PITCH + lc4);
+                        float y[4] = {a4.x + pre[u].x, a4.y + pre[u].y, a4.z + pre[u].z, a4.w + pre[u].w};
+                        y[0] = fmaf(y[0], s4.x, h4.x) + res[u].x; y[1] = fmaf(y[1], s4.y, h4.y) + res[u].y;
+                        y[2] = fmaf(y[2], s4.z, h4.z) + res[u].z; y[3] = fmaf(y[3], s4.w, h4.w) + res[u].w;
+                        if (p.relu) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) y[q] = fmaxf(y[q], 0.f);
+                        }
+                        if (io.out) *reinterpret_cast<float4*>(io.out + ro) = make_float4(y[0], y[1], y[2], y[3]);
+                        if (io.out_h) store_split4(io.out_h, orow, NCOLS, col, y);
+                        if (io.out_gated || io.out_gated_h) {
+                            y[0] *= gat[u].x; y[1] *= gat[u].y; y[2] *= gat[u].z; y[3] *= gat[u].w;
+                            if (io.out_gated) *reinterpret_cast<float4*>(io.out_gated + ro) = make_float4(y[0], y[1], y[2], y[3]);
+                            if (io.out_gated_h) store_split4(io.out_gated_h, orow, NCOLS, col, y);
+                        }
+                    }
+                }
+            }
+            mbar_arrive(meta_empty(b));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(512u) : "memory");
+}
+
+static size_t smem_bytes(int stages) {
+    return 1024 + (size_t)stages * (2 * A_TILE + 2 * (size_t)NCOLS * 128) + SLAB_BYTES + META * BM * sizeof(int) +
+           4 * META * sizeof(uint32_t) + (3 * MAX_STAGES + 4 + 2 * META) * 8 + 64;
+}
+
+}  // namespace tc3
+
+bool lb2_spconv_tc3_supported(const lb2_conv_desc* d) {
+    if (d->cout != 256) return false;
+    for (int p = 0; p < d->npass; ++p) {
+        if (!d->io[p].in1_h) return false;
+        if (d->c2 > 0 && !d->io[p].in2_h) return false;
+    }
+    return tc3::smem_bytes(2) <= 227 * 1024;
+}
+
+int lb2_spconv_tc3_launch(Lb2Handle* h, cudaStream_t s, const lb2_conv_desc* d, int step_budget) {
+    tc3::Params p;
+    p.c1 = d->c1; p.c2 = d->c2; p.cout = d->cout; p.kvol = d->kvol; p.npass = d->npass;
+    p.wpacked = (const unsigned char*)d->weight_packed;
+    p.scale = d->scale; p.shift = d->shift; p.relu = d->relu;
+    p.nbr = d->nbr; p.nbr_stride = d->nbr_stride; p.d_mout = d->d_mout; p.mout_cap = d->mout_cap; p.row_perm = d->row_perm;
+    p.nchunks = (d->c1 + d->c2 + tc::KC - 1) / tc::KC;
+    p.stages = 2;
+    p.nbuf = 2; p.acc_stride = 256; p.tot_col = 0; p.tmem_cols = 512;
+    const int steps_per_offset = 3 * ((d->c1 + d->c2 + 15) / 16);
+    p.group = std::max(1, step_budget / steps_per_offset);
+    p.io[0] = d->io[0]; p.io[1] = d->io[d->npass > 1 ? 1 : 0];
+    const size_t smem = tc3::smem_bytes(p.stages);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(tc3::k_spconv_tc_n256, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+        if (e != cudaSuccess) return lb2_fail(h, LB2_ERR_CUDA, "k_spconv_tc_n256 smem attribute: %s", cudaGetErrorString(e));
+        configured = true;
+    }
+    const long long tiles_cap = (long long)cdiv(d->mout_cap, tc::BM) * d->npass;
+    const unsigned grid = (unsigned)std::min<long long>(h->num_sms, tiles_cap);
+    tc3::k_spconv_tc_n256<<<grid, tc3::THREADS, smem, s>>>(p);
+    LB2_POST_LAUNCH(h, "k_spconv_tc_n256");
+    return LB2_OK;
+}

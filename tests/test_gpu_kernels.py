@@ -482,6 +482,17 @@ def test_persistent_kernel_equals_per_tile_kernel(c1, c2, cout, lvl, kind):
     sc_, sh_ = (torch.rand(cout, generator=gen) + 0.5).to(DEV), torch.randn(cout, generator=gen).to(DEV)
     tab = torch.randn(40, cout, generator=gen).to(DEV)
     gi = torch.randint(0, 40, (N,), generator=gen, dtype=torch.int32).to(DEV)
+
+    def split_of(x):                                   # fp16 hi/lo companion through the library's own split (gate_mul by 1)
+        if x is None:
+            return None
+        c = x.shape[-1]
+        one = torch.ones(1, c, device=DEV)
+        xh = torch.zeros(2, N, 2 * c, dtype=torch.float16, device=DEV)
+        for p_ in range(2):
+            h.gate_mul(x[p_], one, None, None, N, c, torch.empty_like(x[p_]), xh[p_])
+        return xh
+    A_h, B_h = split_of(A), split_of(B)                # with companions the 256-channel layers take the register-total kernel
     res = []
     for algo in (_lib.ALGO_TC_TILE, _lib.ALGO_TC):
         out, outg = torch.zeros(2, N, cout, device=DEV), torch.zeros(2, N, cout, device=DEV)
@@ -495,7 +506,8 @@ def test_persistent_kernel_equals_per_tile_kernel(c1, c2, cout, lvl, kind):
         d.row_perm = perm.data_ptr() if perm is not None else None
         for p_ in range(2):
             d.io[p_] = ConvIO(A[p_].data_ptr(), B[p_].data_ptr() if B is not None else None, R[p_].data_ptr(), out[p_].data_ptr(),
-                              tab.data_ptr(), gi.data_ptr() if p_ == 0 else None, outg[p_].data_ptr(), None, None, None, out_h[p_].data_ptr(), None)
+                              tab.data_ptr(), gi.data_ptr() if p_ == 0 else None, outg[p_].data_ptr(), None,
+                              A_h[p_].data_ptr(), B_h[p_].data_ptr() if B_h is not None else None, out_h[p_].data_ptr(), None)
         h.spconv(d, algo)
         res.append((out[:, :M].clone(), outg[:, :M].clone(), out_h[:, :M].clone()))
     for a, b in zip(res[0], res[1]):
