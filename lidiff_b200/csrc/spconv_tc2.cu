@@ -42,7 +42,7 @@ struct Params {
     const int* d_mout;
     int mout_cap;
     const int* row_perm;
-    int stages, nchunks, tmem_cols, tot_col, group, nbuf, acc_stride, npass;
+    int stages, lag, nchunks, tmem_cols, tot_col, group, nbuf, acc_stride, npass;
     lb2_conv_io io[2];
 };
 
@@ -92,23 +92,32 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_persist(const Params p
     const float out_scale = __ldg(reinterpret_cast<const float*>(p.wpacked) + 1);
 
     auto tile_kmask = [&](int b) { return wmask[b * 4] | wmask[b * 4 + 1] | wmask[b * 4 + 2] | wmask[b * 4 + 3]; };
+    struct Ring {                                        // position in the stage ring without integer division
+        int s; uint32_t par; int n;
+        __device__ __forceinline__ void next() { if (++s == n) { s = 0; par ^= 1u; } }
+    };
 
     if (warp < 4) {
         // =========================== A producers ===========================
         const int t = threadIdx.x;
         const int sub = t & 7, rbase = t >> 3;
-        const int D = p.stages - 1;
+        // cp.async lookahead.  A stage's full_a arrival is signalled D stage-iterations after its copies were issued; issuing
+        // iteration it+D needs the slot of it+D-S free.  D = S-1 would couple "stage `it` may be consumed" to "the MMAs of stage
+        // it-1 have retired" and leave the tensor pipe idle for the producers' reaction time once per stage; D = S-2 keeps one
+        // full stage of slack.
+        const int D = p.lag;
         int it = 0, arrived = 0, j = 0;
+        Ring ri{0, 0u, p.stages}, ra{0, 0u, p.stages};                  // issue position / arrival position
         auto fetch_row = [&](int item) {                                // output row of this thread's slot in work item `item`
             if (item >= total) return -1;
-            const int tile = item % n_tiles;
+            const int tile = (item >= n_tiles) ? item - n_tiles : item;
             const int slot = tile * BM + t;
             return (slot < M) ? (p.row_perm ? __ldg(p.row_perm + slot) : slot) : -1;
         };
         int next_row = fetch_row(blockIdx.x);
         for (int item = blockIdx.x; item < total; item += gridDim.x, ++j) {
             const int b = j % META;
-            const int pass = item / n_tiles;
+            const int pass = (item >= n_tiles) ? 1 : 0;
             const lb2_conv_io io = p.io[pass];
             if (j >= META) mbar_wait(meta_empty(b), ((j / META) - 1) & 1);
             asm volatile("bar.sync 2, 128;" ::: "memory");              // everybody is done reading the previous tile's idx_s
@@ -146,9 +155,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_persist(const Params p
                 int src[8];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) src[q] = idxk[rbase + 16 * q];
-                for (int c = 0; c < p.nchunks; ++c, ++it) {
-                    const int s = it % p.stages;
-                    mbar_wait(empty(s), ((it / p.stages) & 1) ^ 1);
+                for (int c = 0; c < p.nchunks; ++c, ++it, ri.next()) {
+                    const int s = ri.s;
+                    mbar_wait(empty(s), ri.par ^ 1u);
                     unsigned char* a_hi = gen + (size_t)s * stage_bytes;
                     const uint32_t a_hi_u = base + (uint32_t)s * stage_bytes;
                     const int ch = c * KC + sub * 8;
@@ -163,7 +172,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_persist(const Params p
                     if (it >= D) {
                         cp_async_wait_dyn(D);
                         fence_proxy_async();
-                        mbar_arrive(full_a(arrived % p.stages));
+                        mbar_arrive(full_a(ra.s));
+                        ra.next();
                         ++arrived;
                     }
                 }
@@ -171,12 +181,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_persist(const Params p
         }
         cp_async_wait<0>();
         fence_proxy_async();
-        for (; arrived < it; ++arrived) mbar_arrive(full_a(arrived % p.stages));
+        for (; arrived < it; ++arrived, ra.next()) mbar_arrive(full_a(ra.s));
     } else if (warp == 4) {
         // =========================== MMA issuer ===========================
         if (lane == 0) {
             const uint32_t idesc = make_idesc(p.cout);
-            int it = 0, gcount = 0, j = 0;
+            int gcount = 0, j = 0;
+            Ring r{0, 0u, p.stages};
+            const bool two = p.nbuf == 2;
             for (int item = blockIdx.x; item < total; item += gridDim.x, ++j) {
                 const int b = j % META;
                 mbar_wait(meta_full(b), (j / META) & 1);
@@ -184,24 +196,25 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_persist(const Params p
                 const int n_off = __popc(kmask);
                 int in_group = 0, off_idx = 0;
                 for (uint32_t km = kmask; km; km &= km - 1, ++off_idx) {
-                    const int buf = gcount % p.nbuf;
+                    const int buf = two ? (gcount & 1) : 0;
+                    const int use = two ? (gcount >> 1) : gcount;         // how often this accumulator has been used before
                     const uint32_t tmem_acc = tmem_d + (uint32_t)(buf * p.acc_stride);
-                    if (in_group == 0 && gcount >= p.nbuf) {
-                        mbar_wait(acc_empty(buf), ((gcount / p.nbuf) - 1) & 1);
+                    if (in_group == 0 && use >= 1) {
+                        mbar_wait(acc_empty(buf), (use - 1) & 1);
                         tc_fence_after();
                     }
-                    for (int c = 0; c < p.nchunks; ++c, ++it) {
-                        const int s = it % p.stages;
-                        const uint32_t par = (it / p.stages) & 1;
+                    for (int c = 0; c < p.nchunks; ++c, r.next()) {
+                        const int s = r.s;
+                        const uint32_t par = r.par;
                         mbar_wait(full_b(s), par);
                         mbar_wait(full_a(s), par);
                         tc_fence_after();
                         const uint32_t a_hi = base + (uint32_t)s * stage_bytes, a_lo = a_hi + A_TILE;
                         const uint32_t b_hi = a_lo + A_TILE, b_lo = b_hi + b_tile;
                         const int ksteps = min(KC, ctot - c * KC) >> 4;
-                        for (int ks = 0; ks < ksteps; ++ks) {
-                            const uint64_t dah = make_desc(a_hi + ks * 32), dal = make_desc(a_lo + ks * 32);
-                            const uint64_t dbh = make_desc(b_hi + ks * 32), dbl = make_desc(b_lo + ks * 32);
+                        const uint64_t dah0 = make_desc(a_hi), dal0 = make_desc(a_lo), dbh0 = make_desc(b_hi), dbl0 = make_desc(b_lo);
+                        for (int ks = 0; ks < ksteps; ++ks) {                 // +32 bytes per K step = +2 in the address field
+                            const uint64_t dah = dah0 + 2u * ks, dal = dal0 + 2u * ks, dbh = dbh0 + 2u * ks, dbl = dbl0 + 2u * ks;
                             umma(tmem_acc, dah, dbh, idesc, (in_group | c | ks) ? 1u : 0u);
                             umma(tmem_acc, dal, dbh, idesc, 1);
                             umma(tmem_acc, dah, dbl, idesc, 1);
@@ -221,16 +234,17 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_persist(const Params p
     } else if (warp == 5) {
         // =========================== weight loader ===========================
         if (lane == 0) {
-            int it = 0, j = 0;
+            int j = 0;
+            Ring r{0, 0u, p.stages};
             for (int item = blockIdx.x; item < total; item += gridDim.x, ++j) {
                 const int b = j % META;
                 mbar_wait(meta_full(b), (j / META) & 1);
                 const uint32_t kmask = tile_kmask(b);
                 for (uint32_t km = kmask; km; km &= km - 1) {
                     const int k = __ffs(km) - 1;
-                    for (int c = 0; c < p.nchunks; ++c, ++it) {
-                        const int s = it % p.stages;
-                        mbar_wait(empty(s), ((it / p.stages) & 1) ^ 1);
+                    for (int c = 0; c < p.nchunks; ++c, r.next()) {
+                        const int s = r.s;
+                        mbar_wait(empty(s), r.par ^ 1u);
                         const uint32_t dst = base + (uint32_t)s * stage_bytes + 2u * A_TILE;
                         const unsigned char* src = p.wpacked + PACK_HEADER + ((size_t)k * p.nchunks + c) * (2u * b_tile);
                         mbar_expect_tx(full_b(s), 2u * b_tile);
@@ -249,7 +263,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_persist(const Params p
         int gcount = 0, j = 0;
         for (int item = blockIdx.x; item < total; item += gridDim.x, ++j) {
             const int b = j % META;
-            const int pass = item / n_tiles;
+            const int pass = (item >= n_tiles) ? 1 : 0;
             const lb2_conv_io io = p.io[pass];
             mbar_wait(meta_full(b), (j / META) & 1);
             const uint32_t kmask = tile_kmask(b);
@@ -264,10 +278,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_persist(const Params p
             }
             for (int g = 0; g < max(n_groups, 1); ++g) {
                 const bool last = g >= n_groups - 1;
-                const int buf = gcount % p.nbuf;
+                const int buf = (p.nbuf == 2) ? (gcount & 1) : 0;
                 const uint32_t acc_col = (uint32_t)(buf * p.acc_stride);
                 if (n_groups > 0) {
-                    mbar_wait(acc_full(buf), (gcount / p.nbuf) & 1);
+                    mbar_wait(acc_full(buf), ((p.nbuf == 2) ? (gcount >> 1) : gcount) & 1);
                     tc_fence_after();
                 }
                 for (int c0 = 0; c0 < p.cout; c0 += 32) {
@@ -388,6 +402,11 @@ int lb2_spconv_tc2_launch(Lb2Handle* h, cudaStream_t s, const lb2_conv_desc* d, 
     int stages = tc2::MAX_STAGES;
     while (stages > 1 && tc2::smem_bytes(d->cout, stages) > 227 * 1024) --stages;
     p.stages = stages;
+    {   // LB2_TC_LAG=full restores the S-1 lookahead (development A/B knob)
+        static int full_lag = -1;
+        if (full_lag < 0) { const char* e = getenv("LB2_TC_LAG"); full_lag = (e && e[0] == 'f') ? 1 : 0; }
+        p.lag = (stages >= 3 && !full_lag) ? stages - 2 : stages - 1;
+    }
     const int half = d->cout <= 32 ? 32 : d->cout <= 64 ? 64 : d->cout <= 128 ? 128 : 256;
     p.nbuf = half <= 128 ? 2 : 1;
     p.acc_stride = half;

@@ -5,6 +5,9 @@
 // in the REGISTERS of eight drain warps instead (setmaxnreg: producer / MMA warpgroups shrink to 56 registers, the two
 // drain warpgroups grow to 200), TMEM holds two 256-column accumulators in ping-pong, and a group's drain as well as the
 // whole epilogue overlap with the tensor-core work of the next group / tile.
+// The gathered-A ring and the weight ring are separate: weights arrive in 2 slots of 64 K-columns (64 KB each, one bulk copy),
+// gathered rows in 4 slots of 32 K-columns (the two halves of a 128-byte swizzled row image are disjoint sets of 16-byte
+// chunks, so each half is its own pipeline slot), which gives the gathers a lookahead of two slots with one slot of slack.
 //   WG0 warps 0-3   A producers (cp.async from the fp16 split companions only; neighbour rows re-read per offset)
 //   WG1 warp 4 MMA issuer, warp 5 weight loader (warps 6,7 idle)
 //   WG2 warps 8-11  drain + epilogue of output channels   0..127        WG3 warps 12-15: channels 128..255
@@ -20,12 +23,14 @@ using namespace tc;
 constexpr int THREADS = 512;
 constexpr int NCOLS = 256;
 constexpr int MAX_KVOL = 27;
-constexpr int MAX_STAGES = 4;
+constexpr int NA = 4;                                 // A slots (half stages, 32 K-columns each)
+constexpr int NB = 2;                                 // B slots (64 K-columns each)
+constexpr int A_LAG = 2;                              // cp.async lookahead in A slots (NA - 2: see spconv_tc2.cu)
 constexpr int SLAB_COLS = 16;
 constexpr int SLAB_PITCH = SLAB_COLS + 4;             // floats per slab row
 constexpr int SLAB_BYTES = 8 * 32 * SLAB_PITCH * 4;   // 8 drain warps x 32 rows
 constexpr int META = 4;                               // ring of per-tile metadata (row ids, offset masks).  Must exceed the cp.async
-                                                      // lookahead D <= MAX_STAGES-1: a tile's last full_a arrival is issued up to D
+                                                      // lookahead A_LAG: a tile's last full_a arrival is issued up to A_LAG
                                                       // stage-iterations (= up to D tiles) later, while re-using a slot waits for the
                                                       // tile META positions back to be completely drained.
 
@@ -40,7 +45,7 @@ struct Params {
     const int* d_mout;
     int mout_cap;
     const int* row_perm;
-    int stages, nchunks, tmem_cols, tot_col, group, nbuf, acc_stride, npass;
+    int stages, lag, nchunks, tmem_cols, tot_col, group, nbuf, acc_stride, npass;
     lb2_conv_io io[2];
 };
 
@@ -56,24 +61,28 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_n256(const Params p) {
     const uint32_t base = (raw + 1023u) & ~1023u;
     unsigned char* gen = smem_raw + (base - raw);
     const uint32_t b_tile = (uint32_t)NCOLS * 128u;
-    const uint32_t stage_bytes = 2u * A_TILE + 2u * b_tile;
-    unsigned char* tail = gen + (size_t)p.stages * stage_bytes;
+    const uint32_t a_stage = 2u * A_TILE;                       // hi + lo image of 128 rows x 64 K-columns (= 2 A slots)
+    const uint32_t b_base = base + (NA / 2) * a_stage;          // weight slots follow the A images
+    unsigned char* tail = gen + (size_t)(NA / 2) * a_stage + (size_t)NB * 2u * b_tile;
     float* slab = reinterpret_cast<float*>(tail);                                   // [8 warps][32][SLAB_PITCH]
     int* row_s = reinterpret_cast<int*>(tail + SLAB_BYTES);                          // [META][BM]
     uint32_t* wmask = reinterpret_cast<uint32_t*>(row_s + META * BM);                // [META][4] per-warp offset masks
     uint64_t* bars = reinterpret_cast<uint64_t*>(wmask + 4 * META);
-    uint32_t* misc = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + 4 + 2 * META);
+    constexpr int NBAR = 2 * NA + 2 * NB + 4 + 2 * META;
+    uint32_t* misc = reinterpret_cast<uint32_t*>(bars + NBAR);
     const uint32_t bar0 = smem_u32(bars);
     auto full_a = [&](int s) { return bar0 + 8u * s; };
-    auto full_b = [&](int s) { return bar0 + 8u * (MAX_STAGES + s); };
-    auto empty = [&](int s) { return bar0 + 8u * (2 * MAX_STAGES + s); };
-    auto acc_full = [&](int b) { return bar0 + 8u * (3 * MAX_STAGES + b); };
-    auto acc_empty = [&](int b) { return bar0 + 8u * (3 * MAX_STAGES + 2 + b); };
-    auto meta_full = [&](int b) { return bar0 + 8u * (3 * MAX_STAGES + 4 + b); };
-    auto meta_empty = [&](int b) { return bar0 + 8u * (3 * MAX_STAGES + 4 + META + b); };
+    auto empty_a = [&](int s) { return bar0 + 8u * (NA + s); };
+    auto full_b = [&](int s) { return bar0 + 8u * (2 * NA + s); };
+    auto empty_b = [&](int s) { return bar0 + 8u * (2 * NA + NB + s); };
+    auto acc_full = [&](int b) { return bar0 + 8u * (2 * NA + 2 * NB + b); };
+    auto acc_empty = [&](int b) { return bar0 + 8u * (2 * NA + 2 * NB + 2 + b); };
+    auto meta_full = [&](int b) { return bar0 + 8u * (2 * NA + 2 * NB + 4 + b); };
+    auto meta_empty = [&](int b) { return bar0 + 8u * (2 * NA + 2 * NB + 4 + META + b); };
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < p.stages; ++s) { mbar_init(full_a(s), 128); mbar_init(full_b(s), 1); mbar_init(empty(s), 1); }
+        for (int s = 0; s < NA; ++s) { mbar_init(full_a(s), 128); mbar_init(empty_a(s), 1); }
+        for (int s = 0; s < NB; ++s) { mbar_init(full_b(s), 1); mbar_init(empty_b(s), 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), 256); }        // 8 drain warps
         for (int b = 0; b < META; ++b) { mbar_init(meta_full(b), 1); mbar_init(meta_empty(b), 258); }   // MMA + loader + 256 drain threads
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -88,23 +97,27 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_n256(const Params p) {
     const uint32_t tmem_d = misc[0];
     const float out_scale = __ldg(reinterpret_cast<const float*>(p.wpacked) + 1);
     auto tile_kmask = [&](int b) { return wmask[b * 4] | wmask[b * 4 + 1] | wmask[b * 4 + 2] | wmask[b * 4 + 3]; };
+    struct Ring {                                        // position in the stage ring without integer division
+        int s; uint32_t par; int n;
+        __device__ __forceinline__ void next() { if (++s == n) { s = 0; par ^= 1u; } }
+    };
 
     if (warp < 4) {
         // =========================== WG0: A producers ===========================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         const int t = threadIdx.x;
-        const int sub = t & 7, rbase = t >> 3;
-        const int D = p.stages - 1;
+        const int sub = t & 3, rbase = t >> 2;                          // 16-byte chunk inside the half row / first of this thread's 4 rows
         int it = 0, arrived = 0, j = 0;
+        Ring ri{0, 0u, NA}, ra{0, 0u, NA};
         auto fetch_row = [&](int item) {
             if (item >= total) return -1;
-            const int slot = (item % n_tiles) * BM + t;
+            const int slot = ((item >= n_tiles) ? item - n_tiles : item) * BM + t;
             return (slot < M) ? (p.row_perm ? __ldg(p.row_perm + slot) : slot) : -1;
         };
         int next_row = fetch_row(blockIdx.x);
         for (int item = blockIdx.x; item < total; item += gridDim.x, ++j) {
             const int b = j % META;
-            const int pass = item / n_tiles;
+            const int pass = (item >= n_tiles) ? 1 : 0;
             const lb2_conv_io io = p.io[pass];
             if (j >= META) mbar_wait(meta_empty(b), ((j / META) - 1) & 1);
             {
@@ -129,54 +142,63 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_n256(const Params p) {
             asm volatile("bar.sync 2, 128;" ::: "memory");
             if (t == 0) mbar_arrive(meta_full(b));
             const uint32_t kmask = tile_kmask(b);
-            int myrows[8];
+            int myrows[4];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) myrows[q] = row_s[b * BM + rbase + 16 * q];
-            auto load_src = [&](int k, int (&dst)[8]) {              // neighbour rows of this thread's 8 tile rows at offset k
+            for (int q = 0; q < 4; ++q) myrows[q] = row_s[b * BM + rbase + 32 * q];
+            auto load_src = [&](int k, int (&dst)[4]) {              // neighbour rows of this thread's 4 tile rows at offset k
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
+                for (int q = 0; q < 4; ++q) {
                     dst[q] = -1;
                     if (myrows[q] >= 0) dst[q] = p.nbr ? __ldg(p.nbr + (long long)k * p.nbr_stride + myrows[q]) : myrows[q];
                 }
             };
-            int src[8], nxt[8];
+            int src[4], nxt[4];
             uint32_t km = kmask;
             if (km) load_src(__ffs(km) - 1, src);
             while (km) {
                 km &= km - 1;
                 if (km) load_src(__ffs(km) - 1, nxt);                 // prefetch the next offset's rows behind this offset's copies
-                for (int c = 0; c < p.nchunks; ++c, ++it) {
-                    const int s = it % p.stages;
-                    mbar_wait(empty(s), ((it / p.stages) & 1) ^ 1);
-                    const uint32_t a_hi_u = base + (uint32_t)s * stage_bytes;
-                    const int ch = c * KC + sub * 8;
-                    if (ch < ctot) {
-                        const bool first = ch < p.c1;
-                        const int cw = first ? p.c1 : p.c2;
-                        const int co = first ? ch : ch - p.c1;
-                        produce_a_split(reinterpret_cast<const __half*>(first ? io.in1_h : io.in2_h), cw, co, src, a_hi_u, a_hi_u + A_TILE, rbase, sub);
+                for (int c2 = 0; c2 < 2 * p.nchunks; ++c2, ++it, ri.next()) {      // c2 = 2 * chunk + half
+                    const int s = ri.s;
+                    mbar_wait(empty_a(s), ri.par ^ 1u);
+                    const uint32_t a_hi_u = base + (uint32_t)(s >> 1) * a_stage;
+                    const int half = s & 1;                             // slots alternate halves: slot parity == c2 parity (NA even)
+                    const int ch = c2 * 32 + sub * 8;                   // first of this thread's 8 input channels
+                    const bool first = ch < p.c1;
+                    const int cw = first ? p.c1 : p.c2;
+                    const int co = first ? ch : ch - p.c1;
+                    const __half* src_h = reinterpret_cast<const __half*>(first ? io.in1_h : io.in2_h);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint32_t off = sw128(rbase + 32 * q, half * 4 + sub);
+                        const bool ok = src[q] >= 0;
+                        const __half* rp = src_h + (ok ? ((long long)src[q] * 2 * cw + co) : 0);
+                        cp_async16(a_hi_u + off, rp, ok ? 16u : 0u);
+                        cp_async16(a_hi_u + A_TILE + off, rp + (ok ? cw : 0), ok ? 16u : 0u);
                     }
                     cp_async_commit();
-                    if (it >= D) {
-                        cp_async_wait_dyn(D);
+                    if (it >= A_LAG) {
+                        cp_async_wait<A_LAG>();
                         fence_proxy_async();
-                        mbar_arrive(full_a(arrived % p.stages));
+                        mbar_arrive(full_a(ra.s));
+                        ra.next();
                         ++arrived;
                     }
                 }
 #pragma unroll
-                for (int q = 0; q < 8; ++q) src[q] = nxt[q];
+                for (int q = 0; q < 4; ++q) src[q] = nxt[q];
             }
         }
         cp_async_wait<0>();
         fence_proxy_async();
-        for (; arrived < it; ++arrived) mbar_arrive(full_a(arrived % p.stages));
+        for (; arrived < it; ++arrived, ra.next()) mbar_arrive(full_a(ra.s));
     } else if (warp < 8) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         if (warp == 4 && lane == 0) {
             // =========================== MMA issuer ===========================
             const uint32_t idesc = make_idesc(NCOLS);
-            int it = 0, gcount = 0, j = 0;
+            int gcount = 0, j = 0;
+            Ring rq{0, 0u, NA}, rb{0, 0u, NB};
             for (int item = blockIdx.x; item < total; item += gridDim.x, ++j) {
                 const int b = j % META;
                 mbar_wait(meta_full(b), (j / META) & 1);
@@ -190,23 +212,29 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_n256(const Params p) {
                         mbar_wait(acc_empty(buf), ((gcount >> 1) - 1) & 1);
                         tc_fence_after();
                     }
-                    for (int c = 0; c < p.nchunks; ++c, ++it) {
-                        const int s = it % p.stages;
-                        const uint32_t par = (it / p.stages) & 1;
-                        mbar_wait(full_b(s), par);
-                        mbar_wait(full_a(s), par);
-                        tc_fence_after();
-                        const uint32_t a_hi = base + (uint32_t)s * stage_bytes, a_lo = a_hi + A_TILE;
-                        const uint32_t b_hi = a_lo + A_TILE, b_lo = b_hi + b_tile;
-                        const int ksteps = min(KC, ctot - c * KC) >> 4;
-                        for (int ks = 0; ks < ksteps; ++ks) {
-                            const uint64_t dah = make_desc(a_hi + ks * 32), dal = make_desc(a_lo + ks * 32);
-                            const uint64_t dbh = make_desc(b_hi + ks * 32), dbl = make_desc(b_lo + ks * 32);
-                            umma(tmem_acc, dah, dbh, idesc, (in_group | c | ks) ? 1u : 0u);
-                            umma(tmem_acc, dal, dbh, idesc, 1);
-                            umma(tmem_acc, dah, dbl, idesc, 1);
+                    for (int c = 0; c < p.nchunks; ++c, rb.next()) {
+                        const int sb = rb.s;
+                        mbar_wait(full_b(sb), rb.par);
+                        const uint32_t b_hi = b_base + (uint32_t)sb * 2u * b_tile, b_lo = b_hi + b_tile;
+                        const uint64_t dbh0 = make_desc(b_hi), dbl0 = make_desc(b_lo);
+#pragma unroll
+                        for (int half = 0; half < 2; ++half, rq.next()) {
+                            const int sa = rq.s;
+                            mbar_wait(full_a(sa), rq.par);
+                            tc_fence_after();
+                            const uint32_t a_hi = base + (uint32_t)(sa >> 1) * a_stage, a_lo = a_hi + A_TILE;
+                            const uint64_t dah0 = make_desc(a_hi), dal0 = make_desc(a_lo);
+#pragma unroll
+                            for (int k2 = 0; k2 < 2; ++k2) {              // +32 bytes per K step = +2 in the address field
+                                const uint32_t ks = (uint32_t)(half * 2 + k2);
+                                const uint64_t dah = dah0 + 2u * ks, dal = dal0 + 2u * ks, dbh = dbh0 + 2u * ks, dbl = dbl0 + 2u * ks;
+                                umma(tmem_acc, dah, dbh, idesc, (in_group | c | (int)ks) ? 1u : 0u);
+                                umma(tmem_acc, dal, dbh, idesc, 1);
+                                umma(tmem_acc, dah, dbl, idesc, 1);
+                            }
+                            umma_commit(empty_a(sa));
                         }
-                        umma_commit(empty(s));
+                        umma_commit(empty_b(sb));
                     }
                     if (++in_group == p.group || off_idx == n_off - 1) {
                         umma_commit(acc_full(buf));
@@ -218,17 +246,18 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_n256(const Params p) {
             }
         } else if (warp == 5 && lane == 0) {
             // =========================== weight loader ===========================
-            int it = 0, j = 0;
+            int j = 0;
+            Ring r{0, 0u, NB};
             for (int item = blockIdx.x; item < total; item += gridDim.x, ++j) {
                 const int b = j % META;
                 mbar_wait(meta_full(b), (j / META) & 1);
                 const uint32_t kmask = tile_kmask(b);
                 for (uint32_t km = kmask; km; km &= km - 1) {
                     const int k = __ffs(km) - 1;
-                    for (int c = 0; c < p.nchunks; ++c, ++it) {
-                        const int s = it % p.stages;
-                        mbar_wait(empty(s), ((it / p.stages) & 1) ^ 1);
-                        const uint32_t dst = base + (uint32_t)s * stage_bytes + 2u * A_TILE;
+                    for (int c = 0; c < p.nchunks; ++c, r.next()) {
+                        const int s = r.s;
+                        mbar_wait(empty_b(s), r.par ^ 1u);
+                        const uint32_t dst = b_base + (uint32_t)s * 2u * b_tile;
                         const unsigned char* src = p.wpacked + PACK_HEADER + ((size_t)k * p.nchunks + c) * (2u * b_tile);
                         mbar_expect_tx(full_b(s), 2u * b_tile);
                         bulk_g2s(dst, src, 2u * b_tile, full_b(s));
@@ -249,7 +278,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_n256(const Params p) {
         int gcount = 0, j = 0;
         for (int item = blockIdx.x; item < total; item += gridDim.x, ++j) {
             const int b = j % META;
-            const int pass = item / n_tiles;
+            const int pass = (item >= n_tiles) ? 1 : 0;
             const lb2_conv_io io = p.io[pass];
             mbar_wait(meta_full(b), (j / META) & 1);
             const uint32_t kmask = tile_kmask(b);
@@ -348,9 +377,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_n256(const Params p) {
     if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(512u) : "memory");
 }
 
-static size_t smem_bytes(int stages) {
-    return 1024 + (size_t)stages * (2 * A_TILE + 2 * (size_t)NCOLS * 128) + SLAB_BYTES + META * BM * sizeof(int) +
-           4 * META * sizeof(uint32_t) + (3 * MAX_STAGES + 4 + 2 * META) * 8 + 64;
+static size_t smem_bytes() {
+    return 1024 + (size_t)(NA / 2) * 2 * A_TILE + (size_t)NB * 2 * NCOLS * 128 + SLAB_BYTES + META * BM * sizeof(int) +
+           4 * META * sizeof(uint32_t) + (2 * NA + 2 * NB + 4 + 2 * META) * 8 + 64;
 }
 
 }  // namespace tc3
@@ -361,7 +390,8 @@ bool lb2_spconv_tc3_supported(const lb2_conv_desc* d) {
         if (!d->io[p].in1_h) return false;
         if (d->c2 > 0 && !d->io[p].in2_h) return false;
     }
-    return tc3::smem_bytes(2) <= 227 * 1024;
+    if ((d->c1 + d->c2) % tc::KC != 0 || d->c1 % 32 != 0) return false;      // whole 64-column chunks; a half never straddles in1/in2
+    return tc3::smem_bytes() <= 227 * 1024;
 }
 
 int lb2_spconv_tc3_launch(Lb2Handle* h, cudaStream_t s, const lb2_conv_desc* d, int step_budget) {
@@ -371,12 +401,12 @@ int lb2_spconv_tc3_launch(Lb2Handle* h, cudaStream_t s, const lb2_conv_desc* d, 
     p.scale = d->scale; p.shift = d->shift; p.relu = d->relu;
     p.nbr = d->nbr; p.nbr_stride = d->nbr_stride; p.d_mout = d->d_mout; p.mout_cap = d->mout_cap; p.row_perm = d->row_perm;
     p.nchunks = (d->c1 + d->c2 + tc::KC - 1) / tc::KC;
-    p.stages = 2;
+    p.stages = tc3::NA; p.lag = tc3::A_LAG;
     p.nbuf = 2; p.acc_stride = 256; p.tot_col = 0; p.tmem_cols = 512;
     const int steps_per_offset = 3 * ((d->c1 + d->c2 + 15) / 16);
     p.group = std::max(1, step_budget / steps_per_offset);
     p.io[0] = d->io[0]; p.io[1] = d->io[d->npass > 1 ? 1 : 0];
-    const size_t smem = tc3::smem_bytes(p.stages);
+    const size_t smem = tc3::smem_bytes();
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(tc3::k_spconv_tc_n256, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));

@@ -85,20 +85,22 @@ __device__ __forceinline__ uint32_t sw128(int row, int chunk) {
     return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4));
 }
 
+// two fp32 -> packed (hi, hi) and (lo, lo) fp16 pairs, saturating at the fp16 range; packed converts (F2FP) round each
+// half independently to nearest-even, i.e. the results equal the scalar split1 below bit for bit
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    x0 = fminf(fmaxf(x0, -65504.f), 65504.f);
+    x1 = fminf(fmaxf(x1, -65504.f), 65504.f);
+    const __half2 h = __floats2half2_rn(x0, x1);
+    const float2 f = __half22float2(h);
+    const __half2 l = __floats2half2_rn(x0 - f.x, x1 - f.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 __device__ __forceinline__ void split8(const float4& a, const float4& b, uint4& hi, uint4& lo) {
-    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-    uint32_t h[4], l[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float x0 = fminf(fmaxf(v[2 * i], -65504.f), 65504.f), x1 = fminf(fmaxf(v[2 * i + 1], -65504.f), 65504.f);
-        const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
-        const __half l0 = __float2half_rn(x0 - __half2float(h0));
-        const __half l1 = __float2half_rn(x1 - __half2float(h1));
-        h[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-        l[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
-    }
-    hi = make_uint4(h[0], h[1], h[2], h[3]);
-    lo = make_uint4(l[0], l[1], l[2], l[3]);
+    split2(a.x, a.y, hi.x, lo.x);
+    split2(a.z, a.w, hi.y, lo.y);
+    split2(b.x, b.y, hi.z, lo.z);
+    split2(b.z, b.w, hi.w, lo.w);
 }
 
 
@@ -110,15 +112,10 @@ __device__ __forceinline__ void split1(float x, __half& hi, __half& lo) {
 }
 // write 4 consecutive channels of a split companion row: hi halfs at row[col], lo halfs at row[c + col]
 __device__ __forceinline__ void store_split4(void* base, long long row, int c, int col, const float (&y)[4]) {
-    __half h[4], l[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) split1(y[j], h[j], l[j]);
     __half* rp = reinterpret_cast<__half*>(base) + row * 2 * c;
     uint2 uh, ul;
-    uh.x = (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16);
-    uh.y = (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16);
-    ul.x = (uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16);
-    ul.y = (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16);
+    split2(y[0], y[1], uh.x, ul.x);
+    split2(y[2], y[3], uh.y, ul.y);
     *reinterpret_cast<uint2*>(rp + col) = uh;
     *reinterpret_cast<uint2*>(rp + c + col) = ul;
 }
