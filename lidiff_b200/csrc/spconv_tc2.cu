@@ -388,11 +388,16 @@ bool lb2_tc_persistent_enabled() {
 
 bool lb2_spconv_tc3_supported(const lb2_conv_desc* d);
 int lb2_spconv_tc3_launch(Lb2Handle* h, cudaStream_t s, const lb2_conv_desc* d, int step_budget);
+bool lb2_spconv_tc4_supported(const lb2_conv_desc* d);
+int lb2_spconv_tc4_launch(Lb2Handle* h, cudaStream_t s, const lb2_conv_desc* d, int step_budget);
 
 int lb2_spconv_tc2_launch(Lb2Handle* h, cudaStream_t s, const lb2_conv_desc* d, int step_budget) {
     static int use_n256 = -1;
     if (use_n256 < 0) { const char* e = getenv("LB2_TC_N256"); use_n256 = (e && e[0] == '0') ? 0 : 1; }
     if (use_n256 && lb2_spconv_tc3_supported(d)) return lb2_spconv_tc3_launch(h, s, d, step_budget);
+    static int use_small = -1;
+    if (use_small < 0) { const char* e = getenv("LB2_TC_SMALL"); use_small = (e && e[0] == '0') ? 0 : 1; }
+    if (use_small && lb2_spconv_tc4_supported(d)) return lb2_spconv_tc4_launch(h, s, d, step_budget);
     tc2::Params p;
     p.c1 = d->c1; p.c2 = d->c2; p.cout = d->cout; p.kvol = d->kvol; p.npass = d->npass;
     p.wpacked = (const unsigned char*)d->weight_packed;

@@ -1,0 +1,439 @@
+// K4 (variant B, persistent, Cout <= 128) — the persistent tcgen05 sparse convolution of spconv_tc2.cu re-balanced for the
+// layers that are bound by memory latency and by the epilogue rather than by the tensor pipe (levels 0-2, level-3 encoder).
+// Profiling the generic kernel on those layers (profiles/r01_ncu_stall_attribution.txt) showed its four drain warps busy
+// >95 % of the time (one warp per scheduler, a long dependent instruction stream per tile) while the MMA warp waited for
+// a free accumulator and the producers for a free stage.  This kernel therefore
+//   * runs TWO drain warpgroups that take alternate tiles, keeps the fp32 running total of the two-level accumulation in
+//     their registers (setmaxnreg: 96 / 48 / 184 / 184 registers for producer / MMA+loader / drain / drain warpgroups) and
+//     releases an accumulator as soon as it has been read, so TMEM holds four accumulators the MMA warp can run ahead into;
+//   * separates the gathered-A ring (4 slots of 32 K-columns: the two halves of a 128-byte swizzled row image are disjoint
+//     sets of 16-byte chunks) from the weight ring (3 slots of 64 K-columns), with a gather lookahead of two slots.
+//   WG0 warps 0-3   A producers (cp.async from the fp16 split companions, or fp32 -> split in registers)
+//   WG1 warp 4 MMA issuer, warp 5 weight loader (warps 6,7 idle)
+//   WG2 warps 8-11  drain + epilogue of even tiles        WG3 warps 12-15: odd tiles
+// Same math and results as k_spconv_tc / k_spconv_tc_persist (tests compare them).
+#include "common.cuh"
+#include <algorithm>
+#include <stdlib.h>
+#include "tc_common.cuh"
+
+namespace tc4 {
+using namespace tc;
+
+constexpr int THREADS = 512;
+constexpr int MAX_KVOL = 27;
+constexpr int NA = 4;                                 // A slots (32 K-columns each; two per 128-byte row image)
+constexpr int A_LAG = 2;                              // cp.async lookahead in A slots (NA - 2, see spconv_tc2.cu)
+constexpr int NB = 3;                                 // weight slots (64 K-columns each)
+constexpr int NACC = 4;                               // TMEM accumulators
+constexpr int SLAB_PITCH = 36;                        // floats per slab row (32 + 4: conflict-free 16-byte accesses)
+constexpr int SLAB_BYTES = 8 * 32 * SLAB_PITCH * 4;   // 8 drain warps x 32 rows
+constexpr int META = 4;                               // ring of per-tile metadata; must exceed the gather lookahead in tiles (<= 1)
+constexpr int NBAR = 2 * NA + 2 * NB + 2 * NACC + 2 * META;
+
+struct Params {
+    int c1, c2, cout, kvol;
+    const unsigned char* wpacked;
+    const float* scale;
+    const float* shift;
+    int relu;
+    const int* nbr;
+    long long nbr_stride;
+    const int* d_mout;
+    int mout_cap;
+    const int* row_perm;
+    int nchunks, nhalf, tmem_cols, group, acc_stride, npass;
+    lb2_conv_io io[2];
+};
+
+struct Ring {                                             // position in a ring without integer division
+    int s; uint32_t par; int n;
+    __device__ __forceinline__ void next() { if (++s == n) { s = 0; par ^= 1u; } }
+};
+
+__global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_small(const Params p) {
+    extern __shared__ unsigned char smem_raw[];
+    const int M = p.d_mout ? min(*p.d_mout, p.mout_cap) : p.mout_cap;
+    const int n_tiles = (M + BM - 1) / BM;
+    const int total = n_tiles * p.npass;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    unsigned char* gen = smem_raw + (base - raw);
+    const uint32_t b_tile = (uint32_t)p.cout * 128u;
+    const uint32_t a_stage = 2u * A_TILE;                       // hi + lo image of 128 rows x 64 K-columns (= 2 A slots)
+    const uint32_t b_base = base + (NA / 2) * a_stage;
+    unsigned char* tail = gen + (size_t)(NA / 2) * a_stage + (size_t)NB * 2u * b_tile;
+    float* slab = reinterpret_cast<float*>(tail);                                   // [8 warps][32][SLAB_PITCH]
+    int* idx_s = reinterpret_cast<int*>(tail + SLAB_BYTES);                          // [kvol][BM] (producer private)
+    int* row_s = idx_s + MAX_KVOL * BM;                                              // [META][BM]
+    uint32_t* wmask = reinterpret_cast<uint32_t*>(row_s + META * BM);                // [META][4] per-warp offset masks
+    uint64_t* bars = reinterpret_cast<uint64_t*>(wmask + 4 * META);
+    uint32_t* misc = reinterpret_cast<uint32_t*>(bars + NBAR);
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_a = [&](int s) { return bar0 + 8u * s; };
+    auto empty_a = [&](int s) { return bar0 + 8u * (NA + s); };
+    auto full_b = [&](int s) { return bar0 + 8u * (2 * NA + s); };
+    auto empty_b = [&](int s) { return bar0 + 8u * (2 * NA + NB + s); };
+    auto acc_full = [&](int b) { return bar0 + 8u * (2 * NA + 2 * NB + b); };
+    auto acc_empty = [&](int b) { return bar0 + 8u * (2 * NA + 2 * NB + NACC + b); };
+    auto meta_full = [&](int b) { return bar0 + 8u * (2 * NA + 2 * NB + 2 * NACC + b); };
+    auto meta_empty = [&](int b) { return bar0 + 8u * (2 * NA + 2 * NB + 2 * NACC + META + b); };
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NA; ++s) { mbar_init(full_a(s), 128); mbar_init(empty_a(s), 1); }
+        for (int s = 0; s < NB; ++s) { mbar_init(full_b(s), 1); mbar_init(empty_b(s), 1); }
+        for (int b = 0; b < NACC; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), 128); }    // the drain warpgroup that owns the tile
+        for (int b = 0; b < META; ++b) { mbar_init(meta_full(b), 1); mbar_init(meta_empty(b), 258); }   // MMA + loader + both drain warpgroups
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&misc[0])), "r"((uint32_t)p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = misc[0];
+    const float out_scale = __ldg(reinterpret_cast<const float*>(p.wpacked) + 1);
+    auto tile_kmask = [&](int b) { return wmask[b * 4] | wmask[b * 4 + 1] | wmask[b * 4 + 2] | wmask[b * 4 + 3]; };
+
+    if (warp < 4) {
+        // =========================== WG0: A producers ===========================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+        const int t = threadIdx.x;
+        const int sub = t & 3, rbase = t >> 2;                          // 16-byte chunk inside the half row / first of this thread's 4 rows
+        int it = 0, arrived = 0, j = 0;
+        Ring ri{0, 0u, NA}, ra{0, 0u, NA};                              // issue position / arrival position
+        auto fetch_row = [&](int item) {                                // output row of this thread's slot in work item `item`
+            if (item >= total) return -1;
+            const int slot = ((item >= n_tiles) ? item - n_tiles : item) * BM + t;
+            return (slot < M) ? (p.row_perm ? __ldg(p.row_perm + slot) : slot) : -1;
+        };
+        int next_row = fetch_row(blockIdx.x);
+        for (int item = blockIdx.x; item < total; item += gridDim.x, ++j) {
+            const int b = j % META;
+            const lb2_conv_io io = p.io[(item >= n_tiles) ? 1 : 0];
+            if (j >= META) mbar_wait(meta_empty(b), ((j / META) - 1) & 1);
+            asm volatile("bar.sync 2, 128;" ::: "memory");              // everybody is done reading the previous tile's idx_s
+            {
+                const int row = next_row;
+                next_row = fetch_row(item + gridDim.x);                 // prefetch: its latency hides behind this tile's gathers
+                row_s[b * BM + t] = row;
+                uint32_t mymask = 0;
+                for (int k0 = 0; k0 < p.kvol; k0 += 9) {                // 9 independent loads in flight, then the votes
+                    int v[9];
+#pragma unroll
+                    for (int q = 0; q < 9; ++q) {
+                        const int k = k0 + q;
+                        v[q] = -1;
+                        if (k < p.kvol && row >= 0) v[q] = p.nbr ? __ldg(p.nbr + (long long)k * p.nbr_stride + row) : row;
+                    }
+#pragma unroll
+                    for (int q = 0; q < 9; ++q) {
+                        const int k = k0 + q;
+                        if (k < p.kvol) {
+                            idx_s[k * BM + t] = v[q];
+                            if (__any_sync(0xffffffffu, v[q] >= 0)) mymask |= 1u << k;
+                        }
+                    }
+                }
+                if (lane == 0) wmask[b * 4 + warp] = mymask;
+            }
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+            if (t == 0) mbar_arrive(meta_full(b));
+            const uint32_t kmask = tile_kmask(b);
+            const bool use_h = (io.in1_h != nullptr) && (p.c2 == 0 || io.in2_h != nullptr);
+            for (uint32_t km = kmask; km; km &= km - 1) {
+                const int k = __ffs(km) - 1;
+                int src[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) src[q] = idx_s[k * BM + rbase + 32 * q];
+                for (int c2 = 0; c2 < p.nhalf; ++c2, ++it, ri.next()) {
+                    const int s = ri.s;
+                    mbar_wait(empty_a(s), ri.par ^ 1u);
+                    const uint32_t img = (uint32_t)(s >> 1) * a_stage;
+                    const int ch = c2 * 32 + sub * 8;                   // first of this thread's 8 input channels
+                    const bool first = ch < p.c1;
+                    const int cw = first ? p.c1 : p.c2;
+                    const int co = first ? ch : ch - p.c1;
+                    if (use_h) {
+                        const __half* src_h = reinterpret_cast<const __half*>(first ? io.in1_h : io.in2_h);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const uint32_t off = img + sw128(rbase + 32 * q, (s & 1) * 4 + sub);
+                            const bool ok = src[q] >= 0;
+                            const __half* rp = src_h + (ok ? ((long long)src[q] * 2 * cw + co) : 0);
+                            cp_async16(base + off, rp, ok ? 16u : 0u);
+                            cp_async16(base + A_TILE + off, rp + (ok ? cw : 0), ok ? 16u : 0u);
+                        }
+                    } else {
+                        const float* srcp = first ? io.in1 : io.in2;
+                        float4 va[4], vb[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            va[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            vb[q] = va[q];
+                            if (src[q] >= 0) {
+                                const float4* rp = reinterpret_cast<const float4*>(srcp + (long long)src[q] * cw + co);
+                                va[q] = __ldg(rp);
+                                vb[q] = __ldg(rp + 1);
+                            }
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            uint4 hi, lo;
+                            split8(va[q], vb[q], hi, lo);
+                            const uint32_t off = img + sw128(rbase + 32 * q, (s & 1) * 4 + sub);
+                            *reinterpret_cast<uint4*>(gen + off) = hi;
+                            *reinterpret_cast<uint4*>(gen + A_TILE + off) = lo;
+                        }
+                    }
+                    cp_async_commit();                                  // (empty group on the fp32 path)
+                    if (it >= A_LAG) {
+                        cp_async_wait<A_LAG>();
+                        fence_proxy_async();
+                        mbar_arrive(full_a(ra.s));
+                        ra.next();
+                        ++arrived;
+                    }
+                }
+            }
+        }
+        cp_async_wait<0>();
+        fence_proxy_async();
+        for (; arrived < it; ++arrived, ra.next()) mbar_arrive(full_a(ra.s));
+    } else if (warp < 8) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+        if (warp == 4 && lane == 0) {
+            // =========================== MMA issuer ===========================
+            const uint32_t idesc = make_idesc(p.cout);
+            int gcount = 0, j = 0;
+            Ring rq{0, 0u, NA}, rb{0, 0u, NB};
+            for (int item = blockIdx.x; item < total; item += gridDim.x, ++j) {
+                const int b = j % META;
+                mbar_wait(meta_full(b), (j / META) & 1);
+                const uint32_t kmask = tile_kmask(b);
+                const int n_off = __popc(kmask);
+                int in_group = 0, off_idx = 0;
+                for (uint32_t km = kmask; km; km &= km - 1, ++off_idx) {
+                    const int buf = gcount & (NACC - 1);
+                    const uint32_t tmem_acc = tmem_d + (uint32_t)(buf * p.acc_stride);
+                    if (in_group == 0 && gcount >= NACC) {
+                        mbar_wait(acc_empty(buf), ((gcount / NACC) - 1) & 1);
+                        tc_fence_after();
+                    }
+                    for (int c = 0; c < p.nchunks; ++c, rb.next()) {
+                        const int sb = rb.s;
+                        mbar_wait(full_b(sb), rb.par);
+                        const uint32_t b_hi = b_base + (uint32_t)sb * 2u * b_tile, b_lo = b_hi + b_tile;
+                        const uint64_t dbh0 = make_desc(b_hi), dbl0 = make_desc(b_lo);
+                        const int halves = min(2, p.nhalf - 2 * c);
+                        for (int half = 0; half < halves; ++half, rq.next()) {
+                            const int sa = rq.s;
+                            mbar_wait(full_a(sa), rq.par);
+                            tc_fence_after();
+                            const uint32_t a_hi = base + (uint32_t)(sa >> 1) * a_stage, a_lo = a_hi + A_TILE;
+                            const uint64_t dah0 = make_desc(a_hi) + 4u * (uint32_t)(sa & 1), dal0 = make_desc(a_lo) + 4u * (uint32_t)(sa & 1);
+#pragma unroll
+                            for (int k2 = 0; k2 < 2; ++k2) {              // +32 bytes per K step = +2 in the descriptor's address field
+                                const uint32_t kb = 2u * (uint32_t)(half * 2 + k2);
+                                const uint64_t dah = dah0 + 2u * k2, dal = dal0 + 2u * k2, dbh = dbh0 + kb, dbl = dbl0 + kb;
+                                umma(tmem_acc, dah, dbh, idesc, (in_group | c | half | k2) ? 1u : 0u);
+                                umma(tmem_acc, dal, dbh, idesc, 1);
+                                umma(tmem_acc, dah, dbl, idesc, 1);
+                            }
+                            umma_commit(empty_a(sa));
+                        }
+                        umma_commit(empty_b(sb));
+                    }
+                    if (++in_group == p.group || off_idx == n_off - 1) {
+                        umma_commit(acc_full(buf));
+                        in_group = 0;
+                        ++gcount;
+                    }
+                }
+                mbar_arrive(meta_empty(b));
+            }
+        } else if (warp == 5 && lane == 0) {
+            // =========================== weight loader ===========================
+            int j = 0;
+            Ring r{0, 0u, NB};
+            for (int item = blockIdx.x; item < total; item += gridDim.x, ++j) {
+                const int b = j % META;
+                mbar_wait(meta_full(b), (j / META) & 1);
+                const uint32_t kmask = tile_kmask(b);
+                for (uint32_t km = kmask; km; km &= km - 1) {
+                    const int k = __ffs(km) - 1;
+                    for (int c = 0; c < p.nchunks; ++c, r.next()) {
+                        const int s = r.s;
+                        mbar_wait(empty_b(s), r.par ^ 1u);
+                        const uint32_t dst = b_base + (uint32_t)s * 2u * b_tile;
+                        const unsigned char* src = p.wpacked + PACK_HEADER + ((size_t)k * p.nchunks + c) * (2u * b_tile);
+                        mbar_expect_tx(full_b(s), 2u * b_tile);
+                        bulk_g2s(dst, src, 2u * b_tile, full_b(s));
+                    }
+                }
+                mbar_arrive(meta_empty(b));
+            }
+        }
+        __syncwarp();
+    } else {
+        // =========================== WG2 / WG3: drain (register-resident fp32 total) + epilogue of alternate tiles ===========================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 184;");
+        const int q4 = warp & 3;                                   // TMEM lane quarter
+        const int mine = (warp >= 12) ? 1 : 0;                     // tile parity this warpgroup owns
+        const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;
+        float* myslab = slab + (size_t)(warp - 8) * 32 * SLAB_PITCH;
+        float tot[128];
+        int gcount = 0, j = 0;
+        for (int item = blockIdx.x; item < total; item += gridDim.x, ++j) {
+            const int b = j % META;
+            const lb2_conv_io io = p.io[(item >= n_tiles) ? 1 : 0];
+            mbar_wait(meta_full(b), (j / META) & 1);
+            const uint32_t kmask = tile_kmask(b);
+            const int n_off = __popc(kmask);
+            int n_groups = 0;
+            for (int o = 0; o < n_off; o += p.group) ++n_groups;
+            if ((j & 1) != mine) {                                  // the other warpgroup's tile: only keep the accumulator count in step
+                gcount += n_groups;
+                mbar_arrive(meta_empty(b));
+                continue;
+            }
+            const int* rows = row_s + b * BM + q4 * 32;
+            int orows[8], gidx[8];                                  // the 8 rows this lane serves in the epilogue + their gate rows
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                orows[i] = rows[(lane >> 3) + 4 * i];
+                gidx[i] = (io.gate_table && io.gate_idx && orows[i] >= 0) ? __ldg(io.gate_idx + orows[i]) : 0;
+            }
+            if (n_groups == 0) {
+#pragma unroll
+                for (int q = 0; q < 128; ++q) tot[q] = 0.f;
+            }
+            for (int g = 0; g < n_groups; ++g) {
+                const int buf = gcount & (NACC - 1);
+                mbar_wait(acc_full(buf), (gcount / NACC) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    if (cc * 32 < p.cout) {
+                        uint32_t r[32];
+                        tmem_ld32(tmem_d + lane_base + (uint32_t)(buf * p.acc_stride + cc * 32), r);
+                        tmem_ld_wait();
+                        if (g == 0) {
+#pragma unroll
+                            for (int q = 0; q < 32; ++q) tot[cc * 32 + q] = __uint_as_float(r[q]);
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 32; ++q) tot[cc * 32 + q] = __fadd_rn(tot[cc * 32 + q], __uint_as_float(r[q]));
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(acc_empty(buf));                       // accumulator free again: the MMA warp runs on while we finish
+                ++gcount;
+            }
+            // ---- epilogue from registers, 32 channels at a time through the warp's slab (coalesced global accesses) ----
+            const int lc4 = (lane & 7) * 4;
+#pragma unroll
+            for (int cs = 0; cs < 4; ++cs) {
+                if (cs * 32 < p.cout) {
+                    __syncwarp();
+                    float* srow = myslab + lane * SLAB_PITCH;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        *reinterpret_cast<float4*>(srow + q * 4) = make_float4(tot[cs * 32 + q * 4] * out_scale, tot[cs * 32 + q * 4 + 1] * out_scale,
+                                                                               tot[cs * 32 + q * 4 + 2] * out_scale, tot[cs * 32 + q * 4 + 3] * out_scale);
+                    __syncwarp();
+                    const int col = cs * 32 + lc4;
+                    float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f), h4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (p.scale) { s4 = __ldg(reinterpret_cast<const float4*>(p.scale + col)); h4 = __ldg(reinterpret_cast<const float4*>(p.shift + col)); }
+#pragma unroll
+                    for (int i0 = 0; i0 < 8; i0 += 4) {             // four rows per batch: loads first, then math + stores
+                        float4 pre[4], res[4], gat[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int i = i0 + u;
+                            pre[u] = make_float4(0.f, 0.f, 0.f, 0.f); res[u] = pre[u]; gat[u] = make_float4(1.f, 1.f, 1.f, 1.f);
+                            if (orows[i] >= 0) {
+                                const long long ro = (long long)orows[i] * p.cout + col;
+                                if (io.pre_add) pre[u] = __ldg(reinterpret_cast<const float4*>(io.pre_add + ro));
+                                if (io.residual) res[u] = __ldg(reinterpret_cast<const float4*>(io.residual + ro));
+                                if (io.gate_table) gat[u] = __ldg(reinterpret_cast<const float4*>(io.gate_table + (long long)gidx[i] * p.cout + col));
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int i = i0 + u;
+                            const int orow = orows[i];
+                            if (orow < 0) continue;
+                            const int rr = (lane >> 3) + 4 * i;
+                            const long long ro = (long long)orow * p.cout + col;
+                            const float4 a4 = *reinterpret_cast<const float4*>(myslab + rr * SLAB_PITCH + lc4);
+                            float y[4] = {a4.x + pre[u].x, a4.y + pre[u].y, a4.z + pre[u].z, a4.w + pre[u].w};
+                            y[0] = fmaf(y[0], s4.x, h4.x) + res[u].x; y[1] = fmaf(y[1], s4.y, h4.y) + res[u].y;
+                            y[2] = fmaf(y[2], s4.z, h4.z) + res[u].z; y[3] = fmaf(y[3], s4.w, h4.w) + res[u].w;
+                            if (p.relu) {
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) y[q] = fmaxf(y[q], 0.f);
+                            }
+                            if (io.out) *reinterpret_cast<float4*>(io.out + ro) = make_float4(y[0], y[1], y[2], y[3]);
+                            if (io.out_h) store_split4(io.out_h, orow, p.cout, col, y);
+                            if (io.out_gated || io.out_gated_h) {
+                                y[0] *= gat[u].x; y[1] *= gat[u].y; y[2] *= gat[u].z; y[3] *= gat[u].w;
+                                if (io.out_gated) *reinterpret_cast<float4*>(io.out_gated + ro) = make_float4(y[0], y[1], y[2], y[3]);
+                                if (io.out_gated_h) store_split4(io.out_gated_h, orow, p.cout, col, y);
+                            }
+                        }
+                    }
+                }
+            }
+            mbar_arrive(meta_empty(b));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)p.tmem_cols) : "memory");
+}
+
+static size_t smem_bytes(int cout) {
+    return 1024 + (size_t)(NA / 2) * 2 * A_TILE + (size_t)NB * 2 * cout * 128 + SLAB_BYTES + MAX_KVOL * BM * sizeof(int) + META * BM * sizeof(int) +
+           4 * META * sizeof(uint32_t) + NBAR * 8 + 64;
+}
+
+}  // namespace tc4
+
+bool lb2_spconv_tc4_supported(const lb2_conv_desc* d) {
+    if (d->cout > 128 || d->cout % 32 != 0) return false;
+    if ((d->c1 + d->c2) % 32 != 0 || d->c1 % 32 != 0) return false;          // whole 32-column A slots; a slot never straddles in1/in2
+    return tc4::smem_bytes(d->cout) <= 227 * 1024;
+}
+
+int lb2_spconv_tc4_launch(Lb2Handle* h, cudaStream_t s, const lb2_conv_desc* d, int step_budget) {
+    tc4::Params p;
+    p.c1 = d->c1; p.c2 = d->c2; p.cout = d->cout; p.kvol = d->kvol; p.npass = d->npass;
+    p.wpacked = (const unsigned char*)d->weight_packed;
+    p.scale = d->scale; p.shift = d->shift; p.relu = d->relu;
+    p.nbr = d->nbr; p.nbr_stride = d->nbr_stride; p.d_mout = d->d_mout; p.mout_cap = d->mout_cap; p.row_perm = d->row_perm;
+    p.nchunks = (d->c1 + d->c2 + tc::KC - 1) / tc::KC;
+    p.nhalf = (d->c1 + d->c2) / 32;
+    p.acc_stride = d->cout <= 32 ? 32 : d->cout <= 64 ? 64 : 128;
+    p.tmem_cols = tc4::NACC * p.acc_stride;                       // 128 / 256 / 512: powers of two >= 32
+    const int steps_per_offset = 3 * ((d->c1 + d->c2 + 15) / 16);
+    p.group = std::max(1, step_budget / steps_per_offset);
+    p.io[0] = d->io[0]; p.io[1] = d->io[d->npass > 1 ? 1 : 0];
+    const size_t smem = tc4::smem_bytes(d->cout);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(tc4::k_spconv_tc_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+        if (e != cudaSuccess) return lb2_fail(h, LB2_ERR_CUDA, "k_spconv_tc_small smem attribute: %s", cudaGetErrorString(e));
+        configured = true;
+    }
+    const long long tiles_cap = (long long)cdiv(d->mout_cap, tc::BM) * d->npass;
+    const unsigned grid = (unsigned)std::min<long long>(h->num_sms, tiles_cap);
+    tc4::k_spconv_tc_small<<<grid, tc4::THREADS, smem, s>>>(p);
+    LB2_POST_LAUNCH(h, "k_spconv_tc_small");
+    return LB2_OK;
+}
