@@ -138,6 +138,8 @@ typedef struct {
     const int32_t* d_mout;      /* device row count or NULL => mout_cap */
     int32_t        mout_cap;
     const int32_t* row_perm;    /* execution order from lb2_row_order or NULL (natural order) */
+    const uint32_t* row_mask;   /* per output row: bit k set <=> nbr[k][row] >= 0 (lb2_kernel_map's row_mask) or NULL.
+                                   A hint: lets the kernels skip the index loads of absent offsets */
     int32_t        npass;       /* 1 or 2 */
     lb2_conv_io    io[2];
 } lb2_conv_desc;

@@ -32,7 +32,8 @@ class ConvDesc(C.Structure):
                 ("weight", C.c_void_p), ("weight_packed", C.c_void_p),
                 ("scale", C.c_void_p), ("shift", C.c_void_p), ("relu", C.c_int32),
                 ("nbr", C.c_void_p), ("nbr_stride", C.c_int64),
-                ("d_mout", C.c_void_p), ("mout_cap", C.c_int32), ("row_perm", C.c_void_p), ("npass", C.c_int32),
+                ("d_mout", C.c_void_p), ("mout_cap", C.c_int32), ("row_perm", C.c_void_p), ("row_mask", C.c_void_p),
+                ("npass", C.c_int32),
                 ("io", ConvIO * 2)]
 
 

@@ -42,6 +42,7 @@ struct Params {
     const int* d_mout;
     int mout_cap;
     const int* row_perm;
+    const unsigned* row_mask;
     int stages, lag, nchunks, tmem_cols, tot_col, group, nbuf, acc_stride, npass;
     lb2_conv_io io[2];
 };
@@ -114,7 +115,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_persist(const Params p
             const int slot = tile * BM + t;
             return (slot < M) ? (p.row_perm ? __ldg(p.row_perm + slot) : slot) : -1;
         };
+        auto fetch_mask = [&](int row) -> uint32_t {                   // candidate offsets of a row: its neighbour bit mask if the caller has one
+            if (row < 0) return 0u;
+            return p.row_mask ? __ldg(p.row_mask + row) : ((p.kvol >= 32) ? 0xffffffffu : ((1u << p.kvol) - 1u));
+        };
         int next_row = fetch_row(blockIdx.x);
+        int next2_row = fetch_row(blockIdx.x + gridDim.x);
+        uint32_t next_mask = fetch_mask(next_row);
         for (int item = blockIdx.x; item < total; item += gridDim.x, ++j) {
             const int b = j % META;
             const int pass = (item >= n_tiles) ? 1 : 0;
@@ -123,27 +130,31 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_persist(const Params p
             asm volatile("bar.sync 2, 128;" ::: "memory");              // everybody is done reading the previous tile's idx_s
             {
                 const int row = next_row;
-                next_row = fetch_row(item + gridDim.x);                 // prefetch: its latency hides behind this tile's gathers
+                const uint32_t have = next_mask;                        // offsets this row may have a neighbour at
+                next_row = next2_row;
+                next2_row = fetch_row(item + 2 * gridDim.x);            // prefetch two tiles ahead (row), one tile ahead (its mask):
+                next_mask = fetch_mask(next_row);                       // their latency hides behind this tile's gathers
                 row_s[b * BM + t] = row;
-                uint32_t mymask = 0;
-                for (int k0 = 0; k0 < p.kvol; k0 += 9) {        // 9 independent loads in flight, then the votes
+                uint32_t found = 0;
+                for (int k0 = 0; k0 < p.kvol; k0 += 9) {                // up to 9 independent loads in flight, only for present offsets
                     int v[9];
 #pragma unroll
                     for (int q = 0; q < 9; ++q) {
                         const int k = k0 + q;
                         v[q] = -1;
-                        if (k < p.kvol && row >= 0) v[q] = p.nbr ? __ldg(p.nbr + (long long)k * p.nbr_stride + row) : row;
+                        if (k < p.kvol && ((have >> k) & 1u)) v[q] = p.nbr ? __ldg(p.nbr + (long long)k * p.nbr_stride + row) : row;
                     }
 #pragma unroll
                     for (int q = 0; q < 9; ++q) {
                         const int k = k0 + q;
                         if (k < p.kvol) {
                             idx_s[k * BM + t] = v[q];
-                            if (__any_sync(0xffffffffu, v[q] >= 0)) mymask |= 1u << k;
+                            if (v[q] >= 0) found |= 1u << k;
                         }
                     }
                 }
-                if (lane == 0) wmask[b * 4 + warp] = mymask;
+                const uint32_t wm = __reduce_or_sync(0xffffffffu, p.row_mask ? have : found);
+                if (lane == 0) wmask[b * 4 + warp] = wm;
             }
             asm volatile("bar.sync 2, 128;" ::: "memory");
             if (t == 0) mbar_arrive(meta_full(b));
@@ -402,7 +413,7 @@ int lb2_spconv_tc2_launch(Lb2Handle* h, cudaStream_t s, const lb2_conv_desc* d, 
     p.c1 = d->c1; p.c2 = d->c2; p.cout = d->cout; p.kvol = d->kvol; p.npass = d->npass;
     p.wpacked = (const unsigned char*)d->weight_packed;
     p.scale = d->scale; p.shift = d->shift; p.relu = d->relu;
-    p.nbr = d->nbr; p.nbr_stride = d->nbr_stride; p.d_mout = d->d_mout; p.mout_cap = d->mout_cap; p.row_perm = d->row_perm;
+    p.nbr = d->nbr; p.nbr_stride = d->nbr_stride; p.d_mout = d->d_mout; p.mout_cap = d->mout_cap; p.row_perm = d->row_perm; p.row_mask = d->row_mask;
     p.nchunks = (d->c1 + d->c2 + tc::KC - 1) / tc::KC;
     int stages = tc2::MAX_STAGES;
     while (stages > 1 && tc2::smem_bytes(d->cout, stages) > 227 * 1024) --stages;

@@ -45,6 +45,7 @@ struct Params {
     const int* d_mout;
     int mout_cap;
     const int* row_perm;
+    const unsigned* row_mask;
     int stages, lag, nchunks, tmem_cols, tot_col, group, nbuf, acc_stride, npass;
     lb2_conv_io io[2];
 };
@@ -66,7 +67,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_n256(const Params p) {
     unsigned char* tail = gen + (size_t)(NA / 2) * a_stage + (size_t)NB * 2u * b_tile;
     float* slab = reinterpret_cast<float*>(tail);                                   // [8 warps][32][SLAB_PITCH]
     int* row_s = reinterpret_cast<int*>(tail + SLAB_BYTES);                          // [META][BM]
-    uint32_t* wmask = reinterpret_cast<uint32_t*>(row_s + META * BM);                // [META][4] per-warp offset masks
+    uint32_t* mask_s = reinterpret_cast<uint32_t*>(row_s + META * BM);               // [META][BM] neighbour bit mask of each tile row
+    uint32_t* wmask = mask_s + META * BM;                                            // [META][4] per-warp offset masks
     uint64_t* bars = reinterpret_cast<uint64_t*>(wmask + 4 * META);
     constexpr int NBAR = 2 * NA + 2 * NB + 4 + 2 * META;
     uint32_t* misc = reinterpret_cast<uint32_t*>(bars + NBAR);
@@ -114,7 +116,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_n256(const Params p) {
             const int slot = ((item >= n_tiles) ? item - n_tiles : item) * BM + t;
             return (slot < M) ? (p.row_perm ? __ldg(p.row_perm + slot) : slot) : -1;
         };
+        auto fetch_mask = [&](int row) -> uint32_t {                   // candidate offsets of a row: its neighbour bit mask if the caller has one
+            if (row < 0) return 0u;
+            return p.row_mask ? __ldg(p.row_mask + row) : ((p.kvol >= 32) ? 0xffffffffu : ((1u << p.kvol) - 1u));
+        };
         int next_row = fetch_row(blockIdx.x);
+        int next2_row = fetch_row(blockIdx.x + gridDim.x);
+        uint32_t next_mask = fetch_mask(next_row);
         for (int item = blockIdx.x; item < total; item += gridDim.x, ++j) {
             const int b = j % META;
             const int pass = (item >= n_tiles) ? 1 : 0;
@@ -122,34 +130,43 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_n256(const Params p) {
             if (j >= META) mbar_wait(meta_empty(b), ((j / META) - 1) & 1);
             {
                 const int row = next_row;
-                next_row = fetch_row(item + gridDim.x);
+                const uint32_t have = next_mask;
+                next_row = next2_row;
+                next2_row = fetch_row(item + 2 * gridDim.x);            // prefetch two tiles ahead (row), one tile ahead (its mask)
+                next_mask = fetch_mask(next_row);
                 row_s[b * BM + t] = row;
-                uint32_t mymask = 0;
-                for (int k0 = 0; k0 < p.kvol; k0 += 9) {
-                    int v[9];
+                uint32_t found = have;
+                if (!p.row_mask) {                                      // no mask from the caller: find the populated offsets by reading the map
+                    found = 0;
+                    for (int k0 = 0; k0 < p.kvol; k0 += 9) {
+                        int v[9];
 #pragma unroll
-                    for (int q = 0; q < 9; ++q) {
-                        const int k = k0 + q;
-                        v[q] = -1;
-                        if (k < p.kvol && row >= 0) v[q] = p.nbr ? __ldg(p.nbr + (long long)k * p.nbr_stride + row) : row;
+                        for (int q = 0; q < 9; ++q) {
+                            const int k = k0 + q;
+                            v[q] = -1;
+                            if (k < p.kvol && row >= 0) v[q] = p.nbr ? __ldg(p.nbr + (long long)k * p.nbr_stride + row) : row;
+                        }
+#pragma unroll
+                        for (int q = 0; q < 9; ++q)
+                            if (k0 + q < p.kvol && v[q] >= 0) found |= 1u << (k0 + q);
                     }
-#pragma unroll
-                    for (int q = 0; q < 9; ++q)
-                        if (k0 + q < p.kvol && __any_sync(0xffffffffu, v[q] >= 0)) mymask |= 1u << (k0 + q);
                 }
-                if (lane == 0) wmask[b * 4 + warp] = mymask;
+                mask_s[b * BM + t] = found;
+                const uint32_t wm = __reduce_or_sync(0xffffffffu, found);
+                if (lane == 0) wmask[b * 4 + warp] = wm;
             }
             asm volatile("bar.sync 2, 128;" ::: "memory");
             if (t == 0) mbar_arrive(meta_full(b));
             const uint32_t kmask = tile_kmask(b);
             int myrows[4];
+            uint32_t mymasks[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) myrows[q] = row_s[b * BM + rbase + 32 * q];
+            for (int q = 0; q < 4; ++q) { myrows[q] = row_s[b * BM + rbase + 32 * q]; mymasks[q] = mask_s[b * BM + rbase + 32 * q]; }
             auto load_src = [&](int k, int (&dst)[4]) {              // neighbour rows of this thread's 4 tile rows at offset k
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     dst[q] = -1;
-                    if (myrows[q] >= 0) dst[q] = p.nbr ? __ldg(p.nbr + (long long)k * p.nbr_stride + myrows[q]) : myrows[q];
+                    if ((mymasks[q] >> k) & 1u) dst[q] = p.nbr ? __ldg(p.nbr + (long long)k * p.nbr_stride + myrows[q]) : myrows[q];
                 }
             };
             int src[4], nxt[4];
@@ -379,7 +396,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_n256(const Params p) {
 
 static size_t smem_bytes() {
     return 1024 + (size_t)(NA / 2) * 2 * A_TILE + (size_t)NB * 2 * NCOLS * 128 + SLAB_BYTES + META * BM * sizeof(int) +
-           4 * META * sizeof(uint32_t) + (2 * NA + 2 * NB + 4 + 2 * META) * 8 + 64;
+           META * BM * sizeof(uint32_t) + 4 * META * sizeof(uint32_t) + (2 * NA + 2 * NB + 4 + 2 * META) * 8 + 64;
 }
 
 }  // namespace tc3
@@ -399,7 +416,7 @@ int lb2_spconv_tc3_launch(Lb2Handle* h, cudaStream_t s, const lb2_conv_desc* d, 
     p.c1 = d->c1; p.c2 = d->c2; p.cout = d->cout; p.kvol = d->kvol; p.npass = d->npass;
     p.wpacked = (const unsigned char*)d->weight_packed;
     p.scale = d->scale; p.shift = d->shift; p.relu = d->relu;
-    p.nbr = d->nbr; p.nbr_stride = d->nbr_stride; p.d_mout = d->d_mout; p.mout_cap = d->mout_cap; p.row_perm = d->row_perm;
+    p.nbr = d->nbr; p.nbr_stride = d->nbr_stride; p.d_mout = d->d_mout; p.mout_cap = d->mout_cap; p.row_perm = d->row_perm; p.row_mask = d->row_mask;
     p.nchunks = (d->c1 + d->c2 + tc::KC - 1) / tc::KC;
     p.stages = tc3::NA; p.lag = tc3::A_LAG;
     p.nbuf = 2; p.acc_stride = 256; p.tot_col = 0; p.tmem_cols = 512;

@@ -3,14 +3,14 @@
 // Profiling the generic kernel on those layers (profiles/r01_ncu_stall_attribution.txt) showed its four drain warps busy
 // >95 % of the time (one warp per scheduler, a long dependent instruction stream per tile) while the MMA warp waited for
 // a free accumulator and the producers for a free stage.  This kernel therefore
-//   * runs TWO drain warpgroups that take alternate tiles, keeps the fp32 running total of the two-level accumulation in
+//   * runs TWO drain warpgroups (alternate tiles for Cout <= 64, half the channels each for Cout 96 / 128), keeps the fp32 running total of the two-level accumulation in
 //     their registers (setmaxnreg: 96 / 48 / 184 / 184 registers for producer / MMA+loader / drain / drain warpgroups) and
 //     releases an accumulator as soon as it has been read, so TMEM holds four accumulators the MMA warp can run ahead into;
 //   * separates the gathered-A ring (4 slots of 32 K-columns: the two halves of a 128-byte swizzled row image are disjoint
 //     sets of 16-byte chunks) from the weight ring (3 slots of 64 K-columns), with a gather lookahead of two slots.
 //   WG0 warps 0-3   A producers (cp.async from the fp16 split companions, or fp32 -> split in registers)
 //   WG1 warp 4 MMA issuer, warp 5 weight loader (warps 6,7 idle)
-//   WG2 warps 8-11  drain + epilogue of even tiles        WG3 warps 12-15: odd tiles
+//   WG2 warps 8-11  drain + epilogue of even tiles / the low channels        WG3 warps 12-15: odd tiles / the high channels
 // Same math and results as k_spconv_tc / k_spconv_tc_persist (tests compare them).
 #include "common.cuh"
 #include <algorithm>
@@ -26,7 +26,7 @@ constexpr int NA = 4;                                 // A slots (32 K-columns e
 constexpr int A_LAG = 2;                              // cp.async lookahead in A slots (NA - 2, see spconv_tc2.cu)
 constexpr int NB = 3;                                 // weight slots (64 K-columns each)
 constexpr int NACC = 4;                               // TMEM accumulators
-constexpr int SLAB_PITCH = 36;                        // floats per slab row (32 + 4: conflict-free 16-byte accesses)
+constexpr int SLAB_PITCH = 20;                        // floats per slab row (16 + 4: conflict-free 16-byte accesses)
 constexpr int SLAB_BYTES = 8 * 32 * SLAB_PITCH * 4;   // 8 drain warps x 32 rows
 constexpr int META = 4;                               // ring of per-tile metadata; must exceed the gather lookahead in tiles (<= 1)
 constexpr int NBAR = 2 * NA + 2 * NB + 2 * NACC + 2 * META;
@@ -42,6 +42,7 @@ struct Params {
     const int* d_mout;
     int mout_cap;
     const int* row_perm;
+    const unsigned* row_mask;
     int nchunks, nhalf, tmem_cols, group, acc_stride, npass;
     lb2_conv_io io[2];
 };
@@ -51,6 +52,7 @@ struct Ring {                                             // position in a ring 
     __device__ __forceinline__ void next() { if (++s == n) { s = 0; par ^= 1u; } }
 };
 
+template <int NCC>                                        // NCC = Cout / 32: sizes the register-resident running total
 __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_small(const Params p) {
     extern __shared__ unsigned char smem_raw[];
     const int M = p.d_mout ? min(*p.d_mout, p.mout_cap) : p.mout_cap;
@@ -68,7 +70,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_small(const Params p) 
     float* slab = reinterpret_cast<float*>(tail);                                   // [8 warps][32][SLAB_PITCH]
     int* idx_s = reinterpret_cast<int*>(tail + SLAB_BYTES);                          // [kvol][BM] (producer private)
     int* row_s = idx_s + MAX_KVOL * BM;                                              // [META][BM]
-    uint32_t* wmask = reinterpret_cast<uint32_t*>(row_s + META * BM);                // [META][4] per-warp offset masks
+    int* gate_s = row_s + META * BM;                                                 // [8 drain warps][32] gate-table rows of the tile being drained
+    uint32_t* wmask = reinterpret_cast<uint32_t*>(gate_s + 8 * 32);                  // [META][4] per-warp offset masks
     uint64_t* bars = reinterpret_cast<uint64_t*>(wmask + 4 * META);
     uint32_t* misc = reinterpret_cast<uint32_t*>(bars + NBAR);
     const uint32_t bar0 = smem_u32(bars);
@@ -84,7 +87,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_small(const Params p) 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NA; ++s) { mbar_init(full_a(s), 128); mbar_init(empty_a(s), 1); }
         for (int s = 0; s < NB; ++s) { mbar_init(full_b(s), 1); mbar_init(empty_b(s), 1); }
-        for (int b = 0; b < NACC; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), 128); }    // the drain warpgroup that owns the tile
+        for (int b = 0; b < NACC; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), NCC >= 3 ? 256 : 128); }    // the drain warpgroup(s) reading it
         for (int b = 0; b < META; ++b) { mbar_init(meta_full(b), 1); mbar_init(meta_empty(b), 258); }   // MMA + loader + both drain warpgroups
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -111,7 +114,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_small(const Params p) 
             const int slot = ((item >= n_tiles) ? item - n_tiles : item) * BM + t;
             return (slot < M) ? (p.row_perm ? __ldg(p.row_perm + slot) : slot) : -1;
         };
+        auto fetch_mask = [&](int row) -> uint32_t {                   // candidate offsets of a row: its neighbour bit mask if the caller has one
+            if (row < 0) return 0u;
+            return p.row_mask ? __ldg(p.row_mask + row) : ((p.kvol >= 32) ? 0xffffffffu : ((1u << p.kvol) - 1u));
+        };
         int next_row = fetch_row(blockIdx.x);
+        int next2_row = fetch_row(blockIdx.x + gridDim.x);
+        uint32_t next_mask = fetch_mask(next_row);
         for (int item = blockIdx.x; item < total; item += gridDim.x, ++j) {
             const int b = j % META;
             const lb2_conv_io io = p.io[(item >= n_tiles) ? 1 : 0];
@@ -119,27 +128,31 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_small(const Params p) 
             asm volatile("bar.sync 2, 128;" ::: "memory");              // everybody is done reading the previous tile's idx_s
             {
                 const int row = next_row;
-                next_row = fetch_row(item + gridDim.x);                 // prefetch: its latency hides behind this tile's gathers
+                const uint32_t have = next_mask;                        // offsets this row may have a neighbour at
+                next_row = next2_row;
+                next2_row = fetch_row(item + 2 * gridDim.x);            // prefetch two tiles ahead (row), one tile ahead (its mask):
+                next_mask = fetch_mask(next_row);                       // their latency hides behind this tile's gathers
                 row_s[b * BM + t] = row;
-                uint32_t mymask = 0;
-                for (int k0 = 0; k0 < p.kvol; k0 += 9) {                // 9 independent loads in flight, then the votes
+                uint32_t found = 0;
+                for (int k0 = 0; k0 < p.kvol; k0 += 9) {                // up to 9 independent loads in flight, only for present offsets
                     int v[9];
 #pragma unroll
                     for (int q = 0; q < 9; ++q) {
                         const int k = k0 + q;
                         v[q] = -1;
-                        if (k < p.kvol && row >= 0) v[q] = p.nbr ? __ldg(p.nbr + (long long)k * p.nbr_stride + row) : row;
+                        if (k < p.kvol && ((have >> k) & 1u)) v[q] = p.nbr ? __ldg(p.nbr + (long long)k * p.nbr_stride + row) : row;
                     }
 #pragma unroll
                     for (int q = 0; q < 9; ++q) {
                         const int k = k0 + q;
                         if (k < p.kvol) {
                             idx_s[k * BM + t] = v[q];
-                            if (__any_sync(0xffffffffu, v[q] >= 0)) mymask |= 1u << k;
+                            if (v[q] >= 0) found |= 1u << k;
                         }
                     }
                 }
-                if (lane == 0) wmask[b * 4 + warp] = mymask;
+                const uint32_t wm = __reduce_or_sync(0xffffffffu, p.row_mask ? have : found);
+                if (lane == 0) wmask[b * 4 + warp] = wm;
             }
             asm volatile("bar.sync 2, 128;" ::: "memory");
             if (t == 0) mbar_arrive(meta_full(b));
@@ -280,113 +293,112 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_small(const Params p) 
         }
         __syncwarp();
     } else {
-        // =========================== WG2 / WG3: drain (register-resident fp32 total) + epilogue of alternate tiles ===========================
+        // =========================== WG2 / WG3: drain (register-resident fp32 total) + epilogue ===========================
+        // Cout <= 64: the warpgroups take alternate tiles (all channels); Cout 96 / 128: both take every tile, half the channels each
+        // (48 / 64 running totals per thread either way leave the registers for a 4-row epilogue batch).
         asm volatile("setmaxnreg.inc.sync.aligned.u32 184;");
+        constexpr bool COLSPLIT = NCC >= 3;
+        constexpr int TOT = COLSPLIT ? 16 * NCC : 32 * NCC;       // channels this warp drains per tile
         const int q4 = warp & 3;                                   // TMEM lane quarter
-        const int mine = (warp >= 12) ? 1 : 0;                     // tile parity this warpgroup owns
+        const int wg = (warp >= 12) ? 1 : 0;
+        const int cb = COLSPLIT ? wg * TOT : 0;                    // first of them
         const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;
         float* myslab = slab + (size_t)(warp - 8) * 32 * SLAB_PITCH;
-        float tot[128];
+        float tot[TOT];
         int gcount = 0, j = 0;
         for (int item = blockIdx.x; item < total; item += gridDim.x, ++j) {
             const int b = j % META;
-            const lb2_conv_io io = p.io[(item >= n_tiles) ? 1 : 0];
+            const lb2_conv_io& io = p.io[(item >= n_tiles) ? 1 : 0];       // fields are read from the parameter bank when used
             mbar_wait(meta_full(b), (j / META) & 1);
             const uint32_t kmask = tile_kmask(b);
             const int n_off = __popc(kmask);
             int n_groups = 0;
             for (int o = 0; o < n_off; o += p.group) ++n_groups;
-            if ((j & 1) != mine) {                                  // the other warpgroup's tile: only keep the accumulator count in step
+            if (!COLSPLIT && (j & 1) != wg) {                       // the other warpgroup's tile: only keep the accumulator count in step
                 gcount += n_groups;
                 mbar_arrive(meta_empty(b));
                 continue;
             }
-            const int* rows = row_s + b * BM + q4 * 32;
-            int orows[8], gidx[8];                                  // the 8 rows this lane serves in the epilogue + their gate rows
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                orows[i] = rows[(lane >> 3) + 4 * i];
-                gidx[i] = (io.gate_table && io.gate_idx && orows[i] >= 0) ? __ldg(io.gate_idx + orows[i]) : 0;
+            const int* rows = row_s + b * BM + q4 * 32;             // this warp's 32 output rows
+            int* grow = gate_s + (warp - 8) * 32;                   // ... and their gate-table rows (kept in shared memory: registers hold the totals)
+            {
+                const int r = rows[lane];
+                __syncwarp();
+                grow[lane] = (io.gate_table && io.gate_idx && r >= 0) ? __ldg(io.gate_idx + r) : 0;
+                __syncwarp();
             }
             if (n_groups == 0) {
 #pragma unroll
-                for (int q = 0; q < 128; ++q) tot[q] = 0.f;
+                for (int q = 0; q < TOT; ++q) tot[q] = 0.f;
             }
             for (int g = 0; g < n_groups; ++g) {
                 const int buf = gcount & (NACC - 1);
                 mbar_wait(acc_full(buf), (gcount / NACC) & 1);
                 tc_fence_after();
 #pragma unroll
-                for (int cc = 0; cc < 4; ++cc) {
-                    if (cc * 32 < p.cout) {
-                        uint32_t r[32];
-                        tmem_ld32(tmem_d + lane_base + (uint32_t)(buf * p.acc_stride + cc * 32), r);
-                        tmem_ld_wait();
-                        if (g == 0) {
+                for (int cc = 0; cc < TOT / 16; ++cc) {
+                    uint32_t r[16];
+                    tmem_ld16(tmem_d + lane_base + (uint32_t)(buf * p.acc_stride + cb + cc * 16), r);
+                    tmem_ld_wait();
+                    if (g == 0) {
 #pragma unroll
-                            for (int q = 0; q < 32; ++q) tot[cc * 32 + q] = __uint_as_float(r[q]);
-                        } else {
+                        for (int q = 0; q < 16; ++q) tot[cc * 16 + q] = __uint_as_float(r[q]);
+                    } else {
 #pragma unroll
-                            for (int q = 0; q < 32; ++q) tot[cc * 32 + q] = __fadd_rn(tot[cc * 32 + q], __uint_as_float(r[q]));
-                        }
+                        for (int q = 0; q < 16; ++q) tot[cc * 16 + q] = __fadd_rn(tot[cc * 16 + q], __uint_as_float(r[q]));
                     }
                 }
                 tc_fence_before();
                 mbar_arrive(acc_empty(buf));                       // accumulator free again: the MMA warp runs on while we finish
                 ++gcount;
             }
-            // ---- epilogue from registers, 32 channels at a time through the warp's slab (coalesced global accesses) ----
-            const int lc4 = (lane & 7) * 4;
+            // ---- epilogue from registers, 16 channels at a time through the warp's slab (coalesced global accesses) ----
+            const int lc4 = (lane & 3) * 4;
 #pragma unroll
-            for (int cs = 0; cs < 4; ++cs) {
-                if (cs * 32 < p.cout) {
-                    __syncwarp();
-                    float* srow = myslab + lane * SLAB_PITCH;
+            for (int cs = 0; cs < TOT / 16; ++cs) {
+                __syncwarp();
+                float* srow = myslab + lane * SLAB_PITCH;
 #pragma unroll
-                    for (int q = 0; q < 8; ++q)
-                        *reinterpret_cast<float4*>(srow + q * 4) = make_float4(tot[cs * 32 + q * 4] * out_scale, tot[cs * 32 + q * 4 + 1] * out_scale,
-                                                                               tot[cs * 32 + q * 4 + 2] * out_scale, tot[cs * 32 + q * 4 + 3] * out_scale);
-                    __syncwarp();
-                    const int col = cs * 32 + lc4;
-                    float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f), h4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (p.scale) { s4 = __ldg(reinterpret_cast<const float4*>(p.scale + col)); h4 = __ldg(reinterpret_cast<const float4*>(p.shift + col)); }
+                for (int q = 0; q < 4; ++q)
+                    *reinterpret_cast<float4*>(srow + q * 4) = make_float4(tot[cs * 16 + q * 4] * out_scale, tot[cs * 16 + q * 4 + 1] * out_scale,
+                                                                           tot[cs * 16 + q * 4 + 2] * out_scale, tot[cs * 16 + q * 4 + 3] * out_scale);
+                __syncwarp();
+                const int col = cb + cs * 16 + lc4;
+                float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f), h4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.scale) { s4 = __ldg(reinterpret_cast<const float4*>(p.scale + col)); h4 = __ldg(reinterpret_cast<const float4*>(p.shift + col)); }
+                float4 pre[4], res[4], gat[4];                      // this lane's 4 rows: all loads first, then math + stores
 #pragma unroll
-                    for (int i0 = 0; i0 < 8; i0 += 4) {             // four rows per batch: loads first, then math + stores
-                        float4 pre[4], res[4], gat[4];
+                for (int u = 0; u < 4; ++u) {
+                    const int rr = (lane >> 2) + 8 * u;
+                    const int orow = rows[rr];
+                    pre[u] = make_float4(0.f, 0.f, 0.f, 0.f); res[u] = pre[u]; gat[u] = make_float4(1.f, 1.f, 1.f, 1.f);
+                    if (orow >= 0) {
+                        const long long ro = (long long)orow * p.cout + col;
+                        if (io.pre_add) pre[u] = __ldg(reinterpret_cast<const float4*>(io.pre_add + ro));
+                        if (io.residual) res[u] = __ldg(reinterpret_cast<const float4*>(io.residual + ro));
+                        if (io.gate_table) gat[u] = __ldg(reinterpret_cast<const float4*>(io.gate_table + (long long)grow[rr] * p.cout + col));
+                    }
+                }
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int i = i0 + u;
-                            pre[u] = make_float4(0.f, 0.f, 0.f, 0.f); res[u] = pre[u]; gat[u] = make_float4(1.f, 1.f, 1.f, 1.f);
-                            if (orows[i] >= 0) {
-                                const long long ro = (long long)orows[i] * p.cout + col;
-                                if (io.pre_add) pre[u] = __ldg(reinterpret_cast<const float4*>(io.pre_add + ro));
-                                if (io.residual) res[u] = __ldg(reinterpret_cast<const float4*>(io.residual + ro));
-                                if (io.gate_table) gat[u] = __ldg(reinterpret_cast<const float4*>(io.gate_table + (long long)gidx[i] * p.cout + col));
-                            }
-                        }
+                for (int u = 0; u < 4; ++u) {
+                    const int rr = (lane >> 2) + 8 * u;
+                    const int orow = rows[rr];
+                    if (orow < 0) continue;
+                    const long long ro = (long long)orow * p.cout + col;
+                    const float4 a4 = *reinterpret_cast<const float4*>(myslab + rr * SLAB_PITCH + lc4);
+                    float y[4] = {a4.x + pre[u].x, a4.y + pre[u].y, a4.z + pre[u].z, a4.w + pre[u].w};
+                    y[0] = fmaf(y[0], s4.x, h4.x) + res[u].x; y[1] = fmaf(y[1], s4.y, h4.y) + res[u].y;
+                    y[2] = fmaf(y[2], s4.z, h4.z) + res[u].z; y[3] = fmaf(y[3], s4.w, h4.w) + res[u].w;
+                    if (p.relu) {
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int i = i0 + u;
-                            const int orow = orows[i];
-                            if (orow < 0) continue;
-                            const int rr = (lane >> 3) + 4 * i;
-                            const long long ro = (long long)orow * p.cout + col;
-                            const float4 a4 = *reinterpret_cast<const float4*>(myslab + rr * SLAB_PITCH + lc4);
-                            float y[4] = {a4.x + pre[u].x, a4.y + pre[u].y, a4.z + pre[u].z, a4.w + pre[u].w};
-                            y[0] = fmaf(y[0], s4.x, h4.x) + res[u].x; y[1] = fmaf(y[1], s4.y, h4.y) + res[u].y;
-                            y[2] = fmaf(y[2], s4.z, h4.z) + res[u].z; y[3] = fmaf(y[3], s4.w, h4.w) + res[u].w;
-                            if (p.relu) {
-#pragma unroll
-                                for (int q = 0; q < 4; ++q) y[q] = fmaxf(y[q], 0.f);
-                            }
-                            if (io.out) *reinterpret_cast<float4*>(io.out + ro) = make_float4(y[0], y[1], y[2], y[3]);
-                            if (io.out_h) store_split4(io.out_h, orow, p.cout, col, y);
-                            if (io.out_gated || io.out_gated_h) {
-                                y[0] *= gat[u].x; y[1] *= gat[u].y; y[2] *= gat[u].z; y[3] *= gat[u].w;
-                                if (io.out_gated) *reinterpret_cast<float4*>(io.out_gated + ro) = make_float4(y[0], y[1], y[2], y[3]);
-                                if (io.out_gated_h) store_split4(io.out_gated_h, orow, p.cout, col, y);
-                            }
-                        }
+                        for (int q = 0; q < 4; ++q) y[q] = fmaxf(y[q], 0.f);
+                    }
+                    if (io.out) *reinterpret_cast<float4*>(io.out + ro) = make_float4(y[0], y[1], y[2], y[3]);
+                    if (io.out_h) store_split4(io.out_h, orow, p.cout, col, y);
+                    if (io.out_gated || io.out_gated_h) {
+                        y[0] *= gat[u].x; y[1] *= gat[u].y; y[2] *= gat[u].z; y[3] *= gat[u].w;
+                        if (io.out_gated) *reinterpret_cast<float4*>(io.out_gated + ro) = make_float4(y[0], y[1], y[2], y[3]);
+                        if (io.out_gated_h) store_split4(io.out_gated_h, orow, p.cout, col, y);
                     }
                 }
             }
@@ -400,7 +412,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_small(const Params p) 
 
 static size_t smem_bytes(int cout) {
     return 1024 + (size_t)(NA / 2) * 2 * A_TILE + (size_t)NB * 2 * cout * 128 + SLAB_BYTES + MAX_KVOL * BM * sizeof(int) + META * BM * sizeof(int) +
-           4 * META * sizeof(uint32_t) + NBAR * 8 + 64;
+           8 * 32 * sizeof(int) + 4 * META * sizeof(uint32_t) + NBAR * 8 + 64;
 }
 
 }  // namespace tc4
@@ -416,7 +428,7 @@ int lb2_spconv_tc4_launch(Lb2Handle* h, cudaStream_t s, const lb2_conv_desc* d, 
     p.c1 = d->c1; p.c2 = d->c2; p.cout = d->cout; p.kvol = d->kvol; p.npass = d->npass;
     p.wpacked = (const unsigned char*)d->weight_packed;
     p.scale = d->scale; p.shift = d->shift; p.relu = d->relu;
-    p.nbr = d->nbr; p.nbr_stride = d->nbr_stride; p.d_mout = d->d_mout; p.mout_cap = d->mout_cap; p.row_perm = d->row_perm;
+    p.nbr = d->nbr; p.nbr_stride = d->nbr_stride; p.d_mout = d->d_mout; p.mout_cap = d->mout_cap; p.row_perm = d->row_perm; p.row_mask = d->row_mask;
     p.nchunks = (d->c1 + d->c2 + tc::KC - 1) / tc::KC;
     p.nhalf = (d->c1 + d->c2) / 32;
     p.acc_stride = d->cout <= 32 ? 32 : d->cout <= 64 ? 64 : 128;
@@ -427,13 +439,21 @@ int lb2_spconv_tc4_launch(Lb2Handle* h, cudaStream_t s, const lb2_conv_desc* d, 
     const size_t smem = tc4::smem_bytes(d->cout);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(tc4::k_spconv_tc_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+        cudaError_t e = cudaFuncSetAttribute(tc4::k_spconv_tc_small<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc4::k_spconv_tc_small<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc4::k_spconv_tc_small<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc4::k_spconv_tc_small<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
         if (e != cudaSuccess) return lb2_fail(h, LB2_ERR_CUDA, "k_spconv_tc_small smem attribute: %s", cudaGetErrorString(e));
         configured = true;
     }
     const long long tiles_cap = (long long)cdiv(d->mout_cap, tc::BM) * d->npass;
     const unsigned grid = (unsigned)std::min<long long>(h->num_sms, tiles_cap);
-    tc4::k_spconv_tc_small<<<grid, tc4::THREADS, smem, s>>>(p);
+    switch (d->cout / 32) {
+        case 1: tc4::k_spconv_tc_small<1><<<grid, tc4::THREADS, smem, s>>>(p); break;
+        case 2: tc4::k_spconv_tc_small<2><<<grid, tc4::THREADS, smem, s>>>(p); break;
+        case 3: tc4::k_spconv_tc_small<3><<<grid, tc4::THREADS, smem, s>>>(p); break;
+        default: tc4::k_spconv_tc_small<4><<<grid, tc4::THREADS, smem, s>>>(p); break;
+    }
     LB2_POST_LAUNCH(h, "k_spconv_tc_small");
     return LB2_OK;
 }

@@ -116,7 +116,7 @@ class Geometry:
         self.pairs = torch.zeros(18, dtype=torch.int64, device=dev)
         self.map_id = {}
         # execution order of the output rows of each map (rows bucketed by neighbour mask, lb2_row_order)
-        self.row_mask = torch.zeros(n_cap, **i32)
+        self.mask_of = {}                                    # map -> its per-row neighbour bit mask (conv kernels skip absent offsets)
         self.ro_scratch = torch.zeros(256, **i32)            # lb2_row_order_scratch_bytes() = 1 KB
         self.perm3 = [torch.zeros(n_cap, **i32) for _ in range(levels)]
         self.perm_dn = [None] + [torch.zeros(n_cap, **i32) for _ in range(levels - 1)]
@@ -141,8 +141,11 @@ class Geometry:
         self.pairs.zero_()
 
         def one(grid, l_out, ks, step, nbr, perm, slot):
-            h.kernel_map(grid, self.C[l_out], self.d_n[l_out], N, ks, step, nbr, N, self.pairs[slot:slot + 1], self.row_mask)
-            h.row_order(self.row_mask, self.d_n[l_out], N, ks ** 3, perm, self.ro_scratch)
+            mask = self.mask_of.get(nbr.data_ptr())
+            if mask is None:
+                mask = self.mask_of[nbr.data_ptr()] = torch.zeros(N, dtype=torch.int32, device=nbr.device)
+            h.kernel_map(grid, self.C[l_out], self.d_n[l_out], N, ks, step, nbr, N, self.pairs[slot:slot + 1], mask)
+            h.row_order(mask, self.d_n[l_out], N, ks ** 3, perm, self.ro_scratch)
             self.map_id[nbr.data_ptr()] = slot
             self.perm_of[nbr.data_ptr()] = perm
 
@@ -212,6 +215,7 @@ class DenoiseEngine:
         self._perm_lookup = {}
         self.geom = Geometry(h, self.N, with_up=True)
         self._perm_lookup = self.geom.perm_of
+        self._mask_lookup = self.geom.mask_of
         self._pairs_lookup = _PairLookup(self.geom)
         self.geom_cond = None
         self.part_cap = 0
@@ -345,6 +349,8 @@ class DenoiseEngine:
         d.mout_cap, d.npass = cap, npass
         perm = self._perm_lookup.get(nbr.data_ptr()) if (nbr is not None and self.use_row_order) else None
         d.row_perm = perm.data_ptr() if perm is not None else None
+        mask = self._mask_lookup.get(nbr.data_ptr()) if nbr is not None else None
+        d.row_mask = mask.data_ptr() if mask is not None else None
         for p in range(npass):
             gt = gi = None
             if gate is not None:
@@ -455,6 +461,7 @@ class DenoiseEngine:
         if self.geom_cond is None or self.geom_cond.n_cap != N:
             self.geom_cond = Geometry(self.h, N, with_up=False, use_pairs=False)
             self._perm_lookup = ChainMap(self.geom.perm_of, self.geom_cond.perm_of)
+            self._mask_lookup = ChainMap(self.geom.mask_of, self.geom_cond.mask_of)
         coords = self.buf("cond.coords", (N, 4))
         coords[:, 0] = 0
         self.h.quantize(pts, self.resolution, self.div_mode, self.buf("cond.q", (N, 3)))

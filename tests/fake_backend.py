@@ -190,6 +190,11 @@ class FakeHandle:
         ctot = d.c1 + d.c2
         W = torch.from_numpy(_f(d.weight, (d.kvol, ctot, d.cout)).copy()).double()
         nbr = _i(d.nbr, (d.kvol, d.nbr_stride))[:, :M] if d.nbr else np.arange(M, dtype=np.int32)[None]
+        if d.row_mask and d.nbr:  # hint only: must agree with the map it describes
+            want = np.zeros(M, np.int64)
+            for k in range(d.kvol):
+                want |= (nbr[k] >= 0).astype(np.int64) << k
+            assert np.array_equal(_i(d.row_mask, (M,)).astype(np.int64) & 0xFFFFFFFF, want), "row_mask disagrees with nbr"
         rows_in = int(nbr.max()) + 1 if nbr.size else 0
         for p in range(d.npass):
             io = d.io[p]

@@ -458,7 +458,8 @@ def test_split_companion_inputs_give_identical_results(c1, c2, cout):
 
 
 @pytest.mark.parametrize("c1,c2,cout,lvl,kind", [(32, 0, 32, 0, "3"), (96, 32, 96, 1, "3"), (128, 0, 128, 2, "3"), (256, 128, 256, 3, "3"),
-                                                    (256, 0, 256, 3, "up"), (128, 0, 128, 4, "dn"), (384, 0, 256, 3, "1")])
+                                                    (256, 0, 256, 3, "up"), (128, 0, 128, 4, "dn"), (384, 0, 256, 3, "1"),
+                                                    (64, 0, 64, 2, "3"), (128, 64, 128, 2, "3"), (64, 0, 128, 3, "3"), (32, 0, 64, 2, "1")])
 def test_persistent_kernel_equals_per_tile_kernel(c1, c2, cout, lvl, kind):
     """LB2_ALGO_TC (persistent, cross-tile pipelined) and LB2_ALGO_TC_TILE (one CTA per tile) run the same math in the
     same order: identical results, with row order, two passes, fused epilogue and split outputs"""
@@ -504,6 +505,7 @@ def test_persistent_kernel_equals_per_tile_kernel(c1, c2, cout, lvl, kind):
         d.nbr = nbr.data_ptr() if nbr is not None else None
         d.nbr_stride, d.d_mout, d.mout_cap, d.npass = N, g.d_n[lvl].data_ptr(), N, 2
         d.row_perm = perm.data_ptr() if perm is not None else None
+        d.row_mask = g.mask_of[nbr.data_ptr()].data_ptr() if nbr is not None else None     # persistent kernels skip absent offsets' index loads
         for p_ in range(2):
             d.io[p_] = ConvIO(A[p_].data_ptr(), B[p_].data_ptr() if B is not None else None, R[p_].data_ptr(), out[p_].data_ptr(),
                               tab.data_ptr(), gi.data_ptr() if p_ == 0 else None, outg[p_].data_ptr(), None,
