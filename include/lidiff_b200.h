@@ -94,9 +94,10 @@ int lb2_kernel_map(void* h, void* stream, lb2_grid grid_in, const int32_t* out_c
                    int32_t* nbr, int64_t nbr_stride, uint64_t* pair_count, uint32_t* row_mask);
 
 /* Execution order of the output rows for lb2_spconv_forward (no reference counterpart: scheduling only).
- * perm[0..n) = the rows 0..n-1 grouped by the class of their neighbour mask so that 128-row tiles skip
- * unpopulated kernel offsets.  Results do not depend on the order.  scratch >= lb2_row_order_scratch_bytes(). */
-size_t lb2_row_order_scratch_bytes(void);
+ * perm[0..n) = the rows 0..n-1 sorted by their neighbour mask (kvol 27: centre-only rows, rows with one neighbour grouped
+ * by it, then the rest in mask order; kvol <= 8: by the 8-bit mask) so that 128-row tiles skip unpopulated kernel offsets.
+ * Results do not depend on the order.  scratch >= lb2_row_order_scratch_bytes(n_cap). */
+size_t lb2_row_order_scratch_bytes(int32_t n_cap);
 int lb2_row_order(void* h, void* stream, const uint32_t* row_mask, const int32_t* d_n, int32_t n_cap,
                   int32_t kvol, int32_t* perm, void* scratch);
 

@@ -101,6 +101,7 @@ class Lib:
         d.lb2_kernel_map.argtypes = [vp, vp, Grid, vp, vp, i32, i32, i32, vp, i64, vp, vp]
         d.lb2_row_order.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp]
         d.lb2_row_order_scratch_bytes.restype = C.c_size_t
+        d.lb2_row_order_scratch_bytes.argtypes = [i32]
         d.lb2_spconv_forward.argtypes = [vp, vp, C.POINTER(ConvDesc), C.c_int]
         d.lb2_pack_weights.argtypes = [vp, vp, vp, i32, i32, i32, vp]
         d.lb2_nn_match.argtypes = [vp, vp, vp, vp, i32, vp, vp, i32, i32, vp]
@@ -188,6 +189,9 @@ class Handle:
     def kernel_map(self, grid_in, out_coords, d_nout, nout_cap, ks, step, nbr, nbr_stride, pair_count=None, row_mask=None):
         self._check(self.dll.lb2_kernel_map(self.hp, self._stream(), self._grid(grid_in), _ptr(out_coords), _ptr(d_nout), int(nout_cap),
                                             int(ks), int(step), _ptr(nbr), int(nbr_stride), _ptr(pair_count), _ptr(row_mask)), "lb2_kernel_map")
+
+    def row_order_scratch_bytes(self, n_cap) -> int:
+        return int(self.dll.lb2_row_order_scratch_bytes(int(n_cap)))
 
     def row_order(self, row_mask, d_n, n_cap, kvol, perm, scratch):
         self._check(self.dll.lb2_row_order(self.hp, self._stream(), _ptr(row_mask), _ptr(d_n), int(n_cap), int(kvol), _ptr(perm), _ptr(scratch)),

@@ -345,19 +345,108 @@ extern "C" int lb2_kernel_map(void* handle, void* stream, lb2_grid grid_in, cons
 }
 
 // ---------------------------------------------------------------------------------------------------
-// row order: counting sort of the output rows by the class of their neighbour mask, so that the 128-row
-// tiles of the convolution kernels are (nearly) homogeneous in which kernel offsets are populated and
-// skip the rest.  kvol <= 8: bucket = the 8-bit mask itself; kvol == 27: 0 = centre only,
-// 1..27 = centre + exactly one other offset j, 28..54 = two or more others (bucketed by the lowest).
-// The order inside a bucket is irrelevant for the results (each output row is computed independently).
+// row order: sort of the output rows by their neighbour mask, so that the 128-row tiles of the convolution
+// kernels are (nearly) homogeneous in which kernel offsets are populated and skip the rest.
+//   kvol <= 8 : one counting-sort pass on the 8-bit mask itself.
+//   kvol == 27: stable LSD radix sort (3 passes of 9 bits) on the 27-bit key
+//                  [ 2 or more off-centre neighbours ? 1 : 0 | mask without the (always set) centre bit ]
+//               i.e. centre-only rows first, then the rows with exactly one neighbour grouped by it (tiles that need
+//               two offsets), then everything else in mask order.  Measured on the bench trajectory the issued
+//               (tile, offset) slots drop by 10-30 % on the levels with 3-14 neighbours per row against the
+//               previous 55-class bucketing (profiles/r01_row_order_waste.txt).
+// The order inside a group of equal keys is irrelevant for the results (each output row is computed independently).
 // ---------------------------------------------------------------------------------------------------
 #define RO_BINS 256
-__device__ __forceinline__ int ro_bucket(unsigned mask, int kvol) {
-    if (kvol <= 8) return (int)(mask & 0xffu);
+#define RS_BITS 9
+#define RS_BINS (1 << RS_BITS)
+#define RS_CHUNK 2048                       // rows per block and pass
+#define RS_WARPS 8                          // 256 consecutive rows per warp
+
+__device__ __forceinline__ unsigned ro_key27(unsigned mask) {
     const unsigned extras = mask & ~(1u << 13);
-    if (!extras) return 0;
-    const int j = __ffs(extras);            // 1..27
-    return (__popc(extras) == 1) ? j : 27 + j;
+    const unsigned k26 = ((mask >> 14) << 13) | (mask & 0x1fffu);
+    return ((__popc(extras) >= 2) ? (1u << 26) : 0u) | k26;
+}
+
+// pass 0 reads the masks (key computed on the fly, value = row index), later passes read the ping-pong buffers
+__device__ __forceinline__ unsigned rs_key(const unsigned* __restrict__ keys_in, const unsigned* __restrict__ mask, int i) {
+    return keys_in ? keys_in[i] : ro_key27(mask[i]);
+}
+
+__global__ void __launch_bounds__(256) k_rs_hist(const unsigned* __restrict__ keys_in, const unsigned* __restrict__ mask,
+                                                 const int* __restrict__ d_n, int n_cap, int shift, int nblk, int* __restrict__ hist) {
+    __shared__ int sh[RS_BINS];
+    for (int i = threadIdx.x; i < RS_BINS; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const int n = d_n ? min(*d_n, n_cap) : n_cap;
+    const int lo = blockIdx.x * RS_CHUNK, hi = min(lo + RS_CHUNK, n);
+    for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) atomicAdd(&sh[(rs_key(keys_in, mask, i) >> shift) & (RS_BINS - 1)], 1);
+    __syncthreads();
+    for (int i = threadIdx.x; i < RS_BINS; i += blockDim.x) hist[i * nblk + blockIdx.x] = sh[i];      // bin-major
+}
+
+// one block of RS_BINS threads: hist[bin][blk] -> global position of the first row of (bin, blk)
+__global__ void __launch_bounds__(RS_BINS) k_rs_scan(int* __restrict__ hist, int nblk) {
+    __shared__ int sh[RS_BINS];
+    const int t = threadIdx.x;
+    int run = 0;
+    for (int b = 0; b < nblk; ++b) { const int v = hist[t * nblk + b]; hist[t * nblk + b] = run; run += v; }
+    sh[t] = run;
+    __syncthreads();
+    for (int d = 1; d < RS_BINS; d <<= 1) {
+        const int u = (t >= d) ? sh[t - d] : 0;
+        __syncthreads();
+        sh[t] += u;
+        __syncthreads();
+    }
+    const int base = sh[t] - run;
+    for (int b = 0; b < nblk; ++b) hist[t * nblk + b] += base;
+}
+
+// stable scatter: warp w of block b owns rows [b*2048 + w*256, +256) and walks them in order, 32 at a time
+__global__ void __launch_bounds__(32 * RS_WARPS) k_rs_scatter(const unsigned* __restrict__ keys_in, const int* __restrict__ vals_in,
+                                                              const unsigned* __restrict__ mask, const int* __restrict__ d_n, int n_cap,
+                                                              int shift, int nblk, const int* __restrict__ hist,
+                                                              unsigned* __restrict__ keys_out, int* __restrict__ vals_out) {
+    __shared__ int cnt[RS_WARPS][RS_BINS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < RS_WARPS * RS_BINS; i += blockDim.x) (&cnt[0][0])[i] = 0;
+    __syncthreads();
+    const int n = d_n ? min(*d_n, n_cap) : n_cap;
+    const int w0 = blockIdx.x * RS_CHUNK + warp * (RS_CHUNK / RS_WARPS);
+    for (int g = 0; g < RS_CHUNK / RS_WARPS / 32; ++g) {                       // this warp's digit histogram
+        const int i = w0 + g * 32 + lane;
+        if (i < n) atomicAdd(&cnt[warp][(rs_key(keys_in, mask, i) >> shift) & (RS_BINS - 1)], 1);
+    }
+    __syncthreads();
+    for (int bin = threadIdx.x; bin < RS_BINS; bin += blockDim.x) {            // -> first position of (bin, warp)
+        int run = hist[bin * nblk + blockIdx.x];
+        for (int w = 0; w < RS_WARPS; ++w) { const int v = cnt[w][bin]; cnt[w][bin] = run; run += v; }
+    }
+    __syncthreads();
+    for (int g = 0; g < RS_CHUNK / RS_WARPS / 32; ++g) {
+        const int i = w0 + g * 32 + lane;
+        const bool ok = i < n;
+        const unsigned active = __ballot_sync(0xffffffffu, ok);
+        if (ok) {
+            const unsigned key = rs_key(keys_in, mask, i);
+            const int val = vals_in ? vals_in[i] : i;
+            const int d = (key >> shift) & (RS_BINS - 1);
+            const unsigned peers = __match_any_sync(active, d);
+            const int rank = __popc(peers & ((1u << lane) - 1u));
+            const int pos = cnt[warp][d] + rank;
+            __syncwarp(active);
+            if (rank == 0) cnt[warp][d] += __popc(peers);
+            __syncwarp(active);
+            if (keys_out) keys_out[pos] = key;
+            vals_out[pos] = val;
+        }
+    }
+}
+
+__device__ __forceinline__ int ro_bucket(unsigned mask, int kvol) {
+    (void)kvol;
+    return (int)(mask & 0xffu);
 }
 
 __global__ void k_ro_hist(const unsigned* __restrict__ mask, const int* __restrict__ d_n, int n_cap, int kvol, int* __restrict__ bins) {
@@ -401,13 +490,41 @@ __global__ void k_ro_scatter(const unsigned* __restrict__ mask, const int* __res
     if (i < n) perm[base[b] + local] = i;
 }
 
-extern "C" size_t lb2_row_order_scratch_bytes(void) { return RO_BINS * sizeof(int); }
+static int rs_blocks(int n_cap) { return cdiv(n_cap, RS_CHUNK); }
+
+// scratch layout: [RS_BINS * nblk] histogram, then keys A, keys B, vals A (n_cap each); kvol <= 8 uses the first RO_BINS ints only
+extern "C" size_t lb2_row_order_scratch_bytes(int32_t n_cap) {
+    return ((size_t)RS_BINS * rs_blocks(n_cap) + 3 * (size_t)n_cap) * sizeof(int);
+}
 
 extern "C" int lb2_row_order(void* handle, void* stream, const uint32_t* row_mask, const int32_t* d_n, int32_t n_cap,
                              int32_t kvol, int32_t* perm, void* scratch) {
     Lb2Handle* h = (Lb2Handle*)handle;
     LB2_REQUIRE(h, h && row_mask && perm && scratch && n_cap > 0 && (kvol == 27 || (kvol >= 1 && kvol <= 8)), "row_order");
     cudaStream_t s = (cudaStream_t)stream;
+    if (kvol == 27) {
+        const int nblk = rs_blocks(n_cap);
+        int* hist = (int*)scratch;
+        unsigned* keys_a = (unsigned*)(hist + (size_t)RS_BINS * nblk);
+        unsigned* keys_b = keys_a + n_cap;
+        int* vals_a = (int*)(keys_b + n_cap);
+        // pass 0: masks -> (keys_a, vals_a); pass 1: -> (keys_b, perm); pass 2: -> (none, vals_a)?  keep the final values in perm:
+        //   0: mask   -> keys_a, perm        1: keys_a, perm -> keys_b, vals_a        2: keys_b, vals_a -> perm
+        const unsigned* kin[3] = {nullptr, keys_a, keys_b};
+        const int* vin[3] = {nullptr, perm, vals_a};
+        unsigned* kout[3] = {keys_a, keys_b, nullptr};
+        int* vout[3] = {perm, vals_a, perm};
+        for (int pass = 0; pass < 3; ++pass) {
+            const int shift = pass * RS_BITS;
+            k_rs_hist<<<nblk, 256, 0, s>>>(kin[pass], row_mask, d_n, n_cap, shift, nblk, hist);
+            LB2_POST_LAUNCH(h, "k_rs_hist");
+            k_rs_scan<<<1, RS_BINS, 0, s>>>(hist, nblk);
+            LB2_POST_LAUNCH(h, "k_rs_scan");
+            k_rs_scatter<<<nblk, 32 * RS_WARPS, 0, s>>>(kin[pass], vin[pass], row_mask, d_n, n_cap, shift, nblk, hist, kout[pass], vout[pass]);
+            LB2_POST_LAUNCH(h, "k_rs_scatter");
+        }
+        return LB2_OK;
+    }
     int* bins = (int*)scratch;
     if (cudaMemsetAsync(bins, 0, RO_BINS * sizeof(int), s) != cudaSuccess) return lb2_fail(h, LB2_ERR_CUDA, "row_order memset%s", "");
     k_ro_hist<<<std::min<unsigned>(cdiv(n_cap, 256), 1024u), 256, 0, s>>>(row_mask, d_n, n_cap, kvol, bins);

@@ -219,8 +219,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_small(const Params p) 
         for (; arrived < it; ++arrived, ra.next()) mbar_arrive(full_a(ra.s));
     } else if (warp < 8) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
-        if (warp == 4 && lane == 0) {
-            // =========================== MMA issuer ===========================
+        if (warp == 4) {
+            // =========================== MMA issuer (whole warp converged; one elected lane issues) ===========================
             const uint32_t idesc = make_idesc(p.cout);
             int gcount = 0, j = 0;
             Ring rq{0, 0u, NA}, rb{0, 0u, NB};
@@ -249,25 +249,31 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_small(const Params p) 
                             tc_fence_after();
                             const uint32_t a_hi = base + (uint32_t)(sa >> 1) * a_stage, a_lo = a_hi + A_TILE;
                             const uint64_t dah0 = make_desc(a_hi) + 4u * (uint32_t)(sa & 1), dal0 = make_desc(a_lo) + 4u * (uint32_t)(sa & 1);
+                            if (elect_one()) {
 #pragma unroll
-                            for (int k2 = 0; k2 < 2; ++k2) {              // +32 bytes per K step = +2 in the descriptor's address field
-                                const uint32_t kb = 2u * (uint32_t)(half * 2 + k2);
-                                const uint64_t dah = dah0 + 2u * k2, dal = dal0 + 2u * k2, dbh = dbh0 + kb, dbl = dbl0 + kb;
-                                umma(tmem_acc, dah, dbh, idesc, (in_group | c | half | k2) ? 1u : 0u);
-                                umma(tmem_acc, dal, dbh, idesc, 1);
-                                umma(tmem_acc, dah, dbl, idesc, 1);
+                                for (int k2 = 0; k2 < 2; ++k2) {          // +32 bytes per K step = +2 in the descriptor's address field
+                                    const uint32_t kb = 2u * (uint32_t)(half * 2 + k2);
+                                    const uint64_t dah = dah0 + 2u * k2, dal = dal0 + 2u * k2, dbh = dbh0 + kb, dbl = dbl0 + kb;
+                                    umma(tmem_acc, dah, dbh, idesc, (in_group | c | half | k2) ? 1u : 0u);
+                                    umma(tmem_acc, dal, dbh, idesc, 1);
+                                    umma(tmem_acc, dah, dbl, idesc, 1);
+                                }
+                                umma_commit(empty_a(sa));
                             }
-                            umma_commit(empty_a(sa));
+                            __syncwarp();
                         }
-                        umma_commit(empty_b(sb));
+                        if (elect_one()) umma_commit(empty_b(sb));
+                        __syncwarp();
                     }
                     if (++in_group == p.group || off_idx == n_off - 1) {
-                        umma_commit(acc_full(buf));
+                        if (elect_one()) umma_commit(acc_full(buf));
+                        __syncwarp();
                         in_group = 0;
                         ++gcount;
                     }
                 }
-                mbar_arrive(meta_empty(b));
+                if (lane == 0) mbar_arrive(meta_empty(b));
+                __syncwarp();
             }
         } else if (warp == 5 && lane == 0) {
             // =========================== weight loader ===========================

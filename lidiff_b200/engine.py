@@ -117,14 +117,14 @@ class Geometry:
         self.map_id = {}
         # execution order of the output rows of each map (rows bucketed by neighbour mask, lb2_row_order)
         self.mask_of = {}                                    # map -> its per-row neighbour bit mask (conv kernels skip absent offsets)
-        self.ro_scratch = torch.zeros(256, **i32)            # lb2_row_order_scratch_bytes() = 1 KB
+        self.ro_scratch = torch.zeros((h.row_order_scratch_bytes(n_cap) + 3) // 4, **i32)
         self.perm3 = [torch.zeros(n_cap, **i32) for _ in range(levels)]
         self.perm_dn = [None] + [torch.zeros(n_cap, **i32) for _ in range(levels - 1)]
         self.perm_up = [torch.zeros(n_cap, **i32) for _ in range(levels - 1)] + [None] if with_up else None
         self.perm_of = {}
         # per-offset (in,out) pair lists of the 3^3 maps of the sparse levels (gather-GEMM-scatter form)
         self.pair_levels = min(3, levels)
-        self.pair_level_set = set(int(c) for c in os.environ.get("LB2_SCATTER_LEVELS", "2") if c.isdigit())
+        self.pair_level_set = set(int(c) for c in os.environ.get("LB2_SCATTER_LEVELS", "") if c.isdigit())
         self.pairs_of = {}
         self.pl_scratch = torch.zeros(64, **i32)
         self.pair_in = [torch.zeros(26 * n_cap, **i32) for _ in range(self.pair_levels)]

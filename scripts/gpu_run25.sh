@@ -1,0 +1,10 @@
+#!/usr/bin/env bash
+# radix-sorted row order, elected-lane MMA issue, scatter off by default
+mkdir -p gpurun_out
+timeout 300 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -s -p no:cacheprovider -k "row_order or persistent or fused or split or conv" > gpurun_out/pytest_gate.log 2>&1
+rc=$?; echo "gate exit $rc" >> gpurun_out/pytest_gate.log; grep -E "passed|failed|Error|exit" gpurun_out/pytest_gate.log | tail -5
+if [ $rc -ne 0 ]; then tail -40 gpurun_out/pytest_gate.log; exit 1; fi
+LB2_PROFILE_WASTE=1 timeout 200 python scripts/profile_layers.py 0 25 49 > gpurun_out/profile_layers_r25.log 2>&1
+grep -E "===|conv total|waste" gpurun_out/profile_layers_r25.log
+timeout 300 python bench.py --steps 50 --warmup 3 --no-cpu-baseline > gpurun_out/bench_r25.json 2> gpurun_out/bench_r25.err; echo "bench exit $?"
+cut -c1-200 gpurun_out/bench_r25.json

@@ -113,19 +113,19 @@ class FakeHandle:
                     row_mask[:nout_cap] = 0
                 row_mask[:n] |= torch.from_numpy((hit.astype(np.int64) << k).astype(np.int32))
 
+    def row_order_scratch_bytes(self, n_cap):
+        return 1024
+
     def row_order(self, row_mask, d_n, n_cap, kvol, perm, scratch):
-        self.launches += 3
+        self.launches += 3 if kvol <= 8 else 9
         n = self._n(d_n, n_cap)
         m = row_mask[:n].long() & 0xFFFFFFFF
         if kvol <= 8:
             b = m & 0xFF
-        else:
+        else:                                        # [>= 2 off-centre neighbours | mask without the centre bit]
             extras = m & ~(1 << 13)
-            low = torch.zeros_like(m)
-            for j in range(27):                      # index (1-based) of the lowest set bit
-                low = torch.where((low == 0) & (((extras >> j) & 1) == 1), torch.full_like(m, j + 1), low)
             pop = sum(((extras >> j) & 1) for j in range(27))
-            b = torch.where(extras == 0, torch.zeros_like(m), torch.where(pop == 1, low, 27 + low))
+            b = ((pop >= 2).long() << 26) | ((m >> 14) << 13) | (m & 0x1FFF)
         order = torch.argsort(b, stable=True)
         perm[:n] = torch.flip(order, [0]).int() if n > 3 else order.int()     # any in-bucket order is legal; scramble a bit
         perm[:n] = order.int()

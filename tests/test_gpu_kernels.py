@@ -295,6 +295,10 @@ def test_row_order_is_a_permutation_and_does_not_change_results(spread, algo):
         else:
             centre_only = mask[p] == (1 << 13)
             assert centre_only[: centre_only.sum()].all(), "centre-only rows first"
+            ms = mask[p].astype(np.int64)
+            extras = ms & ~(1 << 13)
+            key = ((np.array([bin(int(v)).count("1") for v in extras]) >= 2).astype(np.int64) << 26) | ((ms >> 14) << 13) | (ms & 0x1FFF)
+            assert (np.diff(key) >= 0).all(), "27-bit masks must come out sorted by [>=2 neighbours | mask]"
         cin, cout = 32, 64
         W = (torch.randn(kvol, cin, cout, generator=gen) * 0.1).to(DEV)
         x = torch.randn(N, cin, generator=gen).to(DEV)
