@@ -374,7 +374,8 @@ __device__ __forceinline__ unsigned rs_key(const unsigned* __restrict__ keys_in,
 }
 
 __global__ void __launch_bounds__(256) k_rs_hist(const unsigned* __restrict__ keys_in, const unsigned* __restrict__ mask,
-                                                 const int* __restrict__ d_n, int n_cap, int shift, int nblk, int* __restrict__ hist) {
+                                                 const int* __restrict__ d_n, int n_cap, int shift, int* __restrict__ hist,
+                                                 int* __restrict__ total) {
     __shared__ int sh[RS_BINS];
     for (int i = threadIdx.x; i < RS_BINS; i += blockDim.x) sh[i] = 0;
     __syncthreads();
@@ -382,35 +383,43 @@ __global__ void __launch_bounds__(256) k_rs_hist(const unsigned* __restrict__ ke
     const int lo = blockIdx.x * RS_CHUNK, hi = min(lo + RS_CHUNK, n);
     for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) atomicAdd(&sh[(rs_key(keys_in, mask, i) >> shift) & (RS_BINS - 1)], 1);
     __syncthreads();
-    for (int i = threadIdx.x; i < RS_BINS; i += blockDim.x) hist[i * nblk + blockIdx.x] = sh[i];      // bin-major
-}
-
-// one block of RS_BINS threads: hist[bin][blk] -> global position of the first row of (bin, blk)
-__global__ void __launch_bounds__(RS_BINS) k_rs_scan(int* __restrict__ hist, int nblk) {
-    __shared__ int sh[RS_BINS];
-    const int t = threadIdx.x;
-    int run = 0;
-    for (int b = 0; b < nblk; ++b) { const int v = hist[t * nblk + b]; hist[t * nblk + b] = run; run += v; }
-    sh[t] = run;
-    __syncthreads();
-    for (int d = 1; d < RS_BINS; d <<= 1) {
-        const int u = (t >= d) ? sh[t - d] : 0;
-        __syncthreads();
-        sh[t] += u;
-        __syncthreads();
+    for (int i = threadIdx.x; i < RS_BINS; i += blockDim.x) {
+        hist[blockIdx.x * RS_BINS + i] = sh[i];                                                        // block-major: coalesced both ways
+        if (sh[i]) atomicAdd(total + i, sh[i]);
     }
-    const int base = sh[t] - run;
-    for (int b = 0; b < nblk; ++b) hist[t * nblk + b] += base;
 }
 
 // stable scatter: warp w of block b owns rows [b*2048 + w*256, +256) and walks them in order, 32 at a time
 __global__ void __launch_bounds__(32 * RS_WARPS) k_rs_scatter(const unsigned* __restrict__ keys_in, const int* __restrict__ vals_in,
                                                               const unsigned* __restrict__ mask, const int* __restrict__ d_n, int n_cap,
-                                                              int shift, int nblk, const int* __restrict__ hist,
+                                                              int shift, const int* __restrict__ hist, const int* __restrict__ total,
                                                               unsigned* __restrict__ keys_out, int* __restrict__ vals_out) {
     __shared__ int cnt[RS_WARPS][RS_BINS];
+    __shared__ int first[RS_BINS];                 // global position of the first row of (bin, this block)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < RS_WARPS * RS_BINS; i += blockDim.x) (&cnt[0][0])[i] = 0;
+    {   // exclusive scan of the bin totals (2 bins per thread) + the rows of the same bin in the blocks before this one
+        const int t = threadIdx.x;
+        const int t0 = total[2 * t], t1 = total[2 * t + 1];
+        first[t] = t0 + t1;                        // pair sums, scanned in place over the first 256 entries
+        __syncthreads();
+        for (int d = 1; d < RS_BINS / 2; d <<= 1) {
+            const int u = (t >= d) ? first[t - d] : 0;
+            __syncthreads();
+            first[t] += u;
+            __syncthreads();
+        }
+        const int excl = first[t] - (t0 + t1);
+        int p0 = 0, p1 = 0;
+#pragma unroll 8
+        for (int b = 0; b < (int)blockIdx.x; ++b) {
+            const int2 v = *reinterpret_cast<const int2*>(hist + b * RS_BINS + 2 * t);
+            p0 += v.x; p1 += v.y;
+        }
+        __syncthreads();
+        first[2 * t] = excl + p0;
+        first[2 * t + 1] = excl + t0 + p1;
+    }
     __syncthreads();
     const int n = d_n ? min(*d_n, n_cap) : n_cap;
     const int w0 = blockIdx.x * RS_CHUNK + warp * (RS_CHUNK / RS_WARPS);
@@ -420,7 +429,7 @@ __global__ void __launch_bounds__(32 * RS_WARPS) k_rs_scatter(const unsigned* __
     }
     __syncthreads();
     for (int bin = threadIdx.x; bin < RS_BINS; bin += blockDim.x) {            // -> first position of (bin, warp)
-        int run = hist[bin * nblk + blockIdx.x];
+        int run = first[bin];
         for (int w = 0; w < RS_WARPS; ++w) { const int v = cnt[w][bin]; cnt[w][bin] = run; run += v; }
     }
     __syncthreads();
@@ -492,9 +501,10 @@ __global__ void k_ro_scatter(const unsigned* __restrict__ mask, const int* __res
 
 static int rs_blocks(int n_cap) { return cdiv(n_cap, RS_CHUNK); }
 
-// scratch layout: [RS_BINS * nblk] histogram, then keys A, keys B, vals A (n_cap each); kvol <= 8 uses the first RO_BINS ints only
+// scratch layout: [nblk][RS_BINS] histogram, [3][RS_BINS] per-pass bin totals, then keys A, keys B, vals A (n_cap each);
+// kvol <= 8 uses the first RO_BINS ints only
 extern "C" size_t lb2_row_order_scratch_bytes(int32_t n_cap) {
-    return ((size_t)RS_BINS * rs_blocks(n_cap) + 3 * (size_t)n_cap) * sizeof(int);
+    return ((size_t)RS_BINS * (rs_blocks(n_cap) + 3) + 3 * (size_t)n_cap) * sizeof(int);
 }
 
 extern "C" int lb2_row_order(void* handle, void* stream, const uint32_t* row_mask, const int32_t* d_n, int32_t n_cap,
@@ -505,7 +515,9 @@ extern "C" int lb2_row_order(void* handle, void* stream, const uint32_t* row_mas
     if (kvol == 27) {
         const int nblk = rs_blocks(n_cap);
         int* hist = (int*)scratch;
-        unsigned* keys_a = (unsigned*)(hist + (size_t)RS_BINS * nblk);
+        int* total = hist + (size_t)RS_BINS * nblk;
+        unsigned* keys_a = (unsigned*)(total + 3 * RS_BINS);
+        if (cudaMemsetAsync(total, 0, 3 * RS_BINS * sizeof(int), s) != cudaSuccess) return lb2_fail(h, LB2_ERR_CUDA, "row_order memset%s", "");
         unsigned* keys_b = keys_a + n_cap;
         int* vals_a = (int*)(keys_b + n_cap);
         // pass 0: masks -> (keys_a, vals_a); pass 1: -> (keys_b, perm); pass 2: -> (none, vals_a)?  keep the final values in perm:
@@ -516,11 +528,10 @@ extern "C" int lb2_row_order(void* handle, void* stream, const uint32_t* row_mas
         int* vout[3] = {perm, vals_a, perm};
         for (int pass = 0; pass < 3; ++pass) {
             const int shift = pass * RS_BITS;
-            k_rs_hist<<<nblk, 256, 0, s>>>(kin[pass], row_mask, d_n, n_cap, shift, nblk, hist);
+            k_rs_hist<<<nblk, 256, 0, s>>>(kin[pass], row_mask, d_n, n_cap, shift, hist, total + pass * RS_BINS);
             LB2_POST_LAUNCH(h, "k_rs_hist");
-            k_rs_scan<<<1, RS_BINS, 0, s>>>(hist, nblk);
-            LB2_POST_LAUNCH(h, "k_rs_scan");
-            k_rs_scatter<<<nblk, 32 * RS_WARPS, 0, s>>>(kin[pass], vin[pass], row_mask, d_n, n_cap, shift, nblk, hist, kout[pass], vout[pass]);
+            k_rs_scatter<<<nblk, 32 * RS_WARPS, 0, s>>>(kin[pass], vin[pass], row_mask, d_n, n_cap, shift, hist, total + pass * RS_BINS,
+                                                        kout[pass], vout[pass]);
             LB2_POST_LAUNCH(h, "k_rs_scatter");
         }
         return LB2_OK;

@@ -117,7 +117,7 @@ class FakeHandle:
         return 1024
 
     def row_order(self, row_mask, d_n, n_cap, kvol, perm, scratch):
-        self.launches += 3 if kvol <= 8 else 9
+        self.launches += 3 if kvol <= 8 else 6
         n = self._n(d_n, n_cap)
         m = row_mask[:n].long() & 0xFFFFFFFF
         if kvol <= 8:
