@@ -208,6 +208,18 @@ int lb2_nn_match_table(void* h, void* stream, const int32_t* q_coords, const int
                        const int32_t* k_coords, const int32_t* d_nk, int32_t nk_cap, const void* table,
                        int32_t key_stride, int32_t max_ring, int32_t* idx);
 
+/* Variant for keys that stay fixed over many calls (the conditioning scan): lb2_nn_tree_build sorts them along a
+ * Morton curve and builds a bounding-box hierarchy once (`tree`: lb2_nn_tree_bytes(nk_cap) bytes); lb2_nn_match_tree
+ * searches it exactly (same result as lb2_nn_match with batch_scale = 0, incl. lowest-row ties) in ~log(nk) box
+ * tests per query, independent of how far the query is from the keys.  Optional hint: hint_idx[hint_of ? hint_of[q] : q]
+ * names a key row that is probably close to query q (e.g. the answer of the coarser voxel containing it; needs
+ * k_coords): the search starts from that key's distance as its bound; the result does not depend on the hint. */
+size_t lb2_nn_tree_bytes(int32_t nk_cap);
+int lb2_nn_tree_build(void* h, void* stream, const int32_t* k_coords, const int32_t* d_nk, int32_t nk_cap, void* tree);
+int lb2_nn_match_tree(void* h, void* stream, const int32_t* q_coords, const int32_t* d_nq, int32_t nq_cap,
+                      const void* tree, int32_t nk_cap, const int32_t* k_coords, const int32_t* hint_of,
+                      const int32_t* hint_idx, int32_t* idx);
+
 /* ---- small dense layers — torch.nn.Linear (+LeakyReLU) of the gate / head MLPs
  * (minkunet.py:165-181,376-380): y = act(x @ W^T + b [+ addend]); W is (n_out, n_in) torch layout.
  * act: 0 none, 1 LeakyReLU(0.1), 2 tanh.  rows read from d_m if non-NULL.

@@ -60,6 +60,7 @@ EXPORTS = [
     "lb2_gate_mul", "lb2_gather_rows", "lb2_guidance_dpm_step", "lb2_farthest_point_sample",
     "lb2_row_order", "lb2_row_order_scratch_bytes", "lb2_nn_match_grid",
     "lb2_nn_table_bytes", "lb2_nn_table_build", "lb2_nn_match_table",
+    "lb2_nn_tree_bytes", "lb2_nn_tree_build", "lb2_nn_match_tree",
     "lb2_pair_list", "lb2_pair_list_scratch_bytes", "lb2_spconv_scatter", "lb2_spconv_scatter_supported",
 ]
 
@@ -110,6 +111,10 @@ class Lib:
         d.lb2_spconv_scatter.argtypes = [vp, vp, C.POINTER(ScatterDesc)]
         d.lb2_spconv_scatter_supported.argtypes = [i32, i32, i32, i32]
         d.lb2_nn_table_bytes.restype = C.c_size_t
+        d.lb2_nn_tree_bytes.restype = C.c_size_t
+        d.lb2_nn_tree_bytes.argtypes = [i32]
+        d.lb2_nn_tree_build.argtypes = [vp, vp, vp, vp, i32, vp]
+        d.lb2_nn_match_tree.argtypes = [vp, vp, vp, vp, i32, vp, i32, vp, vp, vp, vp]
         d.lb2_nn_table_build.argtypes = [vp, vp, vp, vp, i32, vp]
         d.lb2_nn_match_table.argtypes = [vp, vp, vp, vp, i32, vp, vp, i32, vp, i32, i32, vp]
         d.lb2_nn_match_grid.argtypes = [vp, vp, vp, vp, i32, vp, vp, i32, Grid, i32, i32, vp]
@@ -237,6 +242,16 @@ class Handle:
         t = torch.empty(int(self.dll.lb2_nn_table_bytes()), dtype=torch.uint8, device=self.device)
         self._check(self.dll.lb2_nn_table_build(self.hp, self._stream(), _ptr(k), _ptr(d_nk), int(nk_cap), _ptr(t)), "lb2_nn_table_build")
         return t
+
+    def nn_tree(self, k, d_nk, nk_cap):
+        """bounding-box hierarchy over the key voxels for nn_match_tree (one per conditioning scan)"""
+        t = torch.empty(int(self.dll.lb2_nn_tree_bytes(int(nk_cap))), dtype=torch.uint8, device=self.device)
+        self._check(self.dll.lb2_nn_tree_build(self.hp, self._stream(), _ptr(k), _ptr(d_nk), int(nk_cap), _ptr(t)), "lb2_nn_tree_build")
+        return t
+
+    def nn_match_tree(self, q, d_nq, nq_cap, tree, nk_cap, idx, k=None, hint_of=None, hint_idx=None):
+        self._check(self.dll.lb2_nn_match_tree(self.hp, self._stream(), _ptr(q), _ptr(d_nq), int(nq_cap), _ptr(tree), int(nk_cap),
+                                               _ptr(k), _ptr(hint_of), _ptr(hint_idx), _ptr(idx)), "lb2_nn_match_tree")
 
     def nn_match_table(self, q, d_nq, nq_cap, k, d_nk, nk_cap, table, key_stride, max_ring, idx):
         self._check(self.dll.lb2_nn_match_table(self.hp, self._stream(), _ptr(q), _ptr(d_nq), int(nq_cap), _ptr(k), _ptr(d_nk), int(nk_cap),

@@ -546,3 +546,158 @@ extern "C" int lb2_row_order(void* handle, void* stream, const uint32_t* row_mas
     LB2_POST_LAUNCH(h, "k_ro_scatter");
     return LB2_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// nn tree: a bounding-volume hierarchy over the Morton-sorted keys of lb2_nn_match (built once per scan, the keys
+// are the conditioning scan's stride-16 voxels).  Complete binary tree in heap order over leaves of NT_LEAF
+// consecutive sorted keys; every node holds the integer bounding box (and batch range) of its keys.  The exact
+// search of k_nn_match_tree (dense.cu) prunes with box distances, so its cost is ~O(log nk) per query however far the
+// query is from the keys (the shell search of lb2_nn_match_grid grows with the cube of that distance).
+// Buffer layout (ints): [0..15] header {min x,y,z; max x,y,z; shift; nleaf; nk_cap} | nodes [2*nleaf][8] |
+// sorted keys int4[nleaf*NT_LEAF] (x, y, z, original row; -1 past the last key) | batch[nleaf*NT_LEAF] | sort scratch.
+// ---------------------------------------------------------------------------------------------------
+#define NT_LEAF 4
+#define NT_HDR 16
+
+static int nt_nleaf(int nk_cap) { int n = 1; while (n * NT_LEAF < nk_cap) n <<= 1; return n; }
+static size_t nt_sort_ints(int nk_cap) { return (size_t)RS_BINS * (rs_blocks(nk_cap) + 3) + 4 * (size_t)nk_cap; }
+
+extern "C" size_t lb2_nn_tree_bytes(int32_t nk_cap) {
+    return (NT_HDR + (size_t)2 * nt_nleaf(nk_cap) * 8 + 5 * (size_t)nt_nleaf(nk_cap) * NT_LEAF + nt_sort_ints(nk_cap)) * sizeof(int) + 64;
+}
+
+__global__ void k_nt_init(int* __restrict__ hdr, int nleaf, int nk_cap) {
+    if (threadIdx.x < 3) { hdr[threadIdx.x] = 0x7fffffff; hdr[3 + threadIdx.x] = (int)0x80000000; }
+    if (threadIdx.x == 0) { hdr[6] = 0; hdr[7] = nleaf; hdr[8] = nk_cap; }
+}
+
+__global__ void k_nt_minmax(const int4* __restrict__ keys, const int* __restrict__ d_nk, int nk_cap, int* __restrict__ hdr) {
+    const int nk = d_nk ? min(*d_nk, nk_cap) : nk_cap;
+    int lo[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, hi[3] = {(int)0x80000000, (int)0x80000000, (int)0x80000000};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nk; i += gridDim.x * blockDim.x) {
+        const int4 c = __ldg(keys + i);
+        lo[0] = min(lo[0], c.y); lo[1] = min(lo[1], c.z); lo[2] = min(lo[2], c.w);
+        hi[0] = max(hi[0], c.y); hi[1] = max(hi[1], c.z); hi[2] = max(hi[2], c.w);
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { lo[a] = min(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o)); hi[a] = max(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o)); }
+        if ((threadIdx.x & 31) == 0) { atomicMin(hdr + a, lo[a]); atomicMax(hdr + 3 + a, hi[a]); }
+    }
+}
+
+__device__ __forceinline__ unsigned nt_spread9(unsigned v) {        // 9 bits -> every third bit
+    unsigned r = 0;
+#pragma unroll
+    for (int b = 0; b < 9; ++b) r |= ((v >> b) & 1u) << (3 * b);
+    return r;
+}
+
+__global__ void k_nt_morton(const int4* __restrict__ keys, const int* __restrict__ d_nk, int nk_cap, const int* __restrict__ hdr,
+                            unsigned* __restrict__ codes) {
+    const int nk = d_nk ? min(*d_nk, nk_cap) : nk_cap;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nk) return;
+    long long ext = 0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) ext = max(ext, (long long)hdr[3 + a] - (long long)hdr[a]);
+    int shift = 0;
+    while ((ext >> shift) > 511) ++shift;                             // 9 bits per axis after the shift
+    const int4 c = __ldg(keys + i);
+    const unsigned x = (unsigned)(((long long)c.y - hdr[0]) >> shift), y = (unsigned)(((long long)c.z - hdr[1]) >> shift),
+                   z = (unsigned)(((long long)c.w - hdr[2]) >> shift);
+    codes[i] = nt_spread9(x) | (nt_spread9(y) << 1) | (nt_spread9(z) << 2);
+}
+
+__global__ void k_nt_gather(const int4* __restrict__ keys, const int* __restrict__ d_nk, int nk_cap, const int* __restrict__ order,
+                            int slots, int4* __restrict__ skeys, int* __restrict__ sbatch) {
+    const int nk = d_nk ? min(*d_nk, nk_cap) : nk_cap;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= slots) return;
+    if (i >= nk) { skeys[i] = make_int4(0, 0, 0, -1); sbatch[i] = 0; return; }
+    const int j = order[i];
+    const int4 c = __ldg(keys + j);
+    skeys[i] = make_int4(c.y, c.z, c.w, j);
+    sbatch[i] = c.x;
+}
+
+// node = {lo x,y,z, hi x,y,z, batch lo, batch hi}; an empty node has lo > hi
+__global__ void k_nt_leaves(const int4* __restrict__ skeys, const int* __restrict__ sbatch, const int* __restrict__ d_nk, int nk_cap,
+                            int nleaf, int* __restrict__ nodes) {
+    const int nk = d_nk ? min(*d_nk, nk_cap) : nk_cap;
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= nleaf) return;
+    int v[8] = {0x7fffffff, 0x7fffffff, 0x7fffffff, (int)0x80000000, (int)0x80000000, (int)0x80000000, 0x7fffffff, (int)0x80000000};
+    for (int t = 0; t < NT_LEAF; ++t) {
+        const int i = l * NT_LEAF + t;
+        if (i >= nk) break;
+        const int4 c = skeys[i];
+        const int b = sbatch[i];
+        v[0] = min(v[0], c.x); v[1] = min(v[1], c.y); v[2] = min(v[2], c.z);
+        v[3] = max(v[3], c.x); v[4] = max(v[4], c.y); v[5] = max(v[5], c.z);
+        v[6] = min(v[6], b); v[7] = max(v[7], b);
+    }
+    int* n = nodes + (size_t)(nleaf + l) * 8;
+#pragma unroll
+    for (int a = 0; a < 8; ++a) n[a] = v[a];
+}
+
+__global__ void __launch_bounds__(1024) k_nt_internal(int nleaf, int* __restrict__ nodes) {       // one block, level by level bottom-up
+    for (int first = nleaf >> 1; first >= 1; first >>= 1) {
+        for (int i = first + threadIdx.x; i < 2 * first; i += blockDim.x) {
+            const int* a = nodes + (size_t)(2 * i) * 8;
+            const int* b = a + 8;
+            int* n = nodes + (size_t)i * 8;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { n[c] = min(a[c], b[c]); n[3 + c] = max(a[3 + c], b[3 + c]); }
+            n[6] = min(a[6], b[6]); n[7] = max(a[7], b[7]);
+        }
+        __syncthreads();
+    }
+}
+
+extern "C" int lb2_nn_tree_build(void* handle, void* stream, const int32_t* k_coords, const int32_t* d_nk, int32_t nk_cap, void* tree) {
+    Lb2Handle* h = (Lb2Handle*)handle;
+    LB2_REQUIRE(h, h && k_coords && tree && nk_cap > 0, "nn_tree_build");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int nleaf = nt_nleaf(nk_cap);
+    int* hdr = (int*)tree;
+    int* nodes = hdr + NT_HDR;
+    int4* skeys = (int4*)(nodes + (size_t)2 * nleaf * 8);
+    const int slots = nleaf * NT_LEAF;
+    int* sbatch = (int*)(skeys + slots);
+    int* hist = sbatch + slots;
+    const int nblk = rs_blocks(nk_cap);
+    int* total = hist + (size_t)RS_BINS * nblk;
+    unsigned* codes = (unsigned*)(total + 3 * RS_BINS);
+    unsigned* keys_b = codes + nk_cap;
+    int* vals_a = (int*)(keys_b + nk_cap);
+    int* vals_b = vals_a + nk_cap;
+    k_nt_init<<<1, 32, 0, s>>>(hdr, nleaf, nk_cap);
+    LB2_POST_LAUNCH(h, "k_nt_init");
+    k_nt_minmax<<<std::min<unsigned>(cdiv(nk_cap, 256), 256u), 256, 0, s>>>((const int4*)k_coords, d_nk, nk_cap, hdr);
+    LB2_POST_LAUNCH(h, "k_nt_minmax");
+    k_nt_morton<<<cdiv(nk_cap, 256), 256, 0, s>>>((const int4*)k_coords, d_nk, nk_cap, hdr, codes);
+    LB2_POST_LAUNCH(h, "k_nt_morton");
+    if (cudaMemsetAsync(total, 0, 3 * RS_BINS * sizeof(int), s) != cudaSuccess) return lb2_fail(h, LB2_ERR_CUDA, "nn_tree memset%s", "");
+    //   0: codes -> keys_b, vals_a        1: keys_b, vals_a -> codes, vals_b        2: codes, vals_b -> vals_a
+    const unsigned* kin[3] = {codes, keys_b, codes};
+    const int* vin[3] = {nullptr, vals_a, vals_b};
+    unsigned* kout[3] = {keys_b, codes, nullptr};
+    int* vout[3] = {vals_a, vals_b, vals_a};
+    for (int pass = 0; pass < 3; ++pass) {
+        k_rs_hist<<<nblk, 256, 0, s>>>(kin[pass], nullptr, d_nk, nk_cap, pass * RS_BITS, hist, total + pass * RS_BINS);
+        LB2_POST_LAUNCH(h, "k_rs_hist");
+        k_rs_scatter<<<nblk, 32 * RS_WARPS, 0, s>>>(kin[pass], vin[pass], nullptr, d_nk, nk_cap, pass * RS_BITS, hist, total + pass * RS_BINS,
+                                                    kout[pass], vout[pass]);
+        LB2_POST_LAUNCH(h, "k_rs_scatter");
+    }
+    k_nt_gather<<<cdiv(slots, 256), 256, 0, s>>>((const int4*)k_coords, d_nk, nk_cap, vals_a, slots, skeys, sbatch);
+    LB2_POST_LAUNCH(h, "k_nt_gather");
+    k_nt_leaves<<<cdiv(nleaf, 256), 256, 0, s>>>(skeys, sbatch, d_nk, nk_cap, nleaf, nodes);
+    LB2_POST_LAUNCH(h, "k_nt_leaves");
+    k_nt_internal<<<1, 1024, 0, s>>>(nleaf, nodes);
+    LB2_POST_LAUNCH(h, "k_nt_internal");
+    return LB2_OK;
+}

@@ -146,6 +146,91 @@ extern "C" int lb2_nn_match_grid(void* handle, void* stream, const int32_t* q_co
 }
 
 // ---------------------------------------------------------------------------------------------------
+// nn_match on the bounding-volume hierarchy of lb2_nn_tree_build (coords.cu): depth-first search with the nearer
+// child first, a subtree is skipped when its box is strictly farther than the best key so far ('<=' keeps equal
+// distances: the lowest original row must win ties, exactly as in the exhaustive kernel).
+// ---------------------------------------------------------------------------------------------------
+#define NT_LEAF 4
+#define NT_HDR 16
+#define NT_STACK 48
+
+__device__ __forceinline__ unsigned long long nt_box_dist(const int* __restrict__ n, const int4 c) {
+    if (n[0] > n[3]) return ~0ull;                                   // empty node
+    const long long dx = max(max((long long)n[0] - c.y, (long long)c.y - n[3]), 0ll);
+    const long long dy = max(max((long long)n[1] - c.z, (long long)c.z - n[4]), 0ll);
+    const long long dz = max(max((long long)n[2] - c.w, (long long)c.w - n[5]), 0ll);
+    unsigned long long d = (unsigned long long)(dx * dx + dy * dy + dz * dz);
+    if (c.x < n[6] || c.x > n[7]) d += 1ull << 62;                   // no key of the query's batch in this subtree
+    return d;
+}
+
+__global__ void __launch_bounds__(128) k_nn_match_tree(const int4* __restrict__ q, const int* __restrict__ d_nq, int nq_cap,
+                                                       const int* __restrict__ tree, int nk_cap, const int4* __restrict__ keys,
+                                                       const int* __restrict__ hint_of, const int* __restrict__ hint_idx,
+                                                       int* __restrict__ idx) {
+    const int nq = d_nq ? min(*d_nq, nq_cap) : nq_cap;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    const int nleaf = tree[7];
+    const int* nodes = tree + NT_HDR;
+    const int4* skeys = reinterpret_cast<const int4*>(nodes + (size_t)2 * nleaf * 8);
+    const int* sbatch = reinterpret_cast<const int*>(skeys + (size_t)nleaf * NT_LEAF);
+    const int4 c = __ldg(q + i);
+    unsigned long long best = ~0ull;
+    int best_j = 0x7fffffff;
+    if (hint_idx) {                                                  // start from a key that is probably close (a coarser voxel's answer):
+        const int j = __ldg(hint_idx + (hint_of ? __ldg(hint_of + i) : i));    // any key is a valid upper bound, so the result is unchanged
+        const int4 kc = __ldg(keys + j);
+        const long long ex = (long long)c.y - kc.y, ey = (long long)c.z - kc.z, ez = (long long)c.w - kc.w;
+        best = (unsigned long long)(ex * ex + ey * ey + ez * ez);
+        if (kc.x != c.x) best += 1ull << 62;
+        best_j = j;
+    }
+    int st_node[NT_STACK];
+    unsigned long long st_lb[NT_STACK];
+    int sp = 0;
+    st_node[0] = 1; st_lb[0] = nt_box_dist(nodes + 8, c); sp = 1;
+    while (sp > 0) {
+        --sp;
+        const int node = st_node[sp];
+        const unsigned long long lb = st_lb[sp];
+        if (lb == ~0ull || lb > best) continue;
+        if (node >= nleaf) {
+            const int k0 = (node - nleaf) * NT_LEAF;
+#pragma unroll
+            for (int t = 0; t < NT_LEAF; ++t) {
+                const int4 kc = __ldg(skeys + k0 + t);
+                const int kb = __ldg(sbatch + k0 + t);
+                const long long ex = (long long)c.y - kc.x, ey = (long long)c.z - kc.y, ez = (long long)c.w - kc.z;
+                unsigned long long d = (unsigned long long)(ex * ex + ey * ey + ez * ez);
+                if (kb != c.x) d += 1ull << 62;
+                const bool valid = kc.w >= 0;                          // slots past the last key hold row -1
+                if (valid && (d < best || (d == best && kc.w < best_j))) { best = d; best_j = kc.w; }
+            }
+        } else {
+            const unsigned long long l0 = nt_box_dist(nodes + (size_t)(2 * node) * 8, c), l1 = nt_box_dist(nodes + (size_t)(2 * node + 1) * 8, c);
+            const bool first0 = l0 <= l1;                              // visit the nearer child first: push it last
+            const int nf = first0 ? 2 * node + 1 : 2 * node, nn_ = first0 ? 2 * node : 2 * node + 1;
+            const unsigned long long lf = first0 ? l1 : l0, ln = first0 ? l0 : l1;
+            if (lf != ~0ull && lf <= best && sp < NT_STACK) { st_node[sp] = nf; st_lb[sp] = lf; ++sp; }
+            if (ln != ~0ull && ln <= best && sp < NT_STACK) { st_node[sp] = nn_; st_lb[sp] = ln; ++sp; }
+        }
+    }
+    idx[i] = (best_j == 0x7fffffff) ? 0 : best_j;
+}
+
+extern "C" int lb2_nn_match_tree(void* handle, void* stream, const int32_t* q_coords, const int32_t* d_nq, int32_t nq_cap,
+                                 const void* tree, int32_t nk_cap, const int32_t* k_coords, const int32_t* hint_of,
+                                 const int32_t* hint_idx, int32_t* idx) {
+    Lb2Handle* h = (Lb2Handle*)handle;
+    LB2_REQUIRE(h, h && q_coords && tree && idx && nq_cap > 0 && nk_cap > 0 && (!hint_idx || k_coords), "nn_match_tree");
+    k_nn_match_tree<<<cdiv(nq_cap, 128), 128, 0, (cudaStream_t)stream>>>((const int4*)q_coords, d_nq, nq_cap, (const int*)tree, nk_cap,
+                                                                         (const int4*)k_coords, hint_of, hint_idx, idx);
+    LB2_POST_LAUNCH(h, "k_nn_match_tree");
+    return LB2_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // nn_match with the key lattice in SHARED memory: the <= 8192 keys of the partial scan are re-hashed once per scan
 // into a compact 16384-slot table (128 KB keys + 64 KB rows) that every CTA copies into its shared memory, so the
 // 27-125 probes of a query are smem accesses instead of L2 round trips.  Same shell search and tie rule as above.

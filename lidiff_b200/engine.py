@@ -219,6 +219,7 @@ class DenoiseEngine:
         self._pairs_lookup = _PairLookup(self.geom)
         self.geom_cond = None
         self.part_cap = 0
+        self.nn_algo = os.environ.get("LB2_NN_ALGO", "tree")             # "tree" (box hierarchy) or "grid" (lattice shell search): same results
         # optional instrumentation (bench.py): per-conv CUDA events + layer inventory + pair-count history
         self.conv_events = None          # list of (start, end, layer_index) when enabled
         self.layer_log = None            # list of dict(map, lvl, cin, cout, kvol, npass, tc) recorded during one step
@@ -474,6 +475,7 @@ class DenoiseEngine:
         self.part_F = skips[4][0]                                      # (N cap, 256), rows valid < d_n[4]
         self.part_C, self.part_dn, self.part_grid = g.C[4], g.d_n[4], g.grid[4]
         self.part_cap = N
+        self.part_tree = self.h.nn_tree(self.part_C, self.part_dn, N)    # box hierarchy over the scan's stride-16 voxels: built once per scan
         self.A_cond = self._part_A(self.part_F, N, self.part_dn, "c")
 
     # ---- one denoising step ----------------------------------------------------------------------------------
@@ -487,12 +489,17 @@ class DenoiseEngine:
             self._hist_row += 1
         F0 = self.buf("F0", (1, N, 3))
         g.voxel_mean(x_t, N, F0[0])
-        nn = []
-        for l in range(5):
+        nn = [None] * 5
+        for l in range(4, -1, -1):                   # coarse to fine: a voxel's search starts from its parent voxel's answer
             ix = self.buf(f"nn{l}", (N,), torch.int32)
             # (the shared-memory-table variant lb2_nn_match_table measured slower: 2.1 vs 1.7 ms for the 5 levels)
-            h.nn_match_grid(g.C[l], g.d_n[l], N, self.part_C, self.part_dn, self.part_cap, self.part_grid, 16, 4, ix)
-            nn.append(ix)
+            if self.nn_algo == "grid":
+                h.nn_match_grid(g.C[l], g.d_n[l], N, self.part_C, self.part_dn, self.part_cap, self.part_grid, 16, 4, ix)
+            elif l == 4:
+                h.nn_match_tree(g.C[l], g.d_n[l], N, self.part_tree, self.part_cap, ix)
+            else:
+                h.nn_match_tree(g.C[l], g.d_n[l], N, self.part_tree, self.part_cap, ix, self.part_C, g.inv[l + 1], nn[l + 1])
+            nn[l] = ix
         tabs_c = self._gate_tables(self.A_cond, self.part_cap, self.part_dn, i, "c")
         gates = [[(tabs_c[k], nn[GATE_LEVEL[k]]), (self.table_u[k][i:i + 1], None)] for k in range(8)]
         skips, cur = self._encoder(self.diff, g, F0, 2, "d", gates)

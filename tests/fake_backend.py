@@ -244,6 +244,13 @@ class FakeHandle:
     def nn_match_grid(self, q, d_nq, nq_cap, k, d_nk, nk_cap, key_grid, key_stride, max_ring, idx):
         self.nn_match(q, d_nq, nq_cap, k, d_nk, nk_cap, 0, idx)
 
+    def nn_tree(self, k, d_nk, nk_cap):
+        self.launches += 12
+        return (k, d_nk)
+
+    def nn_match_tree(self, q, d_nq, nq_cap, tree, nk_cap, idx, k=None, hint_of=None, hint_idx=None):
+        self.nn_match(q, d_nq, nq_cap, tree[0], tree[1], nk_cap, 0, idx)
+
     def nn_table(self, k, d_nk, nk_cap):
         return torch.zeros(16, dtype=torch.uint8)
 

@@ -347,8 +347,38 @@ def test_nn_match_grid_equals_brute_force():
     tab = h.nn_table(geo.C[4], geo.d_n[4], kc.shape[0])
     h.nn_match_table(q, None, q.shape[0], geo.C[4], geo.d_n[4], kc.shape[0], tab, 16, 4, c)
     assert torch.equal(a, c), "shared-memory table variant"
+    t = torch.empty_like(a)
+    tree = h.nn_tree(geo.C[4], geo.d_n[4], kc.shape[0])
+    h.nn_match_tree(q, None, q.shape[0], tree, kc.shape[0], t)
+    assert torch.equal(a, t), "bounding-box hierarchy variant"
     ref = ome.match_part_to_full(q[:5000].cpu(), keys.cpu())
     assert torch.equal(a[:5000].long().cpu(), ref)
+
+
+def test_nn_match_tree_batches_ties_and_degenerate_sets():
+    """lb2_nn_match_tree == exhaustive argmin for multi-batch keys, duplicated coordinates (lowest row wins), a single key"""
+    h = H()
+    g = torch.Generator().manual_seed(9)
+    for nk, nb in ((1, 1), (5, 1), (3000, 3), (4097, 2)):
+        kxyz = torch.randint(-60, 60, (nk, 3), generator=g) * 16
+        kxyz[nk // 2:] = kxyz[: nk - nk // 2].clone()                 # duplicated coordinates
+        kb = torch.randint(0, nb, (nk, 1), generator=g)
+        keys = torch.cat([kb, kxyz], 1).int().to(DEV).contiguous()
+        q = torch.cat([torch.randint(0, nb + 1, (20_000, 1), generator=g), torch.randint(-1500, 1500, (20_000, 3), generator=g)], 1).int().to(DEV).contiguous()
+        a = torch.empty(q.shape[0], dtype=torch.int32, device=DEV)
+        t = torch.empty_like(a)
+        d_nk = torch.tensor([nk], dtype=torch.int32, device=DEV)
+        cap = nk + 100                                                 # capacity above the live count
+        kpad = torch.cat([keys, torch.full((100, 4), 7, dtype=torch.int32, device=DEV)], 0).contiguous()
+        h.nn_match(q, None, q.shape[0], kpad, d_nk, cap, 0, a)
+        tree = h.nn_tree(kpad, d_nk, cap)
+        h.nn_match_tree(q, None, q.shape[0], tree, cap, t)
+        assert torch.equal(a, t), (nk, nb)
+        hint = torch.randint(0, nk, (777,), generator=g).int().to(DEV)            # arbitrary (even bad) hints never change the answer
+        hof = torch.randint(0, 777, (q.shape[0],), generator=g).int().to(DEV)
+        t2 = torch.empty_like(a)
+        h.nn_match_tree(q, None, q.shape[0], tree, cap, t2, kpad, hof, hint)
+        assert torch.equal(a, t2), ("hinted", nk, nb)
 
 
 @pytest.mark.parametrize("c1,c2,cout,lvl,spread", [(32, 0, 32, 0, 1.0), (96, 32, 96, 1, 0.3), (128, 64, 128, 2, 0.3), (64, 0, 64, 2, 1.0), (128, 0, 128, 0, 0.05)])
