@@ -25,7 +25,7 @@ constexpr int NCOLS = 256;
 constexpr int MAX_KVOL = 27;
 constexpr int NA = 4;                                 // A slots (half stages, 32 K-columns each)
 constexpr int NB = 2;                                 // B slots (64 K-columns each)
-constexpr int A_LAG = 2;                              // cp.async lookahead in A slots (NA - 2: see spconv_tc2.cu)
+constexpr int A_LAG = 3;                              // cp.async lookahead in A slots: NA - 1, arrivals are signalled before the next issue
 constexpr int SLAB_COLS = 16;
 constexpr int SLAB_PITCH = SLAB_COLS + 4;             // floats per slab row
 constexpr int SLAB_BYTES = 8 * 32 * SLAB_PITCH * 4;   // 8 drain warps x 32 rows
@@ -176,6 +176,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_n256(const Params p) {
                 km &= km - 1;
                 if (km) load_src(__ffs(km) - 1, nxt);                 // prefetch the next offset's rows behind this offset's copies
                 for (int c2 = 0; c2 < 2 * p.nchunks; ++c2, ++it, ri.next()) {      // c2 = 2 * chunk + half
+                    if (it >= A_LAG) {                                  // publish the slot issued A_LAG iterations ago BEFORE waiting for a free
+                        cp_async_wait<A_LAG - 1>();                     // slot: its consumer never waits for this iteration's slot to drain
+                        fence_proxy_async();
+                        mbar_arrive(full_a(ra.s));
+                        ra.next();
+                        ++arrived;
+                    }
                     const int s = ri.s;
                     mbar_wait(empty_a(s), ri.par ^ 1u);
                     const uint32_t a_hi_u = base + (uint32_t)(s >> 1) * a_stage;
@@ -194,13 +201,6 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_n256(const Params p) {
                         cp_async16(a_hi_u + A_TILE + off, rp + (ok ? cw : 0), ok ? 16u : 0u);
                     }
                     cp_async_commit();
-                    if (it >= A_LAG) {
-                        cp_async_wait<A_LAG>();
-                        fence_proxy_async();
-                        mbar_arrive(full_a(ra.s));
-                        ra.next();
-                        ++arrived;
-                    }
                 }
 #pragma unroll
                 for (int q = 0; q < 4; ++q) src[q] = nxt[q];

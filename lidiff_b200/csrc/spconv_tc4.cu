@@ -23,7 +23,7 @@ using namespace tc;
 constexpr int THREADS = 512;
 constexpr int MAX_KVOL = 27;
 constexpr int NA = 4;                                 // A slots (32 K-columns each; two per 128-byte row image)
-constexpr int A_LAG = 2;                              // cp.async lookahead in A slots (NA - 2, see spconv_tc2.cu)
+constexpr int A_LAG = 3;                              // cp.async lookahead in A slots: NA - 1, arrivals are signalled before the next issue
 constexpr int NB = 3;                                 // weight slots (64 K-columns each)
 constexpr int NACC = 4;                               // TMEM accumulators
 constexpr int SLAB_PITCH = 20;                        // floats per slab row (16 + 4: conflict-free 16-byte accesses)
@@ -164,6 +164,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_small(const Params p) 
 #pragma unroll
                 for (int q = 0; q < 4; ++q) src[q] = idx_s[k * BM + rbase + 32 * q];
                 for (int c2 = 0; c2 < p.nhalf; ++c2, ++it, ri.next()) {
+                    if (it >= A_LAG) {                                  // publish the slot issued A_LAG iterations ago BEFORE waiting for a free
+                        cp_async_wait<A_LAG - 1>();                     // slot: its consumer never waits for this iteration's slot to drain
+                        fence_proxy_async();
+                        mbar_arrive(full_a(ra.s));
+                        ra.next();
+                        ++arrived;
+                    }
                     const int s = ri.s;
                     mbar_wait(empty_a(s), ri.par ^ 1u);
                     const uint32_t img = (uint32_t)(s >> 1) * a_stage;
@@ -204,13 +211,6 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_small(const Params p) 
                         }
                     }
                     cp_async_commit();                                  // (empty group on the fp32 path)
-                    if (it >= A_LAG) {
-                        cp_async_wait<A_LAG>();
-                        fence_proxy_async();
-                        mbar_arrive(full_a(ra.s));
-                        ra.next();
-                        ++arrived;
-                    }
                 }
             }
         }
