@@ -215,7 +215,8 @@ def run_ours(args, rank, world, local_rank):
     tpath = os.path.join(ROOT, "profiles", "r01_conv_dram_traffic.json")
     if os.path.exists(tpath):                         # dram__bytes_read+write per conv launch from the committed ncu capture
         traffic = json.load(open(tpath)).get("traffic_bytes_per_launch")
-    roofline = {"kernel": "k_spconv_tc (+k_spconv_scatter, k_spconv_ffma): sparse convolution, all layers", "bound": "tensor",
+    roofline = {"kernel": "sparse convolution, all layers: k_spconv_tc_n256 (Cout 256) + k_spconv_tc_small<1-4> (Cout <= 128) [+ k_spconv_ffma stem]",
+                "bound": "tensor",
                 "achieved": round(achieved_tf, 2), "peak": peaks["tf"], "unit": "TFLOP/s", "frac": round(achieved_tf / peaks["tf"], 4),
                 "traffic": traffic, "traffic_unit": "DRAM bytes per conv launch (ncu, profiles/r01_conv_dram_traffic.json)", "peak_source": peaks["src"],
                 "algorithmic_flops_per_launch": flops / n_launch, "avg_launch_ms": round(avg_ms, 4),

@@ -302,27 +302,63 @@ extern "C" int lb2_voxel_mean(void* handle, void* stream, const float* feats, co
 // ---------------------------------------------------------------------------------------------------
 // kernel map: neighbour table nbr[k][o]
 // ---------------------------------------------------------------------------------------------------
-__global__ void k_kernel_map(const unsigned long long* __restrict__ keys, const int* __restrict__ rows, unsigned mask,
-                             const int4* __restrict__ out_coords, const int* __restrict__ d_n, int n_cap,
-                             int ks, int step, int* __restrict__ nbr, long long nbr_stride,
-                             unsigned long long* __restrict__ pair_count, unsigned* __restrict__ row_mask) {
-    int o = blockIdx.x * blockDim.x + threadIdx.x;
-    int k = blockIdx.y;
-    int n = d_n ? min(*d_n, n_cap) : n_cap;
-    int res = -1;
+// one thread per output row walks the K offsets: the row's coordinate is read once, its neighbour mask is built in a
+// register, the K table writes stay coalesced across the warp for each k, and the K hash probes of a thread are
+// independent loads in flight together
+template <int KS>
+__global__ void __launch_bounds__(128) k_kernel_map(const unsigned long long* __restrict__ keys, const int* __restrict__ rows, unsigned mask,
+                                                    const int4* __restrict__ out_coords, const int* __restrict__ d_n, int n_cap,
+                                                    int step, int* __restrict__ nbr, long long nbr_stride,
+                                                    unsigned long long* __restrict__ pair_count, unsigned* __restrict__ row_mask) {
+    constexpr int KV = KS * KS * KS;
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = d_n ? min(*d_n, n_cap) : n_cap;
+    unsigned found = 0;
     if (o < n) {
-        int4 c = __ldg(out_coords + o);
-        int kx = k % ks, ky = (k / ks) % ks, kz = k / (ks * ks);
-        int cen = (ks & 1) ? ks / 2 : 0;
-        int x = c.y + (kx - cen) * step, y = c.z + (ky - cen) * step, z = c.w + (kz - cen) * step;
-        unsigned long long key;
-        if (lb2_pack_key(c.x, x, y, z, key)) res = lb2_grid_lookup(keys, rows, mask, key);
+        const int4 c = __ldg(out_coords + o);
+        constexpr int cen = (KS & 1) ? KS / 2 : 0;
+        int res[KV];
+        unsigned long long key[KV], got[KV];
+        unsigned slot[KV];
+#pragma unroll
+        for (int k = 0; k < KV; ++k) {                                  // first probe of every offset: KV independent loads
+            const int kx = k % KS, ky = (k / KS) % KS, kz = k / (KS * KS);
+            const int x = c.y + (kx - cen) * step, y = c.z + (ky - cen) * step, z = c.w + (kz - cen) * step;
+            const bool ok = lb2_pack_key(c.x, x, y, z, key[k]);
+            slot[k] = ok ? (lb2_hash(key[k]) & mask) : 0u;
+            got[k] = ok ? __ldg(keys + slot[k]) : LB2_KEY_EMPTY;
+            if (!ok) key[k] = ~LB2_KEY_EMPTY;                           // differs from the EMPTY it "read": a miss below
+        }
+#pragma unroll
+        for (int k = 0; k < KV; ++k) {
+            if (got[k] == key[k]) res[k] = __ldg(rows + slot[k]);
+            else if (got[k] == LB2_KEY_EMPTY) res[k] = -1;
+            else {                                                      // collision on the first slot: continue the linear probe
+                unsigned sl = (slot[k] + 1) & mask;
+                res[k] = -1;
+                while (true) {
+                    const unsigned long long kk = __ldg(keys + sl);
+                    if (kk == key[k]) { res[k] = __ldg(rows + sl); break; }
+                    if (kk == LB2_KEY_EMPTY) break;
+                    sl = (sl + 1) & mask;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < KV; ++k) {
+            nbr[(long long)k * nbr_stride + o] = res[k];
+            if (res[k] >= 0) found |= 1u << k;
+        }
+    } else if (o < n_cap) {
+#pragma unroll
+        for (int k = 0; k < KV; ++k) nbr[(long long)k * nbr_stride + o] = -1;
     }
-    if (o < n_cap) nbr[(long long)k * nbr_stride + o] = res;
-    if (row_mask && res >= 0) atomicOr(row_mask + o, 1u << k);
+    if (row_mask && o < n_cap) row_mask[o] = found;
     if (pair_count) {        // algorithmic work counter for the roofline: one atomic per warp
-        unsigned found = __ballot_sync(0xffffffffu, res >= 0);
-        if ((threadIdx.x & 31) == 0 && found) atomicAdd(pair_count, (unsigned long long)__popc(found));
+        int cnt = __popc(found);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+        if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(pair_count, (unsigned long long)cnt);
     }
 }
 
@@ -332,14 +368,14 @@ extern "C" int lb2_kernel_map(void* handle, void* stream, lb2_grid grid_in, cons
     Lb2Handle* h = (Lb2Handle*)handle;
     LB2_REQUIRE(h, h && grid_in.keys && grid_in.vals && out_coords && nbr, "kernel_map null");
     LB2_REQUIRE(h, ks >= 1 && ks <= 3 && step != 0 && nout_cap > 0 && nbr_stride >= nout_cap, "kernel_map args");
-    int kvol = ks * ks * ks;
-    if (row_mask && cudaMemsetAsync(row_mask, 0, (size_t)nout_cap * sizeof(uint32_t), (cudaStream_t)stream) != cudaSuccess)
-        return lb2_fail(h, LB2_ERR_CUDA, "kernel_map memset%s", "");
-    dim3 grid(cdiv(nout_cap, 256), kvol);
-    k_kernel_map<<<grid, 256, 0, (cudaStream_t)stream>>>((const unsigned long long*)grid_in.keys,
-                                                        grid_in.vals + grid_in.cap_table, (unsigned)grid_in.cap_table - 1u,
-                                                        (const int4*)out_coords, d_nout, nout_cap, ks, step, nbr, nbr_stride,
-                                                        (unsigned long long*)pair_count, row_mask);
+    const unsigned long long* gk = (const unsigned long long*)grid_in.keys;
+    const int* gr = grid_in.vals + grid_in.cap_table;
+    const unsigned gm = (unsigned)grid_in.cap_table - 1u;
+    const unsigned blocks = cdiv(nout_cap, 128);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (ks == 3) k_kernel_map<3><<<blocks, 128, 0, s>>>(gk, gr, gm, (const int4*)out_coords, d_nout, nout_cap, step, nbr, nbr_stride, (unsigned long long*)pair_count, row_mask);
+    else if (ks == 2) k_kernel_map<2><<<blocks, 128, 0, s>>>(gk, gr, gm, (const int4*)out_coords, d_nout, nout_cap, step, nbr, nbr_stride, (unsigned long long*)pair_count, row_mask);
+    else k_kernel_map<1><<<blocks, 128, 0, s>>>(gk, gr, gm, (const int4*)out_coords, d_nout, nout_cap, step, nbr, nbr_stride, (unsigned long long*)pair_count, row_mask);
     LB2_POST_LAUNCH(h, "k_kernel_map");
     return LB2_OK;
 }
