@@ -132,12 +132,16 @@ class Geometry:
         self.koff = [torch.zeros(28, **i32) for _ in range(self.pair_levels)]
         self.tile_off = [torch.zeros(28, **i32) for _ in range(self.pair_levels)]
 
-    def build(self, coords_f: torch.Tensor, n_points: int):
-        """coords_f (n_points,4) fp32 integer-valued [b,x,y,z] -> all levels and maps (async)."""
+    def build(self, coords_f: torch.Tensor, n_points: int, after_levels=None):
+        """coords_f (n_points,4) fp32 integer-valued [b,x,y,z] -> all levels and maps (async).  `after_levels()` is called once the
+        coordinate levels (C, inv, d_n, grids) are enqueued and before the kernel maps: work that only needs the levels can be
+        put on another stream there and overlap with the map construction."""
         h, N = self.h, self.n_cap
         h.unique_build(coords_f, None, None, n_points, 0, self.grid[0], self.C[0], self.inv[0], self.d_n[0], self.scratch)
         for l in range(1, self.levels):
             h.unique_build(None, self.C[l - 1], self.d_n[l - 1], N, 1 << l, self.grid[l], self.C[l], self.inv[l], self.d_n[l], self.scratch)
+        if after_levels is not None:
+            after_levels()
         self.pairs.zero_()
 
         def one(grid, l_out, ks, step, nbr, perm, slot):
@@ -220,6 +224,11 @@ class DenoiseEngine:
         self.geom_cond = None
         self.part_cap = 0
         self.nn_algo = os.environ.get("LB2_NN_ALGO", "tree")             # "tree" (box hierarchy) or "grid" (lattice shell search): same results
+        # NN matches + gate tables on a second stream, concurrent with the kernel-map construction (LB2_SIDE_STREAM=0: all on one stream)
+        self.use_side_stream = os.environ.get("LB2_SIDE_STREAM", "1") != "0" and torch.cuda.is_available() and self.device.type == "cuda"
+        if self.use_side_stream:
+            self._side = torch.cuda.Stream(device=self.device)
+            self._side_done = torch.cuda.Event()
         # optional instrumentation (bench.py): per-conv CUDA events + layer inventory + pair-count history
         self.conv_events = None          # list of (start, end, layer_index) when enabled
         self.layer_log = None            # list of dict(map, lvl, cin, cout, kvol, npass, tc) recorded during one step
@@ -482,25 +491,43 @@ class DenoiseEngine:
     def step(self, i: int, x_t, x_next, coords, coords_next, x_init, noise_i, x0_state, eps_out=None):
         h, N, g = self.h, self.N, self.geom
         self._conv_counter = 0
-        g.build(coords, N)
+        nn = [None] * 5
+        tabs_box = []
+
+        def matches_and_gates():
+            # the NN matches need only the coordinate levels and the gate tables nothing of this step's geometry: both run on a side
+            # stream next to the kernel-map / row-order construction (all of them small latency-bound kernels)
+            for l in range(4, -1, -1):               # coarse to fine: a voxel's search starts from its parent voxel's answer
+                ix = self.buf(f"nn{l}", (N,), torch.int32)
+                # (the shared-memory-table variant lb2_nn_match_table measured slower: 2.1 vs 1.7 ms for the 5 levels)
+                if self.nn_algo == "grid":
+                    h.nn_match_grid(g.C[l], g.d_n[l], N, self.part_C, self.part_dn, self.part_cap, self.part_grid, 16, 4, ix)
+                elif l == 4:
+                    h.nn_match_tree(g.C[l], g.d_n[l], N, self.part_tree, self.part_cap, ix)
+                else:
+                    h.nn_match_tree(g.C[l], g.d_n[l], N, self.part_tree, self.part_cap, ix, self.part_C, g.inv[l + 1], nn[l + 1])
+                nn[l] = ix
+            tabs_box.append(self._gate_tables(self.A_cond, self.part_cap, self.part_dn, i, "c"))
+
+        def after_levels():
+            if not self.use_side_stream:
+                return matches_and_gates()
+            main = torch.cuda.current_stream()
+            self._side.wait_stream(main)             # the levels are enqueued; the previous step's readers of nn*/gate_* too
+            with torch.cuda.stream(self._side):
+                matches_and_gates()
+                self._side_done.record(self._side)
+
+        g.build(coords, N, after_levels)
+        if self.use_side_stream:
+            torch.cuda.current_stream().wait_event(self._side_done)
         if self.pair_hist is not None:
             g.pairs[13:18] = torch.cat(g.d_n).long()
             self.pair_hist[self._hist_row % self.pair_hist.shape[0]] = g.pairs
             self._hist_row += 1
         F0 = self.buf("F0", (1, N, 3))
         g.voxel_mean(x_t, N, F0[0])
-        nn = [None] * 5
-        for l in range(4, -1, -1):                   # coarse to fine: a voxel's search starts from its parent voxel's answer
-            ix = self.buf(f"nn{l}", (N,), torch.int32)
-            # (the shared-memory-table variant lb2_nn_match_table measured slower: 2.1 vs 1.7 ms for the 5 levels)
-            if self.nn_algo == "grid":
-                h.nn_match_grid(g.C[l], g.d_n[l], N, self.part_C, self.part_dn, self.part_cap, self.part_grid, 16, 4, ix)
-            elif l == 4:
-                h.nn_match_tree(g.C[l], g.d_n[l], N, self.part_tree, self.part_cap, ix)
-            else:
-                h.nn_match_tree(g.C[l], g.d_n[l], N, self.part_tree, self.part_cap, ix, self.part_C, g.inv[l + 1], nn[l + 1])
-            nn[l] = ix
-        tabs_c = self._gate_tables(self.A_cond, self.part_cap, self.part_dn, i, "c")
+        tabs_c = tabs_box[0]
         gates = [[(tabs_c[k], nn[GATE_LEVEL[k]]), (self.table_u[k][i:i + 1], None)] for k in range(8)]
         skips, cur = self._encoder(self.diff, g, F0, 2, "d", gates)
         y4 = self._decoder(self.diff, g, skips, cur, 2, "d", gates)
