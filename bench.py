@@ -326,21 +326,29 @@ def main():
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    # stdout carries exactly ONE line, the result JSON: libraries that print to fd 1 (NCCL's version banner does) are sent to
+    # stderr for the whole run, the JSON is written to the saved descriptor at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     if args.impl == "reference":
         out = run_reference(args, rank, world)
         if out is not None:
-            print(json.dumps(out), flush=True)
+            emit(out)
         return
     if args.warmup < 3:
         args.warmup = 3
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # NCCL logs to stdout by default: keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     out = run_ours(args, rank, world, local_rank)
     if out is not None:
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
