@@ -11,7 +11,7 @@
 //   WG0 warps 0-3   A producers (cp.async from the fp16 split companions only; neighbour rows re-read per offset)
 //   WG1 warp 4 MMA issuer, warp 5 weight loader (warps 6,7 idle)
 //   WG2 warps 8-11  drain + epilogue of output channels   0..127        WG3 warps 12-15: channels 128..255
-// Same math and results as k_spconv_tc / k_spconv_tc_n256 (tests compare them).
+// Same math and results as the per-tile kernel k_spconv_tc (tests compare them bit for bit).
 #include "common.cuh"
 #include <algorithm>
 #include <stdlib.h>
@@ -46,7 +46,7 @@ struct Params {
     int mout_cap;
     const int* row_perm;
     const unsigned* row_mask;
-    int stages, lag, nchunks, tmem_cols, tot_col, group, nbuf, acc_stride, npass;
+    int nchunks, group, npass;
     lb2_conv_io io[2];
 };
 
@@ -424,8 +424,6 @@ int lb2_spconv_tc3_launch(Lb2Handle* h, cudaStream_t s, const lb2_conv_desc* d, 
     p.scale = d->scale; p.shift = d->shift; p.relu = d->relu;
     p.nbr = d->nbr; p.nbr_stride = d->nbr_stride; p.d_mout = d->d_mout; p.mout_cap = d->mout_cap; p.row_perm = d->row_perm; p.row_mask = d->row_mask;
     p.nchunks = (d->c1 + d->c2 + tc::KC - 1) / tc::KC;
-    p.stages = tc3::NA; p.lag = tc3::A_LAG;
-    p.nbuf = 2; p.acc_stride = 256; p.tot_col = 0; p.tmem_cols = 512;
     const int steps_per_offset = 3 * ((d->c1 + d->c2 + 15) / 16);
     p.group = std::max(1, step_budget / steps_per_offset);
     p.io[0] = d->io[0]; p.io[1] = d->io[d->npass > 1 ? 1 : 0];
