@@ -195,3 +195,20 @@ def test_oracle_end_to_end_small(small_scan, calibrated_sds):
     assert out.shape == (scan.shape[1], 3) and np.isfinite(out).all()
     ref = o.refine.unet_refine(o.points_to_tensor(torch.from_numpy(out)[None]))
     assert ref.shape == (scan.shape[1], 18) and torch.isfinite(ref).all() and ref.abs().max() <= 1
+
+
+def test_nn_match_against_scipy_kdtree():
+    """independent check of the argKmin restatement (minkunet.py:403-418): scipy's exact k-d tree gives the same nearest distance
+    for every query, and the same index wherever the nearest key is unique"""
+    from scipy.spatial import cKDTree
+    g = torch.Generator().manual_seed(21)
+    keys = torch.cat([torch.zeros(3000, 1), torch.round(torch.randn(3000, 3, generator=g) * torch.tensor([300.0, 300.0, 30.0]) / 16) * 16], 1)
+    q = torch.cat([torch.zeros(20000, 1), torch.round(torch.randn(20000, 3, generator=g) * torch.tensor([320.0, 320.0, 35.0]))], 1)
+    idx = ome.match_part_to_full(q, keys).numpy()
+    d_ref, i_ref = cKDTree(keys[:, 1:].numpy().astype(np.float64)).query(q[:, 1:].numpy().astype(np.float64), k=2)
+    d_or = np.linalg.norm(q[:, 1:].numpy().astype(np.float64) - keys[idx, 1:].numpy().astype(np.float64), axis=1)
+    assert np.array_equal(d_or, d_ref[:, 0])
+    unique = d_ref[:, 1] > d_ref[:, 0]
+    assert unique.mean() > 0.9 and np.array_equal(idx[unique], i_ref[unique, 0])
+    ties = ~unique                                                          # among equidistant keys the lowest index wins (App. A.10)
+    assert np.all(idx[ties] <= i_ref[ties].min(1))
