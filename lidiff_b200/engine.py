@@ -127,8 +127,9 @@ class Geometry:
         self.pair_level_set = set(int(c) for c in os.environ.get("LB2_SCATTER_LEVELS", "") if c.isdigit())
         self.pairs_of = {}
         self.pl_scratch = torch.zeros(64, **i32)
-        self.pair_in = [torch.zeros(26 * n_cap, **i32) for _ in range(self.pair_levels)]
-        self.pair_out = [torch.zeros(26 * n_cap, **i32) for _ in range(self.pair_levels)]
+        want = [use_pairs and l in self.pair_level_set for l in range(self.pair_levels)]     # 208 B/row per level: only where asked for
+        self.pair_in = [torch.zeros(26 * n_cap, **i32) if w else None for w in want]
+        self.pair_out = [torch.zeros(26 * n_cap, **i32) if w else None for w in want]
         self.koff = [torch.zeros(28, **i32) for _ in range(self.pair_levels)]
         self.tile_off = [torch.zeros(28, **i32) for _ in range(self.pair_levels)]
 
