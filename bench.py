@@ -119,6 +119,24 @@ def build_pipeline(device, scan):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+def sampled_steps(K: int, T: int):
+    """the K schedule positions the timed region runs: all T steps in order when K >= T (wrapping), otherwise K positions
+    spread evenly over the schedule (first and last included) — a short run costs what the full trajectory costs per step"""
+    if K >= T:
+        return [i % T for i in range(K)]
+    return sorted({int(round(j * (T - 1) / max(K - 1, 1))) for j in range(K)}) if K > 1 else [0]
+
+
+def csrc_digest():
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "lidiff_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh")):
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
     from lidiff_b200.sharding import max_over_ranks
@@ -130,8 +148,10 @@ def run_ours(args, rank, world, local_rank):
     pipe = build_pipeline(device, scan)
     eng = pipe.engine()
     h = eng.h
-    K, W = args.steps, args.warmup
-    noise = torch.randn((K, N_POINTS, 3), device=device, generator=g)
+    K, W, T = args.steps, args.warmup, eng.T
+    steps = sampled_steps(K, T)
+    K = len(steps)
+    noise = torch.randn((T, N_POINTS, 3), device=device, generator=g)
     x_feats = (scan + start).float()
 
     def barrier():
@@ -139,40 +159,47 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up --------------------------------------------------------------------------------------------
-    log(f"warm-up {W} steps")
+    # ---- untimed: the full T-step trajectory once; the loop state in front of every sampled step is kept --------------
+    log(f"trajectory pass: {T} steps (untimed), snapshots in front of steps {steps}")
     st = eng.start(scan, x_feats)
-    for i in range(W):
-        eng.advance(st, noise[i % K])
+    snaps = {}
+    for i in range(T):
+        if i in steps and i not in snaps:
+            snaps[i] = (st["xa"].clone(), st["ca"].clone(), st["x0s"].clone())
+        eng.advance(st, noise[i])
     torch.cuda.synchronize()
 
-    # ---- timed region 1: inputs resident in HBM ----------------------------------------------------------------
-    st = eng.start(scan, x_feats)
-    eng.pair_hist = torch.zeros((K, 18), dtype=torch.int64, device=device)
-    eng._hist_row = 0
-    eng.conv_events = []
-    eng.layer_log = []
+    def restore(i):
+        xa, ca, x0s = snaps[i]
+        st["xa"].copy_(xa); st["ca"].copy_(ca); st["x0s"].copy_(x0s)
+        st["i"] = i
+        eng._have_x0 = i > 0
+
+    log(f"warm-up {W} steps")
+    for j in range(W):
+        restore(steps[j % K])
+        eng.advance(st, noise[steps[j % K]])
+    torch.cuda.synchronize()
+
+    # ---- timed region 1: inputs resident in HBM, no instrumentation -----------------------------------------------------
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     l0 = h.launch_count()
     with ClockSampler(local_rank) as clocks:
         e0.record()
-        for i in range(K):
+        for i in steps:
+            restore(i)
             eng.advance(st, noise[i])
-            if i == 0:
-                eng.layer_log_done, eng.layer_log = eng.layer_log, None
         e1.record()
         barrier()
     launches = h.launch_count() - l0
     ms = e0.elapsed_time(e1)
     log(f"timed region: {K} steps in {ms:.1f} ms")
-    conv_events, eng.conv_events = eng.conv_events, None
-    pair_hist, eng.pair_hist = eng.pair_hist.cpu().numpy(), None
     if h.read_status() & 1:
         raise RuntimeError("a coordinate left the supported key range during the benchmark")
 
-    # ---- timed region 2: end to end through the public loop with HOST buffers ----------------------------------
-    h_noise = torch.empty((K, N_POINTS, 3), dtype=torch.float32).pin_memory()
+    # ---- timed region 2: end to end through the public loop with HOST buffers ----------------------------------------------
+    h_noise = torch.empty((T, N_POINTS, 3), dtype=torch.float32).pin_memory()
     h_noise.copy_(noise)
     h_out = torch.empty((N_POINTS, 3), dtype=torch.float32).pin_memory()
     h_scan, h_start = scan.cpu().pin_memory(), x_feats.cpu().pin_memory()
@@ -180,73 +207,144 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     f0.record()
     st = eng.start(h_scan.to(device, non_blocking=True), h_start.to(device, non_blocking=True))
-    for i in range(K):
+    for i in steps:
+        restore(i)
         eng.advance(st, None, host_noise=h_noise[i], host_out=h_out)
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
     log(f"e2e region: {K} steps in {ms_e2e:.1f} ms")
-
     ms, ms_e2e = max_over_ranks(ms, device), max_over_ranks(ms_e2e, device)
+
+    # ---- instrumented pass (separate from the headline): per-conv CUDA events + pair counts of the same K steps --------------
+    eng.pair_hist = torch.zeros((K, 18), dtype=torch.int64, device=device)
+    eng._hist_row = 0
+    eng.conv_events, eng.layer_log = [], []
+    torch.cuda.synchronize()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for n, i in enumerate(steps):
+        restore(i)
+        eng.advance(st, noise[i])
+        if n == 0:
+            layers, eng.layer_log = eng.layer_log, None
+    g1.record()
+    torch.cuda.synchronize()
+    ms_instr = g0.elapsed_time(g1)
+    conv_events, eng.conv_events = eng.conv_events, None
+    pair_hist, eng.pair_hist = eng.pair_hist.cpu().numpy(), None
+
+    # ---- fixed-geometry micro-benchmark: points = scan + sigma*randn, one schedule position each --------------
+    fixed = {}
+    if rank == 0 and not args.no_fixed:
+        gf = torch.Generator(device=device).manual_seed(4321)
+        for sigma, i in ((1.0, 0), (0.2, T // 2), (0.05, T - 1)):
+            xs = (scan + sigma * torch.randn(scan.shape, device=device, generator=gf, dtype=scan.dtype)).float()
+            st = eng.start(scan, xs)
+            st["i"] = i
+            reps = 3
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            xa0, ca0 = st["xa"].clone(), st["ca"].clone()
+            for r in range(reps + 1):                 # first repetition untimed
+                if r == 1:
+                    a.record()
+                st["xa"].copy_(xa0); st["ca"].copy_(ca0); st["i"] = i
+                eng._have_x0 = False
+                eng.advance(st, noise[i])
+            b.record()
+            torch.cuda.synchronize()
+            fixed[f"sigma_{sigma}"] = {"ms_per_step": round(a.elapsed_time(b) / reps, 3), "level_rows": eng.geom.sizes(),
+                                       "pairs_3x3x3": eng.geom.pairs[:5].tolist()}
     if rank != 0:
         return None
 
-    # ---- roofline of the dominant kernel (sparse convolution) ---------------------------------------------------
+    # ---- rooflines ---------------------------------------------------------------------------------------------------------
     peaks = measured_peaks()
-    layers = eng.layer_log_done
     nconv = len(layers)
     geo = eng.geom
-    flops = bytes_gs = 0.0
-    conv_ms = sum(a.elapsed_time(b) for a, b, _ in conv_events)
-    tc_ms = sum(a.elapsed_time(b) for a, b, j in conv_events if layers[j % nconv]["tc"])
-    for step in range(K):
-        for ent in layers:
-            if ent["map"] is not None and ent["map"] in geo.map_id:
-                pairs = pair_hist[step, geo.map_id[ent["map"]]]
-            else:                                   # 1x1 conv on the identity map: pairs = rows of that level
-                lvl = [d.data_ptr() for d in geo.d_n].index(ent["d_m"])
-                pairs = pair_hist[step, 13 + lvl]
-            flops += 2.0 * pairs * ent["cin"] * ent["cout"] * ent["npass"]
-            bytes_gs += (pairs * (ent["cin"] + ent["cout"]) * 4.0 + pairs * 8.0) * ent["npass"]
-    n_launch = len(conv_events)
-    avg_ms = conv_ms / max(n_launch, 1)
-    achieved_tf = flops / n_launch / (avg_ms * 1e-3) / 1e12
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_conv_dram_traffic.json")
-    if os.path.exists(tpath):                         # dram__bytes_read+write per conv launch from the committed ncu capture
-        traffic = json.load(open(tpath)).get("traffic_bytes_per_launch")
-    roofline = {"kernel": "sparse convolution, all layers: k_spconv_tc_n256 (Cout 256) + k_spconv_tc_small<1-4> (Cout <= 128) [+ k_spconv_ffma stem]",
-                "bound": "tensor",
-                "achieved": round(achieved_tf, 2), "peak": peaks["tf"], "unit": "TFLOP/s", "frac": round(achieved_tf / peaks["tf"], 4),
-                "traffic": traffic, "traffic_unit": "DRAM bytes per conv launch (ncu, profiles/r01_conv_dram_traffic.json)", "peak_source": peaks["src"],
-                "algorithmic_flops_per_launch": flops / n_launch, "avg_launch_ms": round(avg_ms, 4),
-                "conv_share_of_step": round(conv_ms / ms, 3), "tc_share_of_conv_time": round(tc_ms / max(conv_ms, 1e-9), 3),
-                "gather_scatter_model_GBps": round(bytes_gs / (conv_ms * 1e-3) / 1e9, 1), "hbm_peak_GBps": peaks["hbm_gbs"],
-                "note": "algorithmic FLOPs = 2*pairs*Cin*Cout per pass (SURVEY 8d); the FP16x3 split issues 3 MMAs per product, so the tensor ceiling for this figure is peak/3"}
+    cls_of = lambda e: ("ffma" if not e["tc"] else ("n256" if e["cout"] == 256 else "small"))
+    acc = {c: dict(flops=0.0, bytes_gs=0.0, bytes_min=0.0, ms=0.0, n=0) for c in ("n256", "small", "ffma")}
+    lvl_of_dm = {d.data_ptr(): l for l, d in enumerate(geo.d_n)}
+    for n_ev, (a, b, j) in enumerate(conv_events):
+        ent = layers[j % nconv]
+        step_row = n_ev // nconv
+        rows_out = pair_hist[step_row, 13 + lvl_of_dm[ent["d_m"]]]
+        if ent["map"] is not None and ent["map"] in geo.map_id:
+            slot = geo.map_id[ent["map"]]          # 0-4: 3^3 at level slot; 5-8: stride-2 into level slot-4; 9-12: transposed into level slot-9
+            pairs = pair_hist[step_row, slot]
+            lvl_in = slot if slot < 5 else (slot - 5 if slot < 9 else slot - 8)
+            rows_in = pair_hist[step_row, 13 + lvl_in]
+        else:                                   # 1x1 conv on the identity map: pairs = rows of that level
+            pairs, rows_in = rows_out, rows_out
+        c = acc[cls_of(ent)]
+        c["flops"] += 2.0 * pairs * ent["cin"] * ent["cout"] * ent["npass"]
+        c["bytes_gs"] += (pairs * (ent["cin"] + ent["cout"]) * 4.0 + pairs * 8.0) * ent["npass"]
+        c["bytes_min"] += (rows_in * ent["cin"] * 4.0 + rows_out * ent["cout"] * 4.0 + pairs * 8.0) * ent["npass"]
+        c["ms"] += a.elapsed_time(b)
+        c["n"] += 1
+    conv_ms = sum(c["ms"] for c in acc.values())
+    tot = {k: sum(c[k] for c in acc.values()) for k in ("flops", "bytes_gs", "bytes_min", "n")}
+    dom = max(acc, key=lambda k: acc[k]["ms"])
+    d = acc[dom]
+    names = {"n256": "k_spconv_tc_n256 (sparse conv, Cout 256: levels 3-4 + decoder level 3)", "small": "k_spconv_tc_small<1-4> (sparse conv, Cout <= 128)",
+             "ffma": "k_spconv_ffma (Cin=3 stem)"}
+    traffic = traffic_src = None
+    tpath = os.path.join(ROOT, "profiles", "r02_conv_dram_traffic.json")
+    if os.path.exists(tpath):                         # ncu dram bytes per launch: only valid for the kernel sources it was captured on
+        tj = json.load(open(tpath))
+        if tj.get("csrc_digest") == csrc_digest():
+            traffic, traffic_src = tj.get("traffic_bytes_per_launch", {}).get(dom), "profiles/r02_conv_dram_traffic.json (ncu --set full, same kernel sources)"
+    ach = d["flops"] / max(d["ms"], 1e-9) / 1e9          # FLOP / ms / 1e9 = TFLOP/s
+    roofline = {"kernel": names[dom], "bound": "tensor", "achieved": round(ach, 2), "peak": peaks["tf"], "unit": "TFLOP/s",
+                "frac": round(ach / peaks["tf"], 4), "traffic": traffic, "traffic_source": traffic_src, "peak_source": peaks["src"],
+                "algorithmic_flops_per_launch": d["flops"] / max(d["n"], 1), "avg_launch_ms": round(d["ms"] / max(d["n"], 1), 4), "launches": d["n"],
+                "share_of_step": round(d["ms"] / ms_instr, 3),
+                "note": "algorithmic FLOPs = 2*pairs*Cin*Cout per pass (SURVEY 8d); the FP16x3 operand split issues 3 MMAs per product, so "
+                        "the tensor ceiling for this figure is peak/3; per-launch times from CUDA events around every conv launch in a separate "
+                        "instrumented pass over the same steps",
+                "all_conv": {"achieved_TFLOPs": round(tot["flops"] / conv_ms / 1e9, 2), "launches": tot["n"], "share_of_step": round(conv_ms / ms_instr, 3),
+                             "gather_scatter_model_GBps": round(tot["bytes_gs"] / conv_ms / 1e6, 1),
+                             "gather_scatter_frac_of_hbm": round(tot["bytes_gs"] / conv_ms / 1e6 / peaks["hbm_gbs"], 4),
+                             "compulsory_GBps": round(tot["bytes_min"] / conv_ms / 1e6, 1), "hbm_peak_GBps": peaks["hbm_gbs"]},
+                "by_class": {k: {"ms_per_step": round(c["ms"] / K, 3), "achieved_TFLOPs": round(c["flops"] / max(c["ms"], 1e-9) / 1e9, 2),
+                                 "gather_scatter_GBps": round(c["bytes_gs"] / max(c["ms"], 1e-9) / 1e6, 1)} for k, c in acc.items() if c["n"]}}
 
     out = {"metric": METRIC, "value": round(K * world / (ms * 1e-3), 3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
            "ms_per_step": round(ms / K, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "fp16x3 split tensor-core MMA, fp32 accumulate (fp32 CUDA cores for the Cin=3 stem), fp64 DPM update",
            "data": "synthetic",
            "config": {"workload": "BASELINE configs[1]: one synthetic KITTI-shape scan of 180000 points per GPU, T=50 schedule, guidance s=6.0",
-                      "points": N_POINTS, "T": T_STEPS, "guidance_w": GUIDANCE_W, "resolution_m": 0.05,
+                      "points": N_POINTS, "T": T, "guidance_w": GUIDANCE_W, "resolution_m": 0.05,
+                      "schedule_positions_timed": steps,
+                      "steps_note": "the full T-step trajectory runs once untimed; the timed region replays the listed schedule positions from the saved "
+                                    "loop state (3 device copies per step, inside the timed region), so K < T samples the whole trajectory instead of its first K steps",
                       "weights": "seeded random init with reference parameter names, BN statistics calibrated on the scan",
                       "l2": "per-step working set (several GB of feature maps and maps) exceeds the 126 MB L2; no explicit flush",
-                      "level_rows_last_step": pair_hist[-1, 13:18].tolist()},
+                      "level_rows_first_last": [pair_hist[0, 13:18].tolist(), pair_hist[-1, 13:18].tolist()]},
            "clocks": clocks.summary(),
            "e2e": {"value": round(K * world / (ms_e2e * 1e-3), 3), "unit": UNIT, "h2d_bytes_per_step": N_POINTS * 3 * 4,
                    "d2h_bytes_per_step": N_POINTS * 3 * 4,
-                   "what": "same K steps through DenoiseEngine.start/advance with pinned HOST buffers: scan + start uploaded, per-step SDE noise H2D and x_t D2H inside the timed region"},
-           "gpu_launches": int(launches), "roofline": roofline}
+                   "what": "same schedule positions through DenoiseEngine.start/advance with pinned HOST buffers: scan + start uploaded, per-step SDE noise H2D and x_t D2H inside the timed region"},
+           "gpu_launches": int(launches), "roofline": roofline, "fixed_geometry": fixed}
     if world == 1 and not args.no_cpu_baseline:
         log("cpu baseline leg")
-        out["cpu_baseline"] = cpu_reference(scan.cpu(), pipe, sample_budget_s=20.0, steps=1, warmup=0)
+        out["cpu_baseline"] = cpu_reference(scan.cpu(), pipe, budget_s=20.0, steps=1, warmup=0)
     return out
 
 
 # ---------------------------------------------------------------------------------------------------------------
-def cpu_reference(scan, pipe, sample_budget_s, steps, warmup):
-    """CPU restatement of the reference path (oracle port) on the host cores, bounded sample."""
+def wedge(scan: torch.Tensor, frac: float) -> torch.Tensor:
+    """the points of an azimuthal sector holding `frac` of the scan: same local density as the full scan (a random subsample
+    would thin the neighbourhoods and change the cost per point)"""
+    az = torch.atan2(scan[:, 1], scan[:, 0])
+    cut = torch.quantile(az.double(), min(max(frac, 0.0), 1.0))
+    return scan[az.double() <= cut]
+
+
+def cpu_reference(scan, pipe, budget_s, steps, warmup):
+    """CPU restatement of the reference path (oracle port) on the host cores.  One definition for both uses (the cpu_baseline
+    leg and --impl reference): full denoising steps on an azimuthal sector of the scan sized to the time budget, steps/s scaled
+    by the sector's share of the points."""
     from oracle.pipeline import DiffCompletionOracle
     cores = usable_cpus()
     torch.set_num_threads(cores)
@@ -263,15 +361,14 @@ def cpu_reference(scan, pipe, sample_budget_s, steps, warmup):
         o.completion_loop(pts[None], o.points_to_tensor(x), o.points_to_tensor(pts[None]), o.points_to_tensor(torch.zeros_like(pts[None])), nz, n_steps=1)
         return time.time() - t0
 
-    # size the per-step sample: probe on 1/20 of the points, then pick the largest fraction inside the budget
-    n_probe = N_POINTS // 20
-    t_probe = one_step(scan[:: N_POINTS // n_probe][:n_probe])
-    log(f"cpu reference: probe step on {n_probe} points took {t_probe:.2f} s")
-    per_point = 1.5 * t_probe / n_probe          # cost grows a little faster than linearly (denser neighbourhoods)
+    probe = wedge(scan, 0.04)
+    t_probe = one_step(probe)
+    log(f"cpu reference: probe step on a {probe.shape[0]}-point sector took {t_probe:.2f} s")
     total = max(steps + warmup, 1)
-    n_s = int(min(N_POINTS, max(n_probe, sample_budget_s / total / per_point)))
-    sub = scan[torch.linspace(0, N_POINTS - 1, n_s).long()]
-    log(f"cpu reference: {total} step(s) on {n_s} points each")
+    frac = min(1.0, (budget_s / total) / (t_probe / probe.shape[0]) / N_POINTS)
+    sub = wedge(scan, frac) if frac < 1.0 else scan
+    n_s = sub.shape[0]
+    log(f"cpu reference: {total} step(s) on a {n_s}-point sector each")
     for _ in range(warmup):
         one_step(sub)
     ts = []
@@ -281,8 +378,9 @@ def cpu_reference(scan, pipe, sample_budget_s, steps, warmup):
     t_step = sum(ts) / len(ts)
     value = (1.0 / t_step) * (n_s / N_POINTS)
     return {"value": round(value, 5), "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{steps} denoising step(s) of the oracle (fp32 torch-CPU restatement of the ME/KeOps/diffusers path, all host threads) on "
-                      f"{n_s} of the {N_POINTS} points; steps/s scaled linearly by {n_s}/{N_POINTS} to the full scan ({t_step:.2f} s per sampled step)"}
+            "sample": f"{steps} denoising step(s) of the oracle (fp32 torch-CPU restatement of the ME/KeOps/diffusers path, all host threads) on an "
+                      f"azimuthal sector of {n_s} of the {N_POINTS} points (same point density as the full scan); steps/s scaled by "
+                      f"{n_s}/{N_POINTS} to the full scan ({t_step:.2f} s per sampled step)"}
 
 
 def run_reference(args, rank, world):
@@ -305,7 +403,7 @@ def run_reference(args, rank, world):
     rng = np.random.default_rng(0)
     sel = np.sort(rng.choice(raw.shape[0], N_POINTS // 10, replace=False))      # FPS is preprocessing, outside the metric
     scan = torch.tensor(raw[sel]).repeat(10, 1)
-    cb = cpu_reference(scan, p, sample_budget_s=150.0, steps=max(args.steps, 1), warmup=args.warmup)
+    cb = cpu_reference(scan, p, budget_s=150.0, steps=max(args.steps, 1), warmup=args.warmup)
     K = max(args.steps, 1)
     return {"metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
             "ms_per_step": round(1e3 / max(cb["value"], 1e-12), 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -323,6 +421,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fixed", action="store_true", help="skip the fixed-geometry sigma micro-benchmark")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))

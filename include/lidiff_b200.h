@@ -45,6 +45,17 @@ const char* lb2_last_error(void* handle);
 int         lb2_version(void);
 /* number of kernels this library has launched through `handle` since creation (bench gpu_launches) */
 int64_t     lb2_launch_count(void* handle);
+/* Kernel-selection options of a handle (development / A-B knobs; every setting computes the same results and is exercised by
+ * the GPU tests).  Defaults come from the environment variable of the same name (LB2_TC_PAIR, ...) at lb2_create. */
+#define LB2_OPT_TC_PAIR       0   /* CTA-pair cta_group::2 conv kernel: 0 off, 1 = Cout 256, 2 = Cout 256 and 128 (default 1) */
+#define LB2_OPT_TC_N256       1   /* single-CTA register-total kernel for Cout 256 (default 1) */
+#define LB2_OPT_TC_SMALL      2   /* two-drain-warpgroup kernel for Cout <= 128 (default 1) */
+#define LB2_OPT_TC_PERSISTENT 3   /* persistent kernels for LB2_ALGO_TC (default 1; 0 = one CTA per tile) */
+#define LB2_OPT_TC_FULL_LAG   4   /* generic persistent kernel: S-1 gather lookahead (default 0) */
+#define LB2_OPT_TC_NSPLIT     5   /* per-tile kernel: split Cout 256 over two CTAs (default 0) */
+#define LB2_OPT_COUNT         6
+int         lb2_set_option(void* handle, int option, int value);
+int         lb2_get_option(void* handle, int option);   /* value, or a negative LB2_ERR_* */
 /* synchronising read-and-clear of the device status word; bit0 = a coordinate fell outside the key
  * range (10 bit batch, 18 bit signed axes) and was clamped.  Returns the word (>= 0) or an error. */
 int         lb2_read_status(void* handle, void* stream);

@@ -15,6 +15,7 @@ import torch
 _SO = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_C", "liblidiff_b200.so")
 
 ALGO_AUTO, ALGO_FFMA, ALGO_TC, ALGO_TC_TILE = 0, 1, 2, 3
+OPT_TC_PAIR, OPT_TC_N256, OPT_TC_SMALL, OPT_TC_PERSISTENT, OPT_TC_FULL_LAG, OPT_TC_NSPLIT = range(6)
 
 
 class Grid(C.Structure):
@@ -55,6 +56,7 @@ class DpmCoef(C.Structure):
 
 EXPORTS = [
     "lb2_create", "lb2_destroy", "lb2_last_error", "lb2_version", "lb2_launch_count", "lb2_read_status",
+    "lb2_set_option", "lb2_get_option",
     "lb2_quantize", "lb2_unique_scratch_bytes", "lb2_unique_build", "lb2_voxel_mean", "lb2_kernel_map",
     "lb2_spconv_forward", "lb2_packed_weight_bytes", "lb2_pack_weights", "lb2_nn_match", "lb2_linear",
     "lb2_gate_mul", "lb2_gather_rows", "lb2_guidance_dpm_step", "lb2_farthest_point_sample",
@@ -91,6 +93,8 @@ class Lib:
         d.lb2_launch_count.argtypes = [C.c_void_p]
         d.lb2_launch_count.restype = C.c_int64
         d.lb2_read_status.argtypes = [C.c_void_p, C.c_void_p]
+        d.lb2_set_option.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        d.lb2_get_option.argtypes = [C.c_void_p, C.c_int]
         d.lb2_unique_scratch_bytes.argtypes = [C.c_int64]
         d.lb2_unique_scratch_bytes.restype = C.c_size_t
         d.lb2_packed_weight_bytes.argtypes = [C.c_int32] * 3
@@ -164,6 +168,12 @@ class Handle:
 
     def read_status(self) -> int:
         return int(self.dll.lb2_read_status(self.hp, self._stream()))
+
+    def set_option(self, option: int, value: int):
+        self._check(self.dll.lb2_set_option(self.hp, int(option), int(value)), "set_option")
+
+    def get_option(self, option: int) -> int:
+        return int(self.dll.lb2_get_option(self.hp, int(option)))
 
     # -- coordinate manager ------------------------------------------------------------------------
     def new_grid(self, n_cap: int):

@@ -11,8 +11,20 @@ struct Lb2Handle {
     int      num_sms;
     int64_t  launches;
     int32_t* d_status;      // device status word (bit0: coordinate out of key range)
+    int      opt[LB2_OPT_COUNT];   // kernel-selection options (lb2_set_option)
+    uint32_t configured;    // bit per kernel whose max-dynamic-shared-memory attribute has been set on this handle's device
     char     err[512];
 };
+
+// kernels that need more than 48 KB of dynamic shared memory: the attribute is per-device state, the handle is per device
+enum { LB2_K_TC = 0, LB2_K_TC2, LB2_K_TC3, LB2_K_TC4, LB2_K_TC5_256, LB2_K_TC5_128, LB2_K_SCATTER, LB2_K_NN_TABLE };
+template <class K>
+static inline cudaError_t lb2_configure_smem(Lb2Handle* h, int bit, K kernel, int bytes) {
+    if (h->configured & (1u << bit)) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) h->configured |= 1u << bit;
+    return e;
+}
 
 static inline int lb2_fail(Lb2Handle* h, int code, const char* fmt, const char* a = "", const char* b = "") {
     if (h) snprintf(h->err, sizeof(h->err), fmt, a, b);

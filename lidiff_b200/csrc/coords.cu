@@ -5,6 +5,7 @@
 // Stands behind ME.TensorField.sparse() / ME coordinate manager as used at
 // /root/reference/lidiff/tools/diff_completion_pipeline.py:68-84,149 and lidiff/models/minkunet.py:17-24,36-42,135.
 #include "common.cuh"
+#include <stdlib.h>
 #include <limits.h>
 #include <algorithm>
 
@@ -23,7 +24,17 @@ extern "C" int lb2_create(int device, void** handle) {
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return LB2_ERR_CUDA;
     if (prop.major != 10) return LB2_ERR_UNSUP;          // sm_100a binary only
     Lb2Handle* h = new Lb2Handle();
-    h->device = device; h->num_sms = prop.multiProcessorCount; h->launches = 0; h->err[0] = 0;
+    h->device = device; h->num_sms = prop.multiProcessorCount; h->launches = 0; h->err[0] = 0; h->configured = 0;
+    {
+        auto env = [](const char* name, int dflt) { const char* e = getenv(name); return (e && e[0]) ? atoi(e) : dflt; };
+        h->opt[LB2_OPT_TC_PAIR] = env("LB2_TC_PAIR", 1);
+        h->opt[LB2_OPT_TC_N256] = env("LB2_TC_N256", 1);
+        h->opt[LB2_OPT_TC_SMALL] = env("LB2_TC_SMALL", 1);
+        h->opt[LB2_OPT_TC_PERSISTENT] = env("LB2_TC_PERSISTENT", 1);
+        const char* lag = getenv("LB2_TC_LAG");
+        h->opt[LB2_OPT_TC_FULL_LAG] = (lag && lag[0] == 'f') ? 1 : 0;
+        h->opt[LB2_OPT_TC_NSPLIT] = env("LB2_TC_NSPLIT", 0);
+    }
     if (cudaMalloc(&h->d_status, sizeof(int32_t)) != cudaSuccess) { delete h; return LB2_ERR_CUDA; }
     cudaMemset(h->d_status, 0, sizeof(int32_t));
     *handle = h;
@@ -35,6 +46,19 @@ extern "C" void lb2_destroy(void* handle) {
     if (!h) return;
     cudaFree(h->d_status);
     delete h;
+}
+
+extern "C" int lb2_set_option(void* handle, int option, int value) {
+    Lb2Handle* h = (Lb2Handle*)handle;
+    LB2_REQUIRE(h, h && option >= 0 && option < LB2_OPT_COUNT, "set_option");
+    h->opt[option] = value;
+    return LB2_OK;
+}
+
+extern "C" int lb2_get_option(void* handle, int option) {
+    Lb2Handle* h = (Lb2Handle*)handle;
+    if (!h || option < 0 || option >= LB2_OPT_COUNT) return LB2_ERR_ARG;
+    return h->opt[option];
 }
 
 extern "C" const char* lb2_last_error(void* handle) {

@@ -352,11 +352,9 @@ extern "C" int lb2_nn_match_table(void* handle, void* stream, const int32_t* q_c
     Lb2Handle* h = (Lb2Handle*)handle;
     LB2_REQUIRE(h, h && q_coords && k_coords && idx && table && nq_cap > 0 && nk_cap > 0, "nn_match_table");
     LB2_REQUIRE(h, key_stride > 0 && key_stride % 2 == 0 && max_ring >= 0 && max_ring <= 16, "nn_match_table stride/ring");
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_nn_match_table, cudaFuncAttributeMaxDynamicSharedMemorySize, NNT_SLOTS * 12);
+    {
+        cudaError_t e = lb2_configure_smem(h, LB2_K_NN_TABLE, k_nn_match_table, NNT_SLOTS * 12);
         if (e != cudaSuccess) return lb2_fail(h, LB2_ERR_CUDA, "k_nn_match_table smem attribute: %s", cudaGetErrorString(e));
-        configured = true;
     }
     const unsigned long long* tk = (const unsigned long long*)table;
     const int* tr = (const int*)(tk + NNT_SLOTS);
@@ -521,7 +519,8 @@ __global__ void k_guidance_dpm(const float* __restrict__ eps_c, const float* __r
         const double d1 = __dmul_rn(cf.inv_r0, __dsub_rn(x0, x0_state[t]));
         prev = __dadd_rn(prev, __dmul_rn(0.5 * cf.c_x0, d1));
     }
-    prev = __dadd_rn(prev, __dmul_rn(cf.c_noise, (double)noise[t]));
+    // diffusers draws the SDE noise in the model output's dtype (fp32): sigma_t*sqrt(..) * noise is an fp32 product, promoted on the add
+    prev = __dadd_rn(prev, (double)__fmul_rn((float)cf.c_noise, noise[t]));
     x0_state[t] = x0;
     // pipeline:163-164  x_t = x_init + prev ; batched_coordinates(dtype=float32)
     const float xn = __double2float_rn(__dadd_rn(x_init[t], prev));

@@ -361,11 +361,9 @@ extern "C" int lb2_spconv_scatter(void* handle, void* stream, const lb2_scatter_
             LB2_POST_LAUNCH(h, "k_zero_rows");
         }
     }
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(sc::k_spconv_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024 - 256));   // 224 B of static smem
+    {
+        cudaError_t e = lb2_configure_smem(h, LB2_K_SCATTER, sc::k_spconv_scatter, (int)(227 * 1024 - 256));   // 224 B of static smem
         if (e != cudaSuccess) return lb2_fail(h, LB2_ERR_CUDA, "k_spconv_scatter smem attribute: %s", cudaGetErrorString(e));
-        configured = true;
     }
     sc::k_spconv_scatter<<<h->num_sms, sc::THREADS, sc::smem_bytes(d->c1 + d->c2, d->cout, stages), s>>>(p);
     LB2_POST_LAUNCH(h, "k_spconv_scatter");

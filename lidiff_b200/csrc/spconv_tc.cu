@@ -415,24 +415,18 @@ extern "C" int lb2_pack_weights(void* handle, void* stream, const float* weight,
     return LB2_OK;
 }
 
-static bool tc_nsplit_enabled() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("LB2_TC_NSPLIT"); v = (e && e[0] == '1') ? 1 : 0; }   // measured slower (A gathered twice): off
-    return v == 1;
-}
 
 int lb2_spconv_tc2_launch(Lb2Handle* h, cudaStream_t s, const lb2_conv_desc* d, int step_budget);
-bool lb2_tc_persistent_enabled();
 
 int lb2_spconv_tc_launch(Lb2Handle* h, cudaStream_t s, const lb2_conv_desc* d, bool persistent) {
-    if (persistent && lb2_tc_persistent_enabled()) return lb2_spconv_tc2_launch(h, s, d, tc::STEP_BUDGET);
+    if (persistent && h->opt[LB2_OPT_TC_PERSISTENT]) return lb2_spconv_tc2_launch(h, s, d, tc::STEP_BUDGET);
     tc::Params p;
     p.c1 = d->c1; p.c2 = d->c2; p.cout = d->cout; p.kvol = d->kvol;
     p.wpacked = (const unsigned char*)d->weight_packed;
     p.scale = d->scale; p.shift = d->shift; p.relu = d->relu;
     p.nbr = d->nbr; p.nbr_stride = d->nbr_stride; p.d_mout = d->d_mout; p.mout_cap = d->mout_cap; p.row_perm = d->row_perm;
     p.nchunks = (d->c1 + d->c2 + tc::KC - 1) / tc::KC;
-    const int nsplit = (d->cout == 256 && tc_nsplit_enabled()) ? 2 : 1;     // 256 channels: two CTAs of 128 (drain overlap, 3 stages)
+    const int nsplit = (d->cout == 256 && h->opt[LB2_OPT_TC_NSPLIT]) ? 2 : 1;   // measured slower (A gathered twice): off by default     // 256 channels: two CTAs of 128 (drain overlap, 3 stages)
     p.ncta = d->cout / nsplit;
     int stages = tc::MAX_STAGES;
     while (stages > 1 && tc::smem_bytes(p.ncta, stages) > 227 * 1024) --stages;
@@ -446,11 +440,9 @@ int lb2_spconv_tc_launch(Lb2Handle* h, cudaStream_t s, const lb2_conv_desc* d, b
     p.group = std::max(1, tc::STEP_BUDGET / steps_per_offset);
     p.io[0] = d->io[0]; p.io[1] = d->io[d->npass > 1 ? 1 : 0];
     const size_t smem = tc::smem_bytes(p.ncta, stages);
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(tc::k_spconv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    {
+        cudaError_t e = lb2_configure_smem(h, LB2_K_TC, tc::k_spconv_tc, (int)(227 * 1024));
         if (e != cudaSuccess) return lb2_fail(h, LB2_ERR_CUDA, "k_spconv_tc smem attribute: %s", cudaGetErrorString(e));
-        configured = 227 * 1024;
     }
     dim3 grid(cdiv(d->mout_cap, tc::BM), d->npass, nsplit);
     tc::k_spconv_tc<<<grid, tc::THREADS, smem, s>>>(p);

@@ -391,24 +391,19 @@ static size_t smem_bytes(int cout, int stages) {
 
 }  // namespace tc2
 
-bool lb2_tc_persistent_enabled() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("LB2_TC_PERSISTENT"); v = (e && e[0] == '0') ? 0 : 1; }
-    return v == 1;
-}
 
 bool lb2_spconv_tc3_supported(const lb2_conv_desc* d);
 int lb2_spconv_tc3_launch(Lb2Handle* h, cudaStream_t s, const lb2_conv_desc* d, int step_budget);
 bool lb2_spconv_tc4_supported(const lb2_conv_desc* d);
 int lb2_spconv_tc4_launch(Lb2Handle* h, cudaStream_t s, const lb2_conv_desc* d, int step_budget);
+bool lb2_spconv_tc5_supported(const lb2_conv_desc* d);
+int lb2_spconv_tc5_launch(Lb2Handle* h, cudaStream_t s, const lb2_conv_desc* d, int step_budget);
 
 int lb2_spconv_tc2_launch(Lb2Handle* h, cudaStream_t s, const lb2_conv_desc* d, int step_budget) {
-    static int use_n256 = -1;
-    if (use_n256 < 0) { const char* e = getenv("LB2_TC_N256"); use_n256 = (e && e[0] == '0') ? 0 : 1; }
-    if (use_n256 && lb2_spconv_tc3_supported(d)) return lb2_spconv_tc3_launch(h, s, d, step_budget);
-    static int use_small = -1;
-    if (use_small < 0) { const char* e = getenv("LB2_TC_SMALL"); use_small = (e && e[0] == '0') ? 0 : 1; }
-    if (use_small && lb2_spconv_tc4_supported(d)) return lb2_spconv_tc4_launch(h, s, d, step_budget);
+    const int use_pair = h->opt[LB2_OPT_TC_PAIR];           // CTA-pair kernel (cta_group::2): 0 off, 1 = Cout 256 only, 2 = Cout 256 and 128
+    if (use_pair && (d->cout == 256 || use_pair >= 2) && lb2_spconv_tc5_supported(d)) return lb2_spconv_tc5_launch(h, s, d, step_budget);
+    if (h->opt[LB2_OPT_TC_N256] && lb2_spconv_tc3_supported(d)) return lb2_spconv_tc3_launch(h, s, d, step_budget);
+    if (h->opt[LB2_OPT_TC_SMALL] && lb2_spconv_tc4_supported(d)) return lb2_spconv_tc4_launch(h, s, d, step_budget);
     tc2::Params p;
     p.c1 = d->c1; p.c2 = d->c2; p.cout = d->cout; p.kvol = d->kvol; p.npass = d->npass;
     p.wpacked = (const unsigned char*)d->weight_packed;
@@ -419,9 +414,7 @@ int lb2_spconv_tc2_launch(Lb2Handle* h, cudaStream_t s, const lb2_conv_desc* d, 
     while (stages > 1 && tc2::smem_bytes(d->cout, stages) > 227 * 1024) --stages;
     p.stages = stages;
     {   // LB2_TC_LAG=full restores the S-1 lookahead (development A/B knob)
-        static int full_lag = -1;
-        if (full_lag < 0) { const char* e = getenv("LB2_TC_LAG"); full_lag = (e && e[0] == 'f') ? 1 : 0; }
-        p.lag = (stages >= 3 && !full_lag) ? stages - 2 : stages - 1;
+        p.lag = (stages >= 3 && !h->opt[LB2_OPT_TC_FULL_LAG]) ? stages - 2 : stages - 1;
     }
     const int half = d->cout <= 32 ? 32 : d->cout <= 64 ? 64 : d->cout <= 128 ? 128 : 256;
     p.nbuf = half <= 128 ? 2 : 1;
@@ -432,11 +425,9 @@ int lb2_spconv_tc2_launch(Lb2Handle* h, cudaStream_t s, const lb2_conv_desc* d, 
     p.group = std::max(1, step_budget / steps_per_offset);
     p.io[0] = d->io[0]; p.io[1] = d->io[d->npass > 1 ? 1 : 0];
     const size_t smem = tc2::smem_bytes(d->cout, stages);
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(tc2::k_spconv_tc_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    {
+        cudaError_t e = lb2_configure_smem(h, LB2_K_TC2, tc2::k_spconv_tc_persist, (int)(227 * 1024));
         if (e != cudaSuccess) return lb2_fail(h, LB2_ERR_CUDA, "k_spconv_tc_persist smem attribute: %s", cudaGetErrorString(e));
-        configured = true;
     }
     const long long tiles_cap = (long long)cdiv(d->mout_cap, tc::BM) * d->npass;
     const unsigned grid = (unsigned)std::min<long long>(h->num_sms, tiles_cap);

@@ -428,11 +428,9 @@ int lb2_spconv_tc3_launch(Lb2Handle* h, cudaStream_t s, const lb2_conv_desc* d, 
     p.group = std::max(1, step_budget / steps_per_offset);
     p.io[0] = d->io[0]; p.io[1] = d->io[d->npass > 1 ? 1 : 0];
     const size_t smem = tc3::smem_bytes();
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(tc3::k_spconv_tc_n256, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    {
+        cudaError_t e = lb2_configure_smem(h, LB2_K_TC3, tc3::k_spconv_tc_n256, (int)(227 * 1024));
         if (e != cudaSuccess) return lb2_fail(h, LB2_ERR_CUDA, "k_spconv_tc_n256 smem attribute: %s", cudaGetErrorString(e));
-        configured = true;
     }
     const long long tiles_cap = (long long)cdiv(d->mout_cap, tc::BM) * d->npass;
     const unsigned grid = (unsigned)std::min<long long>(h->num_sms, tiles_cap);

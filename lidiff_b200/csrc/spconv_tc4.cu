@@ -443,14 +443,13 @@ int lb2_spconv_tc4_launch(Lb2Handle* h, cudaStream_t s, const lb2_conv_desc* d, 
     p.group = std::max(1, step_budget / steps_per_offset);
     p.io[0] = d->io[0]; p.io[1] = d->io[d->npass > 1 ? 1 : 0];
     const size_t smem = tc4::smem_bytes(d->cout);
-    static bool configured = false;
-    if (!configured) {
+    if (!(h->configured & (1u << LB2_K_TC4))) {
         cudaError_t e = cudaFuncSetAttribute(tc4::k_spconv_tc_small<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
         if (e == cudaSuccess) e = cudaFuncSetAttribute(tc4::k_spconv_tc_small<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
         if (e == cudaSuccess) e = cudaFuncSetAttribute(tc4::k_spconv_tc_small<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
         if (e == cudaSuccess) e = cudaFuncSetAttribute(tc4::k_spconv_tc_small<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
         if (e != cudaSuccess) return lb2_fail(h, LB2_ERR_CUDA, "k_spconv_tc_small smem attribute: %s", cudaGetErrorString(e));
-        configured = true;
+        h->configured |= 1u << LB2_K_TC4;
     }
     const long long tiles_cap = (long long)cdiv(d->mout_cap, tc::BM) * d->npass;
     const unsigned grid = (unsigned)std::min<long long>(h->num_sms, tiles_cap);

@@ -236,6 +236,7 @@ class DenoiseEngine:
         self.pair_hist = None            # (steps, 18) int64 device tensor when enabled
         self._hist_row = 0
         self._conv_counter = 0
+        self._have_x0 = False            # the multistep state (x0_state buffer) holds a prediction of an earlier step
         self._prepare_time_tables()
         self._prepare_uncond()
 
@@ -538,15 +539,20 @@ class DenoiseEngine:
             self._linear(y4[p], self.head[0], hid, act=1, m_cap=N, d_m=g.d_n[0])
             self._linear(hid, self.head[1], eps[p], m_cap=N, d_m=g.d_n[0])
         c = self.sched.coefficients(i)
-        second = i > 0 and not (i == self.T - 1 and self.T < 15)
-        cf = DpmCoef(c["c_sample"], c["c_x0"], c["c_noise"], c["sigma_s"], c["alpha_s"], c.get("inv_r0", 0.0) if second else 0.0,
+        # diffusers: second order once one x0 prediction is stored (lower_order_nums >= 1), also at step 0 of a later scan
+        second = self._have_x0 and not (i == self.T - 1 and self.T < 15)
+        self._have_x0 = True
+        cf = DpmCoef(c["c_sample"], c["c_x0"], c["c_noise"], c["sigma_s"], c["alpha_s"], c["inv_r0"] if second else 0.0,
                      self.w, self.resolution, 1 if second else 0, self.div_mode, 1)
         h.guidance_dpm_step(eps[0], eps[1], g.inv[0], x_t, x_init, noise_i, x0_state, N, cf, eps_out, x_next, coords_next)
 
     # ---- the loop (completion_loop, pipeline:155-169) -----------------------------------------------------------
-    def start(self, x_init: torch.Tensor, x_feats: torch.Tensor):
-        """condition on the scan and load the noisy start; returns the loop state dict"""
+    def start(self, x_init: torch.Tensor, x_feats: torch.Tensor, fresh: bool = True):
+        """condition on the scan and load the noisy start; returns the loop state dict.  fresh=False keeps the multistep
+        state (last x0 prediction) of the previous trajectory like the reference's never-reset scheduler does."""
         dev, N = self.device, self.N
+        if fresh:
+            self._have_x0 = False
         x_init = x_init.reshape(-1, 3).to(device=dev, dtype=torch.float64).contiguous()
         assert x_init.shape[0] == N, f"engine built for {N} points, got {x_init.shape[0]}"
         self.set_condition(x_init)
@@ -571,10 +577,10 @@ class DenoiseEngine:
         if host_out is not None:
             host_out.copy_(st["xa"], non_blocking=True)
 
-    def run(self, x_init: torch.Tensor, x_feats: torch.Tensor, step_noise=None, n_steps=None, return_device=False):
+    def run(self, x_init: torch.Tensor, x_feats: torch.Tensor, step_noise=None, n_steps=None, return_device=False, fresh=True):
         """x_init (1,N,3) fp64 conditioning scan, x_feats (1,N,3) noisy start.  Returns final x_t.F (N,3)."""
         dev, N = self.device, self.N
-        st = self.start(x_init, x_feats)
+        st = self.start(x_init, x_feats, fresh=fresh)
         T = self.T if n_steps is None else n_steps
         if step_noise is None:
             step_noise = torch.randn((T, N, 3), device=dev)

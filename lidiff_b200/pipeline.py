@@ -118,19 +118,22 @@ class DiffCompletion(nn.Module):
         return post_scan[(post_scan[:, 2] < max_z) & (post_scan[:, 2] > min_z)]
 
     # ---- reference: complete_scan :117-132 --------------------------------------------------------
-    def complete_scan(self, scan, start_noise=None, step_noise=None, preprocessed=False):
+    def complete_scan(self, scan, start_noise=None, step_noise=None, preprocessed=False, fresh=False):
+        """fresh=False (default) keeps the scheduler's multistep state between scans like the reference does (its main loop,
+        :213-222, never calls set_timesteps again: the first update of every scan after the first is second-order against the
+        previous scan's last x0); fresh=True starts a new trajectory."""
         scan = scan if preprocessed else self.preprocess_scan(scan)
         scan = scan.to(self.device)
         if start_noise is None:
             start_noise = torch.randn(scan.shape, device=self.device)
         x_feats = scan + start_noise.to(self.device)
         if self.use_engine:
-            completed_scan = self.engine().run(scan, x_feats, step_noise)
+            completed_scan = self.engine().run(scan, x_feats, step_noise, fresh=fresh)
         else:
             x_full = self.points_to_tensor(x_feats)
             x_cond = self.points_to_tensor(scan)
             x_uncond = self.points_to_tensor(torch.zeros_like(scan))
-            completed_scan = self.completion_loop(scan, x_full, x_cond, x_uncond, step_noise)
+            completed_scan = self.completion_loop(scan, x_full, x_cond, x_uncond, step_noise, fresh=fresh)
         post_scan = self.postprocess_scan(completed_scan, scan)
         refine_in = self.points_to_tensor(torch.as_tensor(post_scan)[None, :, :])
         offset = self.refine_forward(refine_in).reshape(-1, 6, 3)
@@ -154,9 +157,10 @@ class DiffCompletion(nn.Module):
         return x_uncond + self.w_uncond * (x_cond - x_uncond)
 
     # ---- reference: completion_loop :155-169 ------------------------------------------------------
-    def completion_loop(self, x_init, x_t, x_cond, x_uncond, step_noise=None, n_steps=None):
+    def completion_loop(self, x_init, x_t, x_cond, x_uncond, step_noise=None, n_steps=None, fresh=False):
         self.scheduler_to_cuda()
-        self.dpm_scheduler.set_timesteps(self.dpm_scheduler.num_inference_steps, device=self.device)
+        if fresh:
+            self.dpm_scheduler.set_timesteps(self.dpm_scheduler.num_inference_steps, device=self.device)
         T = len(self.dpm_scheduler.timesteps) if n_steps is None else n_steps
         for i in range(T):
             t = self.dpm_scheduler.timesteps[i][None]

@@ -62,9 +62,12 @@ class DPMSolverMultistepScheduler:
                  c_x0=alpha[t_prev] * (1 - torch.exp(-2.0 * h)),
                  c_noise=sigma[t_prev] * torch.sqrt(1.0 - torch.exp(-2.0 * h)),
                  sigma_s=sigma[t], alpha_s=alpha[t])
-        if step_index > 0:
-            h0 = lam[t] - lam[ts[step_index - 1]]
-            c["inv_r0"] = 1.0 / (h0 / h)
+        # second-order term: s1 = timesteps[step_index - 1].  At step_index 0 the Python index wraps to timesteps[-1], which is
+        # what diffusers 0.18 evaluates when step() is called for a second trajectory without a new set_timesteps() (the
+        # reference's main loop does exactly that for every scan after the first, pipeline:213-222): the previous scan's last
+        # x0 prediction enters the first update with weight 0.5*c_x0/r0.
+        h0 = lam[t] - lam[ts[step_index - 1]]
+        c["inv_r0"] = 1.0 / (h0 / h)
         return {k: float(v) for k, v in c.items()}
 
     def step_index_of(self, timestep) -> int:
@@ -86,9 +89,8 @@ class DPMSolverMultistepScheduler:
         second = self.use_second_order(i)
         self.model_outputs[0] = self.model_outputs[1]
         self.model_outputs[1] = x0
-        if noise is None:
-            noise = torch.randn(x0.shape, generator=generator, device=dev, dtype=x0.dtype)
-        noise = noise.to(x0.dtype)
+        if noise is None:       # diffusers draws the SDE noise in the model output's dtype (fp32 here), not in x0's (fp64)
+            noise = torch.randn(model_output.shape, generator=generator, device=dev, dtype=model_output.dtype)
         prev = f32(c["c_sample"]) * sample + f32(c["c_x0"]) * x0
         if second:
             d1 = f32(c["inv_r0"]) * (x0 - self.model_outputs[0])

@@ -56,10 +56,12 @@ class DPMSolverSDE2M:
             c_noise=sigma_tp * torch.sqrt(1.0 - torch.exp(-2.0 * h)),
             sigma_s=sigma_s, alpha_s=self.alpha_t[t], h=h,
         )
-        if step_index > 0:
-            s1 = self.timesteps[step_index - 1]
-            h0 = lam_s - self.lambda_t[s1]
-            c["r0"] = h0 / h
+        # s1 = timesteps[step_index - 1]; at step_index 0 the index wraps to timesteps[-1] exactly as in diffusers 0.18 when
+        # step() is called for a second trajectory without set_timesteps() (the reference never resets between scans,
+        # tools/diff_completion_pipeline.py:213-222 -> :155-169)
+        s1 = self.timesteps[step_index - 1]
+        h0 = lam_s - self.lambda_t[s1]
+        c["r0"] = h0 / h
         return c
 
     def step(self, eps: torch.Tensor, timestep, sample: torch.Tensor, noise: torch.Tensor):
@@ -72,7 +74,7 @@ class DPMSolverSDE2M:
         self.model_outputs[0] = self.model_outputs[1]
         self.model_outputs[1] = x0
         c = self.coefficients(i)
-        noise = noise.to(x0.dtype)
+        # diffusers draws the SDE noise in the model output's dtype (fp32): the noise term is an fp32 product, promoted on the add
         if self.lower_order_nums < 1 or lower_order_final:
             prev = c["c_sample"] * sample + c["c_x0"] * x0 + c["c_noise"] * noise
         else:

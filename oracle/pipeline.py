@@ -63,9 +63,12 @@ class DiffCompletionOracle:
         return e_u + self.w_uncond * (e_c - e_u)
 
     # pipeline:155-169
-    def completion_loop(self, x_init, x_t, x_cond, x_uncond, step_noise, n_steps=None):
-        """x_init (B,N,3) f64 (pipeline) or f32 (models.py twin); step_noise (T,B,N,3) f32."""
-        self.dpm.set_timesteps(self.dpm.num_inference_steps)
+    def completion_loop(self, x_init, x_t, x_cond, x_uncond, step_noise, n_steps=None, fresh=True):
+        """x_init (B,N,3) f64 (pipeline) or f32 (models.py twin); step_noise (T,B,N,3) f32.
+        fresh=False keeps the multistep state of the previous trajectory, which is what the reference does for every scan
+        after the first (its main loop never calls set_timesteps again)."""
+        if fresh:
+            self.dpm.set_timesteps(self.dpm.num_inference_steps)
         T = len(self.dpm.timesteps) if n_steps is None else n_steps
         hist = []
         for i in range(T):
@@ -89,12 +92,12 @@ class DiffCompletionOracle:
         return post[(post[:, 2] < max_z) & (post[:, 2] > min_z)]
 
     # pipeline:117-132 (after preprocess_scan); `scan` (1,N,3) f64, noises explicit
-    def complete_scan(self, scan: torch.Tensor, start_noise: torch.Tensor, step_noise: torch.Tensor):
+    def complete_scan(self, scan: torch.Tensor, start_noise: torch.Tensor, step_noise: torch.Tensor, fresh=True):
         x_feats = scan + start_noise
         x_full = self.points_to_tensor(x_feats)
         x_cond = self.points_to_tensor(scan)
         x_uncond = self.points_to_tensor(torch.zeros_like(scan))
-        completed = self.completion_loop(scan, x_full, x_cond, x_uncond, step_noise)
+        completed = self.completion_loop(scan, x_full, x_cond, x_uncond, step_noise, fresh=fresh)
         post = self.postprocess_scan(completed, scan)
         refine_in = self.points_to_tensor(torch.from_numpy(post)[None, :, :])
         offset = self.refine.unet_refine(refine_in).reshape(-1, 6, 3)

@@ -298,7 +298,7 @@ class FakeHandle:
         prev = f32(cf.c_sample) * sample + f32(cf.c_x0) * x0
         if cf.second_order:
             prev = prev + 0.5 * f32(cf.c_x0) * (f32(cf.inv_r0) * (x0 - x0_state[:n]))
-        prev = prev + f32(cf.c_noise) * noise[:n].double()
+        prev = prev + f32(cf.c_noise) * noise[:n].float()       # fp32 product (diffusers: fp32 noise), then promoted
         x0_state[:n] = x0
         xn = (x_init[:n] + prev).float()
         x_next[:n] = xn

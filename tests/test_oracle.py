@@ -67,7 +67,7 @@ def test_first_step_is_closed_form():
     G = GOLD["step_999_979"]
     a, sg = GOLD["tables"]["999"]["alpha_t"], GOLD["tables"]["999"]["sigma_t"]
     x0 = (s - (torch.tensor(sg, dtype=torch.float32) * eps)) / torch.tensor(a, dtype=torch.float32)
-    ref = G["c_sample"] * s + G["c_x0"] * x0 + G["c_noise"] * z.double()
+    ref = G["c_sample"] * s + G["c_x0"] * x0 + (torch.tensor(G["c_noise"], dtype=torch.float32) * z).double()   # fp32 noise term (diffusers)
     assert torch.allclose(out, ref, rtol=0, atol=1e-12)
 
 
