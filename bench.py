@@ -184,7 +184,7 @@ def run_ours(args, rank, world, local_rank):
     # ---- timed region 1: inputs resident in HBM, no instrumentation -----------------------------------------------------
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    l0 = h.launch_count()
+    l0 = eng.launches()
     with ClockSampler(local_rank) as clocks:
         e0.record()
         for i in steps:
@@ -192,7 +192,7 @@ def run_ours(args, rank, world, local_rank):
             eng.advance(st, noise[i])
         e1.record()
         barrier()
-    launches = h.launch_count() - l0
+    launches = eng.launches() - l0
     ms = e0.elapsed_time(e1)
     log(f"timed region: {K} steps in {ms:.1f} ms")
     if h.read_status() & 1:

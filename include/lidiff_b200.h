@@ -136,6 +136,9 @@ typedef struct {
     const void*    in2_h;       /* (rows_in, 2*c2) fp16 or NULL */
     void*          out_h;       /* (m, 2*cout) fp16 or NULL */
     void*          out_gated_h; /* (m, 2*cout) fp16 or NULL */
+    /* An activation may exist as its companion only: in1/in2 may be NULL when in1_h/in2_h are given (tensor-core variants), out /
+       out_gated may be NULL when out_h / out_gated_h are given, and the residual may be read from a companion (hi + lo): */
+    const void*    residual_h;  /* (m, 2*cout) fp16 or NULL; used when residual == NULL */
 } lb2_conv_io;
 
 typedef struct {
@@ -242,7 +245,7 @@ int lb2_linear(void* h, void* stream, const float* x, int64_t ldx, const float* 
                const float* prebias, int32_t pre_act);
 
 /* x * w row-gather multiply (`x0*w0`, minkunet.py:431...): out[r] = x[r] * table[idx ? idx[r] : 0];
- * out_h: optional fp16 split companion of out (see lb2_conv_io). */
+ * out_h: optional fp16 split companion of out (see lb2_conv_io); out may be NULL when out_h is given. */
 int lb2_gate_mul(void* h, void* stream, const float* x, const float* table, const int32_t* idx,
                  const int32_t* d_m, int32_t m_cap, int32_t c, float* out, void* out_h);
 

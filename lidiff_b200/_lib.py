@@ -25,7 +25,8 @@ class Grid(C.Structure):
 class ConvIO(C.Structure):
     _fields_ = [("in1", C.c_void_p), ("in2", C.c_void_p), ("residual", C.c_void_p), ("out", C.c_void_p),
                 ("gate_table", C.c_void_p), ("gate_idx", C.c_void_p), ("out_gated", C.c_void_p), ("pre_add", C.c_void_p),
-                ("in1_h", C.c_void_p), ("in2_h", C.c_void_p), ("out_h", C.c_void_p), ("out_gated_h", C.c_void_p)]
+                ("in1_h", C.c_void_p), ("in2_h", C.c_void_p), ("out_h", C.c_void_p), ("out_gated_h", C.c_void_p),
+                ("residual_h", C.c_void_p)]
 
 
 class ConvDesc(C.Structure):
@@ -253,9 +254,10 @@ class Handle:
         self._check(self.dll.lb2_nn_table_build(self.hp, self._stream(), _ptr(k), _ptr(d_nk), int(nk_cap), _ptr(t)), "lb2_nn_table_build")
         return t
 
-    def nn_tree(self, k, d_nk, nk_cap):
-        """bounding-box hierarchy over the key voxels for nn_match_tree (one per conditioning scan)"""
-        t = torch.empty(int(self.dll.lb2_nn_tree_bytes(int(nk_cap))), dtype=torch.uint8, device=self.device)
+    def nn_tree(self, k, d_nk, nk_cap, out=None):
+        """bounding-box hierarchy over the key voxels for nn_match_tree (one per conditioning scan); `out` re-uses a buffer"""
+        nbytes = int(self.dll.lb2_nn_tree_bytes(int(nk_cap)))
+        t = out if (out is not None and out.numel() == nbytes) else torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         self._check(self.dll.lb2_nn_tree_build(self.hp, self._stream(), _ptr(k), _ptr(d_nk), int(nk_cap), _ptr(t)), "lb2_nn_tree_build")
         return t
 

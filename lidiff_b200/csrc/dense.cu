@@ -456,7 +456,7 @@ __global__ void k_gate_mul(const float* __restrict__ x, const float* __restrict_
     const int r = (int)(t / c), j = (int)(t % c);
     const int g = idx ? __ldg(idx + r) : 0;
     const float y = x[t] * __ldg(table + (long long)g * c + j);
-    out[t] = y;
+    if (out) out[t] = y;
     if (out_h) {
         __half hi, lo;
         tc::split1(y, hi, lo);
@@ -468,7 +468,7 @@ __global__ void k_gate_mul(const float* __restrict__ x, const float* __restrict_
 extern "C" int lb2_gate_mul(void* handle, void* stream, const float* x, const float* table, const int32_t* idx,
                             const int32_t* d_m, int32_t m_cap, int32_t c, float* out, void* out_h) {
     Lb2Handle* h = (Lb2Handle*)handle;
-    LB2_REQUIRE(h, h && x && table && out && m_cap > 0 && c > 0, "gate_mul");
+    LB2_REQUIRE(h, h && x && table && (out || out_h) && m_cap > 0 && c > 0, "gate_mul");
     k_gate_mul<<<cdiv((long long)m_cap * c, 256), 256, 0, (cudaStream_t)stream>>>(x, table, idx, d_m, m_cap, c, out, (__half*)out_h);
     LB2_POST_LAUNCH(h, "k_gate_mul");
     return LB2_OK;

@@ -152,6 +152,10 @@ __global__ void __launch_bounds__(FF_THREADS) k_spconv_ffma(const FfmaParams p) 
             if (io.pre_add) y += __ldg(io.pre_add + ro + col);
             if (p.scale) y = fmaf(y, __ldg(p.scale + col), __ldg(p.shift + col));
             if (io.residual) y += __ldg(io.residual + ro + col);
+            else if (io.residual_h) {
+                const __half* rp = reinterpret_cast<const __half*>(io.residual_h) + 2 * ro + col;
+                y += __half2float(__ldg(rp)) + __half2float(__ldg(rp + p.cout));
+            }
             if (p.relu) y = fmaxf(y, 0.f);
             yv[j] = y;
             gv[j] = gate_row ? y * __ldg(gate_row + col) : y;

@@ -289,8 +289,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc(const Params p) {
                 const float4 h4 = __ldg(reinterpret_cast<const float4*>(p.shift + col));
                 y[0] = fmaf(y[0], s4.x, h4.x); y[1] = fmaf(y[1], s4.y, h4.y); y[2] = fmaf(y[2], s4.z, h4.z); y[3] = fmaf(y[3], s4.w, h4.w);
             }
-            if (io.residual) {
-                const float4 t4 = __ldg(reinterpret_cast<const float4*>(io.residual + ro + col));
+            if (io.residual || io.residual_h) {
+                const float4 t4 = load_residual4(io.residual, io.residual_h, orow, p.cout, col);
                 y[0] += t4.x; y[1] += t4.y; y[2] += t4.z; y[3] += t4.w;
             }
             if (p.relu) {

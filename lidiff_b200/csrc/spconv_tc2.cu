@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_persist(const Params p
                             if (orows[i] >= 0) {
                                 const long long ro = (long long)orows[i] * p.cout + col;
                                 if (io.pre_add) pre[i] = __ldg(reinterpret_cast<const float4*>(io.pre_add + ro));
-                                if (io.residual) res[i] = __ldg(reinterpret_cast<const float4*>(io.residual + ro));
+                                res[i] = load_residual4(io.residual, io.residual_h, orows[i], p.cout, col);
                                 if (io.gate_table) gat[i] = __ldg(reinterpret_cast<const float4*>(io.gate_table + (long long)gidx[i] * p.cout + col));
                             }
                         }

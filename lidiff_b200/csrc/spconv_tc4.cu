@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_small(const Params p) 
                     if (orow >= 0) {
                         const long long ro = (long long)orow * p.cout + col;
                         if (io.pre_add) pre[u] = __ldg(reinterpret_cast<const float4*>(io.pre_add + ro));
-                        if (io.residual) res[u] = __ldg(reinterpret_cast<const float4*>(io.residual + ro));
+                        res[u] = load_residual4(io.residual, io.residual_h, orow, p.cout, col);
                         if (io.gate_table) gat[u] = __ldg(reinterpret_cast<const float4*>(io.gate_table + (long long)grow[rr] * p.cout + col));
                     }
                 }

@@ -66,16 +66,15 @@ __device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("m
 __device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {
     uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank)); return r;
 }
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {      // release at cluster scope: orders this thread's prior writes
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+// Arrive on a barrier of the leader CTA (address from mapa).  Default semantics (release at CTA scope) as in CUTLASS' ClusterBarrier:
+// the .release.cluster / .acquire.cluster forms compile to MEMBAR.ALL.GPU + CCTL.IVALL around every arrive / poll (measured: the
+// kernel ran 2x slower).  What the consumer (the pair's tensor cores, async proxy) needs is that the producer's cp.async writes have
+// landed in its shared memory and are visible to the async proxy: cp.async.wait_group + fence.proxy.async by the writing thread
+// before the arrive give exactly that; shared memory has no cache between the SM and the tensor-core read path.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {   // acquire at cluster scope (arrivals come from the peer CTA)
-    uint32_t ok = 0;
-    while (!ok) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    }
-}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -208,7 +207,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_spconv
                 for (int c2 = 0; c2 < 2 * p.nchunks; ++c2, ++it, ri.next()) {      // c2 = 2 * chunk + half
                     if (it >= A_LAG) {                                  // publish the slot issued A_LAG iterations ago BEFORE waiting for a free one
                         cp_async_wait<A_LAG - 1>();
-                        asm volatile("fence.proxy.async;" ::: "memory");
+                        fence_proxy_async();
                         mbar_arrive_cluster(leader_full_a0 + 8u * ra.s);
                         ra.next();
                         ++arrived;
@@ -237,7 +236,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_spconv
             }
         }
         cp_async_wait<0>();
-        asm volatile("fence.proxy.async;" ::: "memory");
+        fence_proxy_async();
         for (; arrived < it; ++arrived, ra.next()) mbar_arrive_cluster(leader_full_a0 + 8u * ra.s);
     } else if (warp < 8) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
@@ -418,7 +417,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_spconv
                         if (orows[i] >= 0) {
                             const long long ro = (long long)orows[i] * NCOLS + col;
                             if (io.pre_add) pre[u] = __ldg(reinterpret_cast<const float4*>(io.pre_add + ro));
-                            if (io.residual) res[u] = __ldg(reinterpret_cast<const float4*>(io.residual + ro));
+                            res[u] = load_residual4(io.residual, io.residual_h, orows[i], NCOLS, col);
                             if (io.gate_table) gat[u] = __ldg(reinterpret_cast<const float4*>(io.gate_table + (long long)gidx[i] * NCOLS + col));
                         }
                     }

@@ -133,6 +133,17 @@ __device__ __forceinline__ void store_split4(void* base, long long row, int c, i
     *reinterpret_cast<uint2*>(rp + c + col) = ul;
 }
 
+// 4 consecutive channels of a residual row: from the fp32 tensor, else from its split companion (hi + lo), else zero
+__device__ __forceinline__ float4 load_residual4(const float* res, const void* res_h, long long row, int c, int col) {
+    if (res) return __ldg(reinterpret_cast<const float4*>(res + row * c + col));
+    if (!res_h) return make_float4(0.f, 0.f, 0.f, 0.f);
+    const __half* rp = reinterpret_cast<const __half*>(res_h) + row * 2 * c + col;
+    const uint2 uh = __ldg(reinterpret_cast<const uint2*>(rp)), ul = __ldg(reinterpret_cast<const uint2*>(rp + c));
+    const float2 h0 = __half22float2(*reinterpret_cast<const __half2*>(&uh.x)), h1 = __half22float2(*reinterpret_cast<const __half2*>(&uh.y));
+    const float2 l0 = __half22float2(*reinterpret_cast<const __half2*>(&ul.x)), l1 = __half22float2(*reinterpret_cast<const __half2*>(&ul.y));
+    return make_float4(h0.x + l0.x, h0.y + l0.y, h1.x + l1.x, h1.y + l1.y);
+}
+
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }

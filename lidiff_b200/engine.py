@@ -68,6 +68,20 @@ class Linear:
         self.n_out, self.n_in = self.w.shape
 
 
+class Act:
+    """One activation of the fused engine: the fp32 tensor `f` (P, cap, C) and / or its fp16 split companion `h` (P, cap, 2C,
+    row = [hi | lo]).  Activations that only convolutions consume exist as the companion alone (half the epilogue's store traffic);
+    `f` is kept where a non-convolution consumer reads it (gate multiply, head / gate linears, downsample residuals)."""
+    __slots__ = ("f", "h", "P", "cap", "C")
+
+    def __init__(self, P, cap, C, f, h):
+        self.P, self.cap, self.C, self.f, self.h = P, cap, C, f, h
+
+
+def _ptr(t, p):
+    return None if t is None else t[min(p, t.shape[0] - 1)].data_ptr()
+
+
 def _net_layers(h, sd, device, decoder: bool):
     L = {}
 
@@ -186,7 +200,7 @@ class _PairLookup:
 class DenoiseEngine:
     def __init__(self, sd_enc: dict, sd_diff: dict, *, device="cuda", n_points=180000, denoising_steps=50,
                  cond_weight=6.0, resolution=0.05, t_steps=1000, beta_start=3.5e-5, beta_end=0.007,
-                 div_mode=1, conv_algo=_lib.ALGO_AUTO, batch_coord=0.0):
+                 div_mode=1, conv_algo=_lib.ALGO_AUTO, batch_coord=0.0, sd_refine: dict | None = None, max_range=50.0):
         self.device = torch.device(device)
         self.h = _lib.get_handle(self.device)
         self.N = int(n_points)
@@ -197,6 +211,10 @@ class DenoiseEngine:
         h, dev = self.h, self.device
         self.enc = _net_layers(h, sd_enc, dev, decoder=False)
         self.diff = _net_layers(h, sd_diff, dev, decoder=True)
+        # refinement network (MinkUNet, minkunet.py:500-619): same stem / stages / ups without gates, head 96 -> 20 -> 18 + tanh
+        self.refine = _net_layers(h, sd_refine, dev, decoder=True) if sd_refine is not None else None
+        self.refine_head = (Linear(sd_refine, "last.0", dev), Linear(sd_refine, "last.2", dev)) if sd_refine is not None else None
+        self.max_range = float(max_range)
         self.sched = DPMSolverMultistepScheduler(num_train_timesteps=t_steps, beta_start=beta_start, beta_end=beta_end,
                                                  beta_schedule="linear", algorithm_type="sde-dpmsolver++", solver_order=2)
         self.sched.set_timesteps(denoising_steps)
@@ -213,10 +231,13 @@ class DenoiseEngine:
             self.lat_2.append(Linear(sd_diff, f"latemp_{g}.2", dev))
         self.head = (Linear(sd_diff, "last.0", dev), Linear(sd_diff, "last.2", dev))
         self._bufs = {}
+        self._graphs = {}
         self.use_row_order = True
         self.use_scatter = True
         self.use_split = True            # fp16 hi/lo companions + cp.async gathers in the tensor-core kernels
-        self._h_of = {}
+        # lean activations: tensors that only convolutions read are kept as the split companion alone (LB2_LEAN=0: fp32 + companion everywhere)
+        self.lean = os.environ.get("LB2_LEAN", "1") != "0" and not os.environ.get("LB2_SCATTER_LEVELS")
+        self._acts = {}
         self._perm_lookup = {}
         self.geom = Geometry(h, self.N, with_up=True)
         self._perm_lookup = self.geom.perm_of
@@ -237,6 +258,13 @@ class DenoiseEngine:
         self._hist_row = 0
         self._conv_counter = 0
         self._have_x0 = False            # the multistep state (x0_state buffer) holds a prediction of an earlier step
+        # CUDA graphs: one graph per (schedule position, ping-pong parity, solver order) captured on first use after an eager
+        # warm-up step; all row counts are device scalars and every buffer is persistent, so a graph stays valid across scans
+        self.use_graphs = os.environ.get("LB2_GRAPHS", "1") != "0" and torch.cuda.is_available() and self.device.type == "cuda"
+        self._graphs = {}
+        self._eager_steps = 0
+        self.graph_replays = 0
+        self.replayed_launches = 0       # kernels launched through graph replays (the library's own counter only sees eager launches)
         self._prepare_time_tables()
         self._prepare_uncond()
 
@@ -246,6 +274,9 @@ class DenoiseEngine:
         sd_e = {k: v for k, v in pipe.partial_enc.state_dict().items()}
         sd_d = {k: v for k, v in pipe.model.state_dict().items()}
         hp = pipe.hparams
+        if getattr(pipe, "model_refine", None) is not None:
+            kw.setdefault("sd_refine", {k: v for k, v in pipe.model_refine.state_dict().items()})
+        kw.setdefault("max_range", hp["data"].get("max_range", 50.0))
         return cls(sd_e, sd_d, device=pipe.device, n_points=hp["data"]["num_points"], denoising_steps=hp["diff"]["s_steps"],
                    cond_weight=pipe.w_uncond, resolution=hp["data"]["resolution"], t_steps=hp["diff"]["t_steps"],
                    beta_start=hp["diff"]["beta_start"], beta_end=hp["diff"]["beta_end"], **kw)
@@ -253,21 +284,24 @@ class DenoiseEngine:
     def buf(self, name, shape, dtype=torch.float32):
         t = self._bufs.get(name)
         if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            if t is not None:
+                self._graphs.clear()                 # a captured step graph may point at the buffer being replaced
             t = torch.zeros(shape, dtype=dtype, device=self.device)
             self._bufs[name] = t
         return t
 
-    # ---- fp16 split companions of activations consumed by tensor-core convolutions ----------------------
-    def _companion(self, t: torch.Tensor, create: bool):
-        """(P, cap, 2C) fp16 buffer paired with the fp32 activation `t` (row = [hi | lo]); None when unused"""
-        if t is None or not self.use_split or self.conv_algo == _lib.ALGO_FFMA or t.shape[-1] % 8:
-            return None
-        key = t.data_ptr()
-        hbuf = self._h_of.get(key)
-        if hbuf is None and create:
-            hbuf = torch.zeros(tuple(t.shape[:-1]) + (2 * t.shape[-1],), dtype=torch.float16, device=self.device)
-            self._h_of[key] = hbuf
-        return hbuf
+    # ---- activations (fp32 tensor and / or fp16 split companion), allocated once per name ------------------------------
+    def act(self, name, P, cap, C, f32=True, split=True) -> Act:
+        split = bool(split and self.use_split and self.conv_algo != _lib.ALGO_FFMA and C % 8 == 0)
+        f32 = bool(f32 or not split)
+        a = self._acts.get(name)
+        if a is None or (a.P, a.cap, a.C) != (P, cap, C) or (a.f is not None) != f32 or (a.h is not None) != split:
+            if a is not None:
+                self._graphs.clear()                 # a captured step graph may point at the activation being replaced
+            f = torch.zeros((P, cap, C), dtype=torch.float32, device=self.device) if f32 else None
+            hh = torch.zeros((P, cap, 2 * C), dtype=torch.float16, device=self.device) if split else None
+            a = self._acts[name] = Act(P, cap, C, f, hh)
+        return a
 
     # ---- small dense helpers ------------------------------------------------------------------------
     def _linear(self, x, lin: Linear, out, act=0, m_cap=None, d_m=None, prebias=None, pre_act=0, bias=True):
@@ -310,22 +344,21 @@ class DenoiseEngine:
             l0, l2 = self.latent[g]
             h1 = self._linear(part_F, l0, self.buf(f"lat_h_{tag}", (rows_cap, l0.n_out)), act=1, m_cap=rows_cap, d_m=d_rows)
             p = self._linear(h1, l2, self.buf(f"lat_p_{tag}", (rows_cap, l2.n_out)), m_cap=rows_cap, d_m=d_rows)
-            a = torch.empty((rows_cap, self.lat_p[g].n_out), device=self.device)
+            a = self.buf(f"lat_A_{tag}_{g}", (rows_cap, self.lat_p[g].n_out))     # persistent: captured step graphs point at it
             A.append(self._linear(p, self.lat_p[g], a, m_cap=rows_cap, d_m=d_rows, bias=False))
         return A
 
     # ---- convolution helper ---------------------------------------------------------------------------
-    def _conv(self, lay: ConvLayer, nbr, d_m, cap, in1, in2=None, out=None, residual=None, relu=True,
-              gate=None, out_gated=None, npass=1):
-        """in1/in2/residual/out/out_gated: tensors shaped (P, cap, C) with P in {1, npass}; gate: list per
-        pass of (table, idx-or-None)."""
+    def _conv(self, lay: ConvLayer, nbr, d_m, cap, in1: Act, in2: Act = None, out: Act = None, residual: Act = None, relu=True,
+              gate=None, out_gated: Act = None, npass=1):
+        """in1 / in2 / residual / out / out_gated: activations with P in {1, npass} passes; gate: list per pass of (table, idx-or-None).
+        A residual that exists as a companion only is read as hi + lo by the epilogue."""
         d = ConvDesc()
-        d.c1 = in1.shape[-1]
-        d.c2 = in2.shape[-1] if in2 is not None else 0
+        d.c1 = in1.C
+        d.c2 = in2.C if in2 is not None else 0
         assert d.c1 + d.c2 == lay.cin, (d.c1, d.c2, lay.cin)
-        sel = lambda t, p: None if t is None else t[min(p, t.shape[0] - 1)].data_ptr()
-        in1_h, in2_h = self._companion(in1, False), self._companion(in2, False)
-        out_h, outg_h = self._companion(out, True), self._companion(out_gated, True)
+        f = lambda a: None if a is None else a.f
+        hh = lambda a: None if a is None else a.h
         pre = None
         geom_lvl = self._pairs_lookup.get(nbr.data_ptr()) if (nbr is not None and self.use_scatter and lay.Wpc is not None
                                                                and self.conv_algo != _lib.ALGO_FFMA) else None
@@ -340,8 +373,8 @@ class DenoiseEngine:
             sd.koff, sd.tile_off = g.koff[l].data_ptr(), g.tile_off[l].data_ptr()
             sd.npass = npass
             for p in range(npass):
-                sd.in1[p], sd.in2[p], sd.out[p] = sel(in1, p), sel(in2, p), pre[p].data_ptr()
-                sd.in1_h[p], sd.in2_h[p] = sel(in1_h, p), sel(in2_h, p)
+                sd.in1[p], sd.in2[p], sd.out[p] = _ptr(f(in1), p), _ptr(f(in2), p), pre[p].data_ptr()
+                sd.in1_h[p], sd.in2_h[p] = _ptr(hh(in1), p), _ptr(hh(in2), p)
             sd.d_zero_rows, sd.zero_rows_cap = d_m.data_ptr(), cap
         else:
             sd = None
@@ -363,14 +396,15 @@ class DenoiseEngine:
         d.row_perm = perm.data_ptr() if perm is not None else None
         mask = self._mask_lookup.get(nbr.data_ptr()) if nbr is not None else None
         d.row_mask = mask.data_ptr() if mask is not None else None
+        res_h = hh(residual) if (residual is not None and residual.f is None) else None
         for p in range(npass):
             gt = gi = None
             if gate is not None:
                 gt = gate[p][0].data_ptr()
                 gi = gate[p][1].data_ptr() if gate[p][1] is not None else None
-            d.io[p] = ConvIO(sel(in1, p), sel(in2, p), sel(residual, p), sel(out, p), gt, gi, sel(out_gated, p),
+            d.io[p] = ConvIO(_ptr(f(in1), p), _ptr(f(in2), p), _ptr(f(residual), p), _ptr(f(out), p), gt, gi, _ptr(f(out_gated), p),
                              pre[p].data_ptr() if pre is not None else None,
-                             sel(in1_h, p), sel(in2_h, p), sel(out_h, p), sel(outg_h, p))
+                             _ptr(hh(in1), p), _ptr(hh(in2), p), _ptr(hh(out), p), _ptr(hh(out_gated), p), _ptr(res_h, p))
         if self.layer_log is not None:
             self.layer_log.append(dict(name=lay.name, scatter=sd is not None, map=map_ptr, d_m=d_m.data_ptr() if d_m is not None else None,
                                        cin=lay.cin, cout=lay.cout, kvol=lay.kvol, npass=npass,
@@ -389,59 +423,63 @@ class DenoiseEngine:
                 self.h.spconv_scatter(sd)
             self.h.spconv(d, self.conv_algo)
 
-    def _res(self, L, p, geom, lvl, in1, in2, npass, tag, gate=None, want_plain=True):
+    def _res(self, L, p, geom, lvl, in1: Act, in2: Act, npass, tag, gate=None, want_plain=True, lean=False, out_f32=False):
+        """ResidualBlock (minkunet.py:51-80).  lean: the intermediate and the block output exist as split companions only (the
+        1x1 downsample branch, read once as a residual, as fp32 only); out_f32 keeps an fp32 copy of the block output."""
         cap = geom.n_cap
         nbr, d_m = geom.nbr3[lvl], geom.d_n[lvl]
         cmid = L[f"{p}.net.0"].cout
-        hbuf = self.buf(f"{tag}.h", (npass, cap, cmid))
+        hbuf = self.act(f"{tag}.h", npass, cap, cmid, f32=not lean)
         self._conv(L[f"{p}.net.0"], nbr, d_m, cap, in1, in2, out=hbuf, npass=npass)
         if f"{p}.downsample.0" in L:
-            sbuf = self.buf(f"{tag}.s", (npass, cap, cmid))
+            sbuf = self.act(f"{tag}.s", npass, cap, cmid, split=not lean)
             self._conv(L[f"{p}.downsample.0"], None, d_m, cap, in1, in2, out=sbuf, relu=False, npass=npass)
         else:
             assert in2 is None
             sbuf = in1
-        out = self.buf(f"{tag}.o", (npass, cap, cmid)) if want_plain else None
-        og = self.buf(f"{tag}.g", (npass, cap, cmid)) if gate is not None else None
+        out = self.act(f"{tag}.o", npass, cap, cmid, f32=(not lean) or out_f32) if want_plain else None
+        og = self.act(f"{tag}.g", npass, cap, cmid, f32=not lean) if gate is not None else None
         self._conv(L[f"{p}.net.3"], nbr, d_m, cap, hbuf, None, out=out, residual=sbuf, relu=True, gate=gate, out_gated=og, npass=npass)
         return out, og
 
-    def _encoder(self, L, geom, F0, npass, tag, gates=None):
-        """stem + 4 stages.  gates: None (MinkGlobalEnc) or per-gate list of per-pass (table, idx)."""
+    def _encoder(self, L, geom, F0: Act, npass, tag, gates=None, lean=False):
+        """stem + 4 stages.  gates: None (MinkGlobalEnc / refinement net) or per-gate list of per-pass (table, idx)."""
         cap = geom.n_cap
-        s0 = self.buf(f"{tag}.stem0", (1, cap, 32))
+        s0 = self.act(f"{tag}.stem0", 1, cap, 32, f32=not lean)
         self._conv(L["stem.0"], geom.nbr3[0], geom.d_n[0], cap, F0, out=s0, npass=1)
-        x0 = self.buf(f"{tag}.x0", (1, cap, 32))
+        x0 = self.act(f"{tag}.x0", 1, cap, 32, f32=(not lean) or gates is not None)     # the gate multiply reads fp32
         self._conv(L["stem.3"], geom.nbr3[0], geom.d_n[0], cap, s0, out=x0, npass=1)
         skips = [x0]
         if gates is not None:
-            cur = self.buf(f"{tag}.x0g", (npass, cap, 32))
-            cur_h = self._companion(cur, True)
+            cur = self.act(f"{tag}.x0g", npass, cap, 32, f32=not lean)
             for p in range(npass):
                 tb, ix = gates[0][p]
-                self.h.gate_mul(x0[0], tb, ix, geom.d_n[0], cap, 32, cur[p], cur_h[p] if cur_h is not None else None)
+                self.h.gate_mul(x0.f[0], tb, ix, geom.d_n[0], cap, 32, cur.f[p] if cur.f is not None else None,
+                                cur.h[p] if cur.h is not None else None)
         else:
             cur = x0
         for n in range(1, 5):
-            a = self.buf(f"{tag}.s{n}a", (npass, cap, L[f"stage{n}.0.net.0"].cout))
+            a = self.act(f"{tag}.s{n}a", npass, cap, L[f"stage{n}.0.net.0"].cout, f32=not lean)
             self._conv(L[f"stage{n}.0.net.0"], geom.nbr_dn[n], geom.d_n[n], cap, cur, out=a, npass=npass)
-            b, _ = self._res(L, f"stage{n}.1", geom, n, a, None, npass, f"{tag}.s{n}r1")
+            b, _ = self._res(L, f"stage{n}.1", geom, n, a, None, npass, f"{tag}.s{n}r1", lean=lean)
             g = gates[n] if gates is not None else None
-            x, xg = self._res(L, f"stage{n}.2", geom, n, b, None, npass, f"{tag}.s{n}r2", gate=g)
+            x, xg = self._res(L, f"stage{n}.2", geom, n, b, None, npass, f"{tag}.s{n}r2", gate=g, lean=lean)
             skips.append(x)
             cur = xg if gates is not None else x
         return skips, cur
 
-    def _decoder(self, L, geom, skips, cur, npass, tag, gates):
+    def _decoder(self, L, geom, skips, cur: Act, npass, tag, gates, lean=False):
+        """4 ups; the last block's output keeps its fp32 tensor (the head MLP reads it)"""
         cap = geom.n_cap
         y = cur
         for n in range(1, 5):
             lvl = 4 - n
-            d = self.buf(f"{tag}.u{n}d", (npass, cap, L[f"up{n}.0.net.0"].cout))
+            d = self.act(f"{tag}.u{n}d", npass, cap, L[f"up{n}.0.net.0"].cout, f32=not lean)
             self._conv(L[f"up{n}.0.net.0"], geom.nbr_up[lvl], geom.d_n[lvl], cap, y, out=d, npass=npass)
-            b, _ = self._res(L, f"up{n}.1.0", geom, lvl, d, skips[lvl], npass, f"{tag}.u{n}r1")
+            b, _ = self._res(L, f"up{n}.1.0", geom, lvl, d, skips[lvl], npass, f"{tag}.u{n}r1", lean=lean)
             g = gates[4 + n] if (gates is not None and n < 4) else None
-            o, og = self._res(L, f"up{n}.1.1", geom, lvl, b, None, npass, f"{tag}.u{n}r2", gate=g, want_plain=(g is None))
+            o, og = self._res(L, f"up{n}.1.1", geom, lvl, b, None, npass, f"{tag}.u{n}r2", gate=g, want_plain=(g is None), lean=lean,
+                              out_f32=(n == 4))
             y = og if g is not None else o
         return y
 
@@ -453,9 +491,10 @@ class DenoiseEngine:
         g1 = Geometry(self.h, 16, with_up=False, use_pairs=False)
         coords = torch.zeros((16, 4), dtype=torch.float32, device=dev)
         g1.build(coords, 16)
-        F0 = torch.zeros((1, 16, 3), device=dev)
+        F0 = self.act("uenc.F0", 1, 16, 3)
+        F0.f.zero_()
         skips, _ = self._encoder(self.enc, g1, F0, 1, "uenc")
-        part_u = skips[4][0][:1].clone()                              # (1,256)
+        part_u = skips[4].f[0][:1].clone()                            # (1,256)
         A = self._part_A(part_u, 1, None, "u")
         self.table_u = []                                             # [g] -> (T, C_g)
         for g in range(8):
@@ -463,14 +502,15 @@ class DenoiseEngine:
             for s in range(self.T):
                 self._linear(A[g], self.lat_2[g], t[s:s + 1], prebias=self.bvec[g][s], pre_act=1)
             self.table_u.append(t)
-        for k in [k for k in self._bufs if k.startswith("uenc")]:
-            del self._bufs[k]
+        for k in [k for k in self._acts if k.startswith("uenc")]:
+            del self._acts[k]
 
     def set_condition(self, scan: torch.Tensor):
         """scan (N,3): the conditioning point cloud (x_cond).  Runs MinkGlobalEnc once (App. D.2)."""
         dev, N = self.device, scan.shape[0]
         pts = scan.to(device=dev, dtype=torch.float32).contiguous()
         if self.geom_cond is None or self.geom_cond.n_cap != N:
+            self._graphs.clear()
             self.geom_cond = Geometry(self.h, N, with_up=False, use_pairs=False)
             self._perm_lookup = ChainMap(self.geom.perm_of, self.geom_cond.perm_of)
             self._mask_lookup = ChainMap(self.geom.mask_of, self.geom_cond.mask_of)
@@ -480,13 +520,14 @@ class DenoiseEngine:
         coords[:, 1:] = self._bufs["cond.q"]
         g = self.geom_cond
         g.build(coords, N)
-        F0 = self.buf("cond.F0", (1, N, 3))
-        g.voxel_mean(pts, N, F0[0])
+        F0 = self.act("cond.F0", 1, N, 3)
+        g.voxel_mean(pts, N, F0.f[0])
         skips, _ = self._encoder(self.enc, g, F0, 1, "cenc")
-        self.part_F = skips[4][0]                                      # (N cap, 256), rows valid < d_n[4]
+        self.part_F = skips[4].f[0]                                    # (N cap, 256), rows valid < d_n[4]
         self.part_C, self.part_dn, self.part_grid = g.C[4], g.d_n[4], g.grid[4]
         self.part_cap = N
-        self.part_tree = self.h.nn_tree(self.part_C, self.part_dn, N)    # box hierarchy over the scan's stride-16 voxels: built once per scan
+        # box hierarchy over the scan's stride-16 voxels: built once per scan, into the same buffer (captured step graphs point at it)
+        self.part_tree = self.h.nn_tree(self.part_C, self.part_dn, N, out=getattr(self, "part_tree", None))
         self.A_cond = self._part_A(self.part_F, N, self.part_dn, "c")
 
     # ---- one denoising step ----------------------------------------------------------------------------------
@@ -527,16 +568,16 @@ class DenoiseEngine:
             g.pairs[13:18] = torch.cat(g.d_n).long()
             self.pair_hist[self._hist_row % self.pair_hist.shape[0]] = g.pairs
             self._hist_row += 1
-        F0 = self.buf("F0", (1, N, 3))
-        g.voxel_mean(x_t, N, F0[0])
+        F0 = self.act("F0", 1, N, 3)
+        g.voxel_mean(x_t, N, F0.f[0])
         tabs_c = tabs_box[0]
         gates = [[(tabs_c[k], nn[GATE_LEVEL[k]]), (self.table_u[k][i:i + 1], None)] for k in range(8)]
-        skips, cur = self._encoder(self.diff, g, F0, 2, "d", gates)
-        y4 = self._decoder(self.diff, g, skips, cur, 2, "d", gates)
+        skips, cur = self._encoder(self.diff, g, F0, 2, "d", gates, lean=self.lean)
+        y4 = self._decoder(self.diff, g, skips, cur, 2, "d", gates, lean=self.lean)
         eps = self.buf("eps_vox", (2, N, 3))
         hid = self.buf("head_h", (N, 20))
         for p in range(2):
-            self._linear(y4[p], self.head[0], hid, act=1, m_cap=N, d_m=g.d_n[0])
+            self._linear(y4.f[p], self.head[0], hid, act=1, m_cap=N, d_m=g.d_n[0])
             self._linear(hid, self.head[1], eps[p], m_cap=N, d_m=g.d_n[0])
         c = self.sched.coefficients(i)
         # diffusers: second order once one x0 prediction is stored (lower_order_nums >= 1), also at step 0 of a later scan
@@ -553,8 +594,10 @@ class DenoiseEngine:
         dev, N = self.device, self.N
         if fresh:
             self._have_x0 = False
-        x_init = x_init.reshape(-1, 3).to(device=dev, dtype=torch.float64).contiguous()
-        assert x_init.shape[0] == N, f"engine built for {N} points, got {x_init.shape[0]}"
+        x_src = x_init.reshape(-1, 3)
+        assert x_src.shape[0] == N, f"engine built for {N} points, got {x_src.shape[0]}"
+        x_init = self.buf("x_init", (N, 3), torch.float64)               # persistent (captured step graphs point at it)
+        x_init.copy_(x_src)
         self.set_condition(x_init)
         st = dict(x_init=x_init, xa=self.buf("x_a", (N, 3)), xb=self.buf("x_b", (N, 3)), ca=self.buf("c_a", (N, 4)),
                   cb=self.buf("c_b", (N, 4)), x0s=self.buf("x0_state", (N, 3), torch.float64), i=0)
@@ -567,15 +610,40 @@ class DenoiseEngine:
     def advance(self, st, noise_i, host_noise=None, host_out=None):
         """one denoising step on the loop state.  host_noise (pinned (N,3) fp32): copied H2D inside the step;
         host_out (pinned (N,3) fp32): the step's x_t is copied D2H (what a caller that visualises / logs every
-        step pays)."""
-        if host_noise is not None:
-            noise_i = self.buf("noise_in", (self.N, 3))
-            noise_i.copy_(host_noise, non_blocking=True)
-        self.step(st["i"] % self.T, st["xa"], st["xb"], st["ca"], st["cb"], st["x_init"], noise_i, st["x0s"])
+        step pays).  After one eager step the work of a step is replayed from a CUDA graph (LB2_GRAPHS=0: always eager)."""
+        i = st["i"] % self.T
+        graphed = self.use_graphs and self.conv_events is None and self.layer_log is None and self.pair_hist is None
+        if host_noise is not None or graphed:
+            nbuf = self.buf("noise_in", (self.N, 3))
+            nbuf.copy_(host_noise if host_noise is not None else noise_i, non_blocking=True)
+            noise_i = nbuf
+        if not graphed or self._eager_steps < 1:
+            self.step(i, st["xa"], st["xb"], st["ca"], st["cb"], st["x_init"], noise_i, st["x0s"])
+            self._eager_steps += 1
+        else:
+            second = self._have_x0 and not (i == self.T - 1 and self.T < 15)
+            key = (i, st["xa"].data_ptr(), bool(second))
+            ent = self._graphs.get(key)
+            if ent is None:
+                have = self._have_x0
+                l0 = self.h.launch_count()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self.step(i, st["xa"], st["xb"], st["ca"], st["cb"], st["x_init"], noise_i, st["x0s"])
+                ent = self._graphs[key] = (g, self.h.launch_count() - l0)
+                self._have_x0 = have                                   # capture does not execute: the replay below is this step
+            ent[0].replay()
+            self._have_x0 = True
+            self.graph_replays += 1
+            self.replayed_launches += ent[1]
         st["xa"], st["xb"], st["ca"], st["cb"] = st["xb"], st["xa"], st["cb"], st["ca"]
         st["i"] += 1
         if host_out is not None:
             host_out.copy_(st["xa"], non_blocking=True)
+
+    def launches(self) -> int:
+        """kernels launched on behalf of this engine's handle: eager launches counted by the library + graph-replayed ones"""
+        return self.h.launch_count() + self.replayed_launches
 
     def run(self, x_init: torch.Tensor, x_feats: torch.Tensor, step_noise=None, n_steps=None, return_device=False, fresh=True):
         """x_init (1,N,3) fp64 conditioning scan, x_feats (1,N,3) noisy start.  Returns final x_t.F (N,3)."""
@@ -593,3 +661,57 @@ class DenoiseEngine:
         if self.h.read_status() & 1:
             raise RuntimeError("lidiff_b200: a coordinate left the supported key range during sampling")
         return out
+
+    # ---- after the loop: postprocess_scan + refinement forward + 6x offsets (pipeline:107-138) ------------------------------
+    def postprocess(self, completed: torch.Tensor, x_init: torch.Tensor) -> torch.Tensor:
+        """postprocess_scan (pipeline:107-115) on the device: range filter and the z band of the input scan.  completed (N,3) fp32,
+        x_init (N,3) fp64.  Same arithmetic as the reference's numpy expressions (fp32 squared norm summed left to right)."""
+        x, y, z = completed[:, 0], completed[:, 1], completed[:, 2]
+        dist = torch.sqrt((x * x + y * y) + z * z)
+        zi = x_init.reshape(-1, 3)[:, 2]
+        max_z = zi.max().item()
+        min_z = (zi.mean() - 2 * zi.std()).item()
+        keep = (dist < self.max_range) & (z < max_z) & (z > min_z)
+        return completed[keep].contiguous()
+
+    def refine_offsets(self, pts: torch.Tensor) -> torch.Tensor:
+        """refine_forward (pipeline:134-138, MinkUNet.forward minkunet.py:596-619) on `pts` (n,3) fp32 device points, n <= N:
+        voxelise, stem + 4 stages + 4 ups through the fused conv kernels (one pass), head on voxel rows, slice back to the points.
+        Returns (n,18) fp32 offsets on the device."""
+        if self.refine is None:
+            raise RuntimeError("DenoiseEngine was built without the refinement network (sd_refine)")
+        h, g, N = self.h, self.geom, self.N
+        pts = pts.to(device=self.device, dtype=torch.float32).contiguous()
+        n = pts.shape[0]
+        if n > N:
+            raise RuntimeError(f"refine_offsets: {n} points exceed the engine capacity {N}")
+        if n == 0:
+            return torch.zeros((0, 18), device=self.device)
+        coords = self.buf("r.coords", (N, 4))
+        q = self.buf("r.q", (N, 3))
+        h.quantize(pts, self.resolution, self.div_mode, q[:n])
+        coords[:n, 0] = 0
+        coords[:n, 1:] = q[:n]
+        g.build(coords, n)
+        F0 = self.act("r.F0", 1, N, 3)
+        g.voxel_mean(pts, n, F0.f[0])
+        skips, cur = self._encoder(self.refine, g, F0, 1, "r", lean=self.lean)
+        y4 = self._decoder(self.refine, g, skips, cur, 1, "r", None, lean=self.lean)
+        hid = self.buf("r.head_h", (N, 20))
+        off_v = self.buf("r.off_v", (N, 18))
+        self._linear(y4.f[0], self.refine_head[0], hid, act=1, m_cap=N, d_m=g.d_n[0])
+        self._linear(hid, self.refine_head[1], off_v, act=2, m_cap=N, d_m=g.d_n[0])
+        out = torch.empty((n, 18), device=self.device)
+        h.gather_rows(off_v, g.inv[0], n, 18, out)
+        return out
+
+    def complete(self, x_init: torch.Tensor, x_feats: torch.Tensor, step_noise=None, fresh=True):
+        """complete_scan after preprocessing (pipeline:117-132), all on the device: T denoising steps, postprocess, refinement
+        forward, 6 offsets per point.  Returns (refined (6n,3), post (n,3)) device tensors."""
+        x_t = self.run(x_init, x_feats, step_noise, return_device=True, fresh=fresh)
+        post = self.postprocess(x_t, x_init.reshape(-1, 3).to(self.device))
+        off = self.refine_offsets(post).reshape(-1, 6, 3)
+        refined = (post[:, None, :] + off).reshape(-1, 3)
+        if self.h.read_status() & 1:
+            raise RuntimeError("lidiff_b200: a coordinate left the supported key range during sampling")
+        return refined, post

@@ -127,13 +127,13 @@ class DiffCompletion(nn.Module):
         if start_noise is None:
             start_noise = torch.randn(scan.shape, device=self.device)
         x_feats = scan + start_noise.to(self.device)
-        if self.use_engine:
-            completed_scan = self.engine().run(scan, x_feats, step_noise, fresh=fresh)
-        else:
-            x_full = self.points_to_tensor(x_feats)
-            x_cond = self.points_to_tensor(scan)
-            x_uncond = self.points_to_tensor(torch.zeros_like(scan))
-            completed_scan = self.completion_loop(scan, x_full, x_cond, x_uncond, step_noise, fresh=fresh)
+        if self.use_engine:                     # fused path: loop, postprocess, refinement forward and the 6 offsets stay on the device
+            refined, post = self.engine().complete(scan, x_feats, step_noise, fresh=fresh)
+            return refined.cpu().numpy(), post.cpu().numpy()
+        x_full = self.points_to_tensor(x_feats)
+        x_cond = self.points_to_tensor(scan)
+        x_uncond = self.points_to_tensor(torch.zeros_like(scan))
+        completed_scan = self.completion_loop(scan, x_full, x_cond, x_uncond, step_noise, fresh=fresh)
         post_scan = self.postprocess_scan(completed_scan, scan)
         refine_in = self.points_to_tensor(torch.as_tensor(post_scan)[None, :, :])
         offset = self.refine_forward(refine_in).reshape(-1, 6, 3)

@@ -27,6 +27,29 @@ def _i(ptr, shape):
     return _arr(ptr, shape, C.c_int32, np.int32)
 
 
+def _h(ptr, shape):
+    return _arr(ptr, shape, C.c_uint16, np.float16)
+
+
+def _read_act(f_ptr, h_ptr, rows, c):
+    """an activation as float64: from the fp32 tensor, else from its fp16 split companion (row = [hi | lo])"""
+    if f_ptr:
+        return torch.from_numpy(_f(f_ptr, (rows, c)).copy()).double()
+    hl = torch.from_numpy(_h(h_ptr, (rows, 2 * c)).astype(np.float32))
+    return (hl[:, :c] + hl[:, c:]).double()
+
+
+def _write_act(f_ptr, h_ptr, rows, c, y):
+    y32 = y.float()
+    if f_ptr:
+        _f(f_ptr, (rows, c))[:] = y32.numpy()
+    if h_ptr:
+        y32 = y32.clamp(-65504.0, 65504.0)
+        hi = y32.half()
+        lo = (y32 - hi.float()).half()
+        _h(h_ptr, (rows, 2 * c))[:] = torch.cat([hi, lo], 1).numpy()
+
+
 class FakeHandle:
     def __init__(self):
         self.device = torch.device("cpu")
@@ -198,10 +221,9 @@ class FakeHandle:
         rows_in = int(nbr.max()) + 1 if nbr.size else 0
         for p in range(d.npass):
             io = d.io[p]
-            x = torch.from_numpy(_f(io.in1, (rows_in, d.c1)).copy())
+            x = _read_act(io.in1, io.in1_h, rows_in, d.c1)
             if d.c2:
-                x = torch.cat([x, torch.from_numpy(_f(io.in2, (rows_in, d.c2)).copy())], 1)
-            x = x.double()
+                x = torch.cat([x, _read_act(io.in2, io.in2_h, rows_in, d.c2)], 1)
             y = torch.zeros(M, d.cout, dtype=torch.float64)
             for k in range(d.kvol):
                 o = np.nonzero(nbr[k] >= 0)[0]
@@ -211,20 +233,19 @@ class FakeHandle:
                 y = y + torch.from_numpy(_f(io.pre_add, (M, d.cout)).copy()).double()
             if d.scale:
                 y = y * torch.from_numpy(_f(d.scale, (d.cout,)).copy()).double() + torch.from_numpy(_f(d.shift, (d.cout,)).copy()).double()
-            if io.residual:
-                y = y + torch.from_numpy(_f(io.residual, (M, d.cout)).copy()).double()
+            if io.residual or io.residual_h:
+                y = y + _read_act(io.residual, io.residual_h, M, d.cout)
             if d.relu:
                 y = torch.relu(y)
-            if io.out:
-                _f(io.out, (M, d.cout))[:] = y.float().numpy()
-            if io.out_gated:
+            _write_act(io.out, io.out_h, M, d.cout, y)
+            if io.out_gated or io.out_gated_h:
                 g = y
                 if io.gate_table:
                     gi = _i(io.gate_idx, (M,)).astype(np.int64) if io.gate_idx else np.zeros(M, np.int64)
                     rows_g = int(gi.max()) + 1 if M else 0
                     tab = torch.from_numpy(_f(io.gate_table, (rows_g, d.cout)).copy()).double()
                     g = y * tab[torch.from_numpy(gi)]
-                _f(io.out_gated, (M, d.cout))[:] = g.float().numpy()
+                _write_act(io.out_gated, io.out_gated_h, M, d.cout, g)
 
     # misc -----------------------------------------------------------------------------------------
     def nn_match(self, q, d_nq, nq_cap, k, d_nk, nk_cap, batch_scale, idx):
@@ -244,7 +265,7 @@ class FakeHandle:
     def nn_match_grid(self, q, d_nq, nq_cap, k, d_nk, nk_cap, key_grid, key_stride, max_ring, idx):
         self.nn_match(q, d_nq, nq_cap, k, d_nk, nk_cap, 0, idx)
 
-    def nn_tree(self, k, d_nk, nk_cap):
+    def nn_tree(self, k, d_nk, nk_cap, out=None):
         self.launches += 12
         return (k, d_nk)
 
@@ -278,7 +299,13 @@ class FakeHandle:
         self.launches += 1
         M = self._n(d_m, m_cap)
         g = table[idx[:M].long()] if idx is not None else table[0:1]
-        out[:M] = x[:M] * g
+        y = x[:M] * g
+        if out is not None:
+            out[:M] = y
+        if out_h is not None:
+            y = y.clamp(-65504.0, 65504.0)
+            hi = y.half()
+            out_h[:M] = torch.cat([hi, (y - hi.float()).half()], 1)
 
     def gather_rows(self, src, idx, n, c, out):
         self.launches += 1
