@@ -108,11 +108,11 @@ def build_inputs(device, seed):
     return scan, start, g
 
 
-def build_pipeline(device, scan):
+def build_pipeline(device, scan, T=T_STEPS):
     from lidiff_b200.pipeline import DiffCompletion
     from lidiff_b200.weights import calibrate_bn, random_state_dict
-    sds = {"enc": random_state_dict("enc", 0), "diff": random_state_dict("diff", 1), "refine": None}
-    pipe = DiffCompletion(state_dicts=sds, denoising_steps=T_STEPS, cond_weight=GUIDANCE_W, device=device,
+    sds = {"enc": random_state_dict("enc", 0), "diff": random_state_dict("diff", 1), "refine": random_state_dict("refine", 2)}
+    pipe = DiffCompletion(state_dicts=sds, denoising_steps=T, cond_weight=GUIDANCE_W, device=device,
                           hparams={"data": {"num_points": N_POINTS}}, engine=True)
     calibrate_bn(pipe, scan[None])                                  # seeded random weights with sane BN statistics
     return pipe
@@ -145,7 +145,7 @@ def run_ours(args, rank, world, local_rank):
     log("building inputs (synthetic scan, GPU farthest point sampling)")
     scan, start, g = build_inputs(device, seed=rank)
     log("building pipeline (seeded weights, BN calibration)")
-    pipe = build_pipeline(device, scan)
+    pipe = build_pipeline(device, scan, args.T)
     eng = pipe.engine()
     h = eng.h
     K, W, T = args.steps, args.warmup, eng.T
@@ -169,8 +169,12 @@ def run_ours(args, rank, world, local_rank):
         eng.advance(st, noise[i])
     torch.cuda.synchronize()
 
+    bufs = tuple(eng._bufs[k] for k in ("x_a", "x_b", "c_a", "c_b"))       # the loop's ping-pong buffers; step 0 reads x_a / c_a
+
     def restore(i):
         xa, ca, x0s = snaps[i]
+        # schedule position i always runs from the same ping-pong buffer as in the trajectory (captured step graphs are keyed on it)
+        st["xa"], st["xb"], st["ca"], st["cb"] = bufs if i % 2 == 0 else (bufs[1], bufs[0], bufs[3], bufs[2])
         st["xa"].copy_(xa); st["ca"].copy_(ca); st["x0s"].copy_(x0s)
         st["i"] = i
         eng._have_x0 = i > 0
@@ -186,12 +190,16 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     l0 = eng.launches()
     with ClockSampler(local_rank) as clocks:
+        if args.profiler_range:
+            torch.cuda.profiler.start()                 # `ncu --profile-from-start off` then sees exactly the timed region
         e0.record()
         for i in steps:
             restore(i)
             eng.advance(st, noise[i])
         e1.record()
         barrier()
+        if args.profiler_range:
+            torch.cuda.profiler.stop()
     launches = eng.launches() - l0
     ms = e0.elapsed_time(e1)
     log(f"timed region: {K} steps in {ms:.1f} ms")
@@ -199,17 +207,17 @@ def run_ours(args, rank, world, local_rank):
         raise RuntimeError("a coordinate left the supported key range during the benchmark")
 
     # ---- timed region 2: end to end through the public loop with HOST buffers ----------------------------------------------
-    h_noise = torch.empty((T, N_POINTS, 3), dtype=torch.float32).pin_memory()
-    h_noise.copy_(noise)
+    h_noise = torch.empty((K, N_POINTS, 3), dtype=torch.float32).pin_memory()      # the SDE noise of the K timed schedule positions
+    h_noise.copy_(noise[steps])
     h_out = torch.empty((N_POINTS, 3), dtype=torch.float32).pin_memory()
     h_scan, h_start = scan.cpu().pin_memory(), x_feats.cpu().pin_memory()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     f0.record()
     st = eng.start(h_scan.to(device, non_blocking=True), h_start.to(device, non_blocking=True))
-    for i in steps:
+    for n, i in enumerate(steps):
         restore(i)
-        eng.advance(st, None, host_noise=h_noise[i], host_out=h_out)
+        eng.advance(st, None, host_noise=h_noise[n], host_out=h_out)
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
@@ -255,6 +263,26 @@ def run_ours(args, rank, world, local_rank):
             torch.cuda.synchronize()
             fixed[f"sigma_{sigma}"] = {"ms_per_step": round(a.elapsed_time(b) / reps, 3), "level_rows": eng.geom.sizes(),
                                        "pairs_3x3x3": eng.geom.pairs[:5].tolist()}
+    # ---- BASELINE configs[4]: whole-scan completion through the public API (host numpy in, host numpy out) --------------------------
+    scan_e2e = None
+    if not args.no_scan:
+        from lidiff_b200.synth import synthetic_scan
+        raw = synthetic_scan(100 + rank)                                   # (131072, 3) float64 host array, before the range filter
+        pipe.complete_scan(raw)                                            # untimed: graphs of the refinement-free path exist, buffers sized
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t_host = time.time()
+        s0.record()
+        refined, post = pipe.complete_scan(raw)
+        s1.record()
+        barrier()
+        t_host = time.time() - t_host
+        ms_scan = max_over_ranks(max(s0.elapsed_time(s1), 1e3 * t_host), device)
+        scan_e2e = {"value": round(world / (ms_scan * 1e-3), 4), "unit": "scans/s", "ms_per_scan": round(ms_scan, 1), "scans_timed": world,
+                    "points_in": int(raw.shape[0]), "points_out": int(refined.shape[0]),
+                    "what": "DiffCompletion.complete_scan(raw numpy scan) -> refined numpy cloud: range filter (host, as the reference), GPU farthest "
+                            "point sampling to 18000 (INSIDE the timed region), x10, T=50 guided denoising steps, postprocess, refinement "
+                            "network forward, 6 offsets per point, copy back; wall clock incl. all host work, one scan per GPU"}
     if rank != 0:
         return None
 
@@ -313,7 +341,8 @@ def run_ours(args, rank, world, local_rank):
            "ms_per_step": round(ms / K, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "fp16x3 split tensor-core MMA, fp32 accumulate (fp32 CUDA cores for the Cin=3 stem), fp64 DPM update",
            "data": "synthetic",
-           "config": {"workload": "BASELINE configs[1]: one synthetic KITTI-shape scan of 180000 points per GPU, T=50 schedule, guidance s=6.0",
+           "config": {"workload": ("BASELINE configs[1]: one synthetic KITTI-shape scan of 180000 points per GPU, T=50 schedule, guidance s=6.0" if args.T == T_STEPS else
+                                   f"BASELINE configs[3]: one synthetic KITTI-shape scan of 180000 points per GPU, full schedule set_timesteps({args.T}) = {T} steps, guidance s=6.0"),
                       "points": N_POINTS, "T": T, "guidance_w": GUIDANCE_W, "resolution_m": 0.05,
                       "schedule_positions_timed": steps,
                       "steps_note": "the full T-step trajectory runs once untimed; the timed region replays the listed schedule positions from the saved "
@@ -325,7 +354,9 @@ def run_ours(args, rank, world, local_rank):
            "e2e": {"value": round(K * world / (ms_e2e * 1e-3), 3), "unit": UNIT, "h2d_bytes_per_step": N_POINTS * 3 * 4,
                    "d2h_bytes_per_step": N_POINTS * 3 * 4,
                    "what": "same schedule positions through DenoiseEngine.start/advance with pinned HOST buffers: scan + start uploaded, per-step SDE noise H2D and x_t D2H inside the timed region"},
-           "gpu_launches": int(launches), "roofline": roofline, "fixed_geometry": fixed}
+           "gpu_launches": int(launches), "roofline": roofline, "fixed_geometry": fixed, "scan_e2e": scan_e2e,
+           "engine": {"cuda_graphs": bool(eng.use_graphs), "graph_replays": int(eng.graph_replays), "lean_activations": bool(eng.lean),
+                      "tc_pair": int(h.get_option(0))}}
     if world == 1 and not args.no_cpu_baseline:
         log("cpu baseline leg")
         out["cpu_baseline"] = cpu_reference(scan.cpu(), pipe, budget_s=20.0, steps=1, warmup=0)
@@ -422,6 +453,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fixed", action="store_true", help="skip the fixed-geometry sigma micro-benchmark")
+    ap.add_argument("--profiler-range", action="store_true", help="cudaProfilerStart/Stop around the timed region (for ncu --profile-from-start off)")
+    ap.add_argument("--no-scan", action="store_true", help="skip the whole-scan (configs[4]) measurement")
+    ap.add_argument("--T", type=int, default=T_STEPS, help="schedule length (1000 = BASELINE configs[3])")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))

@@ -25,7 +25,6 @@ constexpr int NCOLS = 256;
 constexpr int MAX_KVOL = 27;
 constexpr int NA = 4;                                 // A slots (half stages, 32 K-columns each)
 constexpr int NB = 2;                                 // B slots (64 K-columns each)
-constexpr int A_LAG = 3;                              // cp.async lookahead in A slots: NA - 1, arrivals are signalled before the next issue
 constexpr int SLAB_COLS = 16;
 constexpr int SLAB_PITCH = SLAB_COLS + 4;             // floats per slab row
 constexpr int SLAB_BYTES = 8 * 32 * SLAB_PITCH * 4;   // 8 drain warps x 32 rows
@@ -56,7 +55,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_n256(const Params p) {
     const int n_tiles = (M + BM - 1) / BM;
     const int total = n_tiles * p.npass;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ctot = p.c1 + p.c2;
+    const int pshift = (p.npass == 2) ? 1 : 0;                  // work item -> (tile, pass): heaviest tiles first, passes adjacent (see spconv_tc4.cu)
+    auto item_tile = [&](int item) { return n_tiles - 1 - (item >> pshift); };
+    auto item_pass = [&](int item) { return item & pshift; };
 
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -109,11 +110,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_n256(const Params p) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         const int t = threadIdx.x;
         const int sub = t & 3, rbase = t >> 2;                          // 16-byte chunk inside the half row / first of this thread's 4 rows
-        int it = 0, arrived = 0, j = 0;
-        Ring ri{0, 0u, NA}, ra{0, 0u, NA};
+        int j = 0;
+        Ring ri{0, 0u, NA};
         auto fetch_row = [&](int item) {
             if (item >= total) return -1;
-            const int slot = ((item >= n_tiles) ? item - n_tiles : item) * BM + t;
+            const int slot = item_tile(item) * BM + t;
             return (slot < M) ? (p.row_perm ? __ldg(p.row_perm + slot) : slot) : -1;
         };
         auto fetch_mask = [&](int row) -> uint32_t {                   // candidate offsets of a row: its neighbour bit mask if the caller has one
@@ -125,7 +126,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_n256(const Params p) {
         uint32_t next_mask = fetch_mask(next_row);
         for (int item = blockIdx.x; item < total; item += gridDim.x, ++j) {
             const int b = j % META;
-            const int pass = (item >= n_tiles) ? 1 : 0;
+            const int pass = item_pass(item);
             const lb2_conv_io io = p.io[pass];
             if (j >= META) mbar_wait(meta_empty(b), ((j / META) - 1) & 1);
             {
@@ -175,14 +176,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_n256(const Params p) {
             while (km) {
                 km &= km - 1;
                 if (km) load_src(__ffs(km) - 1, nxt);                 // prefetch the next offset's rows behind this offset's copies
-                for (int c2 = 0; c2 < 2 * p.nchunks; ++c2, ++it, ri.next()) {      // c2 = 2 * chunk + half
-                    if (it >= A_LAG) {                                  // publish the slot issued A_LAG iterations ago BEFORE waiting for a free
-                        cp_async_wait<A_LAG - 1>();                     // slot: its consumer never waits for this iteration's slot to drain
-                        fence_proxy_async();
-                        mbar_arrive(full_a(ra.s));
-                        ra.next();
-                        ++arrived;
-                    }
+                for (int c2 = 0; c2 < 2 * p.nchunks; ++c2, ri.next()) {            // c2 = 2 * chunk + half
                     const int s = ri.s;
                     mbar_wait(empty_a(s), ri.par ^ 1u);
                     const uint32_t a_hi_u = base + (uint32_t)(s >> 1) * a_stage;
@@ -200,15 +194,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_n256(const Params p) {
                         cp_async16(a_hi_u + off, rp, ok ? 16u : 0u);
                         cp_async16(a_hi_u + A_TILE + off, rp + (ok ? cw : 0), ok ? 16u : 0u);
                     }
-                    cp_async_commit();
+                    cp_async_arrive_on(full_a(s));                      // published by the hardware when this thread's copies have landed
                 }
 #pragma unroll
                 for (int q = 0; q < 4; ++q) src[q] = nxt[q];
             }
         }
-        cp_async_wait<0>();
-        fence_proxy_async();
-        for (; arrived < it; ++arrived, ra.next()) mbar_arrive(full_a(ra.s));
     } else if (warp < 8) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         if (warp == 4) {
@@ -301,7 +292,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_n256(const Params p) {
         int gcount = 0, j = 0;
         for (int item = blockIdx.x; item < total; item += gridDim.x, ++j) {
             const int b = j % META;
-            const int pass = (item >= n_tiles) ? 1 : 0;
+            const int pass = item_pass(item);
             const lb2_conv_io io = p.io[pass];
             mbar_wait(meta_full(b), (j / META) & 1);
             const uint32_t kmask = tile_kmask(b);

@@ -23,7 +23,6 @@ using namespace tc;
 constexpr int THREADS = 512;
 constexpr int MAX_KVOL = 27;
 constexpr int NA = 4;                                 // A slots (32 K-columns each; two per 128-byte row image)
-constexpr int A_LAG = 3;                              // cp.async lookahead in A slots: NA - 1, arrivals are signalled before the next issue
 constexpr int NB = 3;                                 // weight slots (64 K-columns each)
 constexpr int NACC = 4;                               // TMEM accumulators
 constexpr int SLAB_PITCH = 20;                        // floats per slab row (16 + 4: conflict-free 16-byte accesses)
@@ -59,6 +58,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_small(const Params p) 
     const int n_tiles = (M + BM - 1) / BM;
     const int total = n_tiles * p.npass;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // work item -> (tile, pass): heaviest tiles first (the row order sorts rows by neighbour mask, light to heavy), the two guidance
+    // passes of a tile adjacent: the last, partially filled round of the persistent loop holds the cheapest tiles, not the dearest
+    const int pshift = (p.npass == 2) ? 1 : 0;
+    auto item_tile = [&](int item) { return n_tiles - 1 - (item >> pshift); };
+    auto item_pass = [&](int item) { return item & pshift; };
 
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -107,11 +111,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_small(const Params p) 
         asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
         const int t = threadIdx.x;
         const int sub = t & 3, rbase = t >> 2;                          // 16-byte chunk inside the half row / first of this thread's 4 rows
-        int it = 0, arrived = 0, j = 0;
-        Ring ri{0, 0u, NA}, ra{0, 0u, NA};                              // issue position / arrival position
+        int j = 0;
+        Ring ri{0, 0u, NA};                                             // issue position
         auto fetch_row = [&](int item) {                                // output row of this thread's slot in work item `item`
             if (item >= total) return -1;
-            const int slot = ((item >= n_tiles) ? item - n_tiles : item) * BM + t;
+            const int slot = item_tile(item) * BM + t;
             return (slot < M) ? (p.row_perm ? __ldg(p.row_perm + slot) : slot) : -1;
         };
         auto fetch_mask = [&](int row) -> uint32_t {                   // candidate offsets of a row: its neighbour bit mask if the caller has one
@@ -123,7 +127,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_small(const Params p) 
         uint32_t next_mask = fetch_mask(next_row);
         for (int item = blockIdx.x; item < total; item += gridDim.x, ++j) {
             const int b = j % META;
-            const lb2_conv_io io = p.io[(item >= n_tiles) ? 1 : 0];
+            const lb2_conv_io io = p.io[item_pass(item)];
             if (j >= META) mbar_wait(meta_empty(b), ((j / META) - 1) & 1);
             asm volatile("bar.sync 2, 128;" ::: "memory");              // everybody is done reading the previous tile's idx_s
             {
@@ -163,14 +167,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_small(const Params p) 
                 int src[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) src[q] = idx_s[k * BM + rbase + 32 * q];
-                for (int c2 = 0; c2 < p.nhalf; ++c2, ++it, ri.next()) {
-                    if (it >= A_LAG) {                                  // publish the slot issued A_LAG iterations ago BEFORE waiting for a free
-                        cp_async_wait<A_LAG - 1>();                     // slot: its consumer never waits for this iteration's slot to drain
-                        fence_proxy_async();
-                        mbar_arrive(full_a(ra.s));
-                        ra.next();
-                        ++arrived;
-                    }
+                for (int c2 = 0; c2 < p.nhalf; ++c2, ri.next()) {
                     const int s = ri.s;
                     mbar_wait(empty_a(s), ri.par ^ 1u);
                     const uint32_t img = (uint32_t)(s >> 1) * a_stage;
@@ -188,6 +185,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_small(const Params p) 
                             cp_async16(base + off, rp, ok ? 16u : 0u);
                             cp_async16(base + A_TILE + off, rp + (ok ? cw : 0), ok ? 16u : 0u);
                         }
+                        cp_async_arrive_on(full_a(s));                  // published by the hardware when this thread's copies have landed
                     } else {
                         const float* srcp = first ? io.in1 : io.in2;
                         float4 va[4], vb[4];
@@ -209,14 +207,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_small(const Params p) 
                             *reinterpret_cast<uint4*>(gen + off) = hi;
                             *reinterpret_cast<uint4*>(gen + A_TILE + off) = lo;
                         }
+                        fence_proxy_async();                            // generic-proxy stores -> visible to the tensor core's reads
+                        mbar_arrive(full_a(s));
                     }
-                    cp_async_commit();                                  // (empty group on the fp32 path)
                 }
             }
         }
-        cp_async_wait<0>();
-        fence_proxy_async();
-        for (; arrived < it; ++arrived, ra.next()) mbar_arrive(full_a(ra.s));
     } else if (warp < 8) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
         if (warp == 4) {
@@ -314,7 +310,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_small(const Params p) 
         int gcount = 0, j = 0;
         for (int item = blockIdx.x; item < total; item += gridDim.x, ++j) {
             const int b = j % META;
-            const lb2_conv_io& io = p.io[(item >= n_tiles) ? 1 : 0];       // fields are read from the parameter bank when used
+            const lb2_conv_io& io = p.io[item_pass(item)];                // fields are read from the parameter bank when used
             mbar_wait(meta_full(b), (j / META) & 1);
             const uint32_t kmask = tile_kmask(b);
             const int n_off = __popc(kmask);

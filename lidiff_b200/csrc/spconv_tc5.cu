@@ -11,10 +11,10 @@
 // same offset set, so the issued MMA work grows by 3-4 % only (measured on the bench geometry).
 //
 //   per CTA (512 threads, setmaxnreg 56 / 56 / 200 / 200):
-//   WG0 warps 0-3   A producers: cp.async 16 B from the fp16 split companions into the SWIZZLE_128B image; every thread
-//                   signals the LEADER's full_a barrier (mbarrier.arrive.release.cluster through mapa)
+//   WG0 warps 0-3   A producers: cp.async 16 B from the fp16 split companions into the SWIZZLE_128B image; a slot is published by
+//                   cp.async.mbarrier.arrive.noinc the moment its copies land (no wait_group in the issue loop: all 6 slots are lookahead)
 //   WG1 warp 4      rank 0: MMA issuer (elected lane, cta_group::2, commits multicast to both CTAs' barriers)
-//                   rank 1: relay — forwards "my half of the weight slot has landed" to the leader's barrier
+//                   rank 1: relay — forwards "my weight half / my gathered slot has landed" to the leader's barriers
 //       warp 5      weight loader: two bulk copies (hi / lo half tile) per slot into its own shared memory
 //   WG2/WG3 warps 8-15: drain (two-level accumulation: fp32 running total in registers) + fused epilogue, each CTA for its own
 //                   128 rows / TMEM lanes; accumulator release is signalled to the leader (one arrive per warp)
@@ -30,7 +30,6 @@ using namespace tc;
 
 constexpr int THREADS = 512;
 constexpr int NA = 6;                                 // A slots (128 rows x 32 K-columns, hi + lo image: 16 KB each)
-constexpr int A_LAG = NA - 1;                         // cp.async lookahead in A slots; arrivals are signalled before the next issue
 constexpr int SLAB_COLS = 16;
 constexpr int SLAB_PITCH = SLAB_COLS + 4;             // floats per slab row
 constexpr int SLAB_BYTES = 8 * 32 * SLAB_PITCH * 4;   // 8 drain warps x 32 rows
@@ -41,7 +40,7 @@ template <int NCOLS> struct Cfg {
     static constexpr int NACC = 512 / NCOLS;                       // TMEM accumulators (ping-pong / 4-deep)
     static constexpr uint32_t B_HALF = (uint32_t)(NCOLS / 2) * 128u;   // bytes of this CTA's half of one hi (or lo) weight tile
     static constexpr uint32_t B_SLOT = 2u * B_HALF;
-    static constexpr int NBAR = 2 * NA + 3 * NB + 2 * NACC + 2 * META;
+    static constexpr int NBAR = 3 * NA + 3 * NB + 2 * NACC + 2 * META;
     static constexpr size_t SMEM = 1024 + (size_t)(NA / 2) * 2 * A_TILE + (size_t)NB * B_SLOT + SLAB_BYTES + META * BM * sizeof(int) +
                                    META * BM * sizeof(uint32_t) + 4 * META * sizeof(uint32_t) + NBAR * 8 + 64;
 };
@@ -105,6 +104,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_spconv
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_rank();
     const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    // work item -> (super-tile, pass): heaviest super-tiles first (the row order sorts rows by neighbour mask, light to heavy), the
+    // two guidance passes of a super-tile adjacent: the last, partially filled round of the persistent loop then holds the cheapest
+    // tiles (centre-only rows) instead of the most expensive ones
+    const int pshift = (p.npass == 2) ? 1 : 0;
+    auto item_tile = [&](int item) { return n_stiles - 1 - (item >> pshift); };
+    auto item_pass = [&](int item) { return item & pshift; };
 
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;               // same offset in both CTAs (same kernel, same dynamic size)
@@ -119,18 +124,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_spconv
     uint64_t* bars = reinterpret_cast<uint64_t*>(wmask + 4 * META);
     uint32_t* misc = reinterpret_cast<uint32_t*>(bars + C::NBAR);
     const uint32_t bar0 = smem_u32(bars);
-    auto full_a = [&](int s) { return bar0 + 8u * s; };                              // leader's: 256 producer threads of both CTAs
-    auto empty_a = [&](int s) { return bar0 + 8u * (NA + s); };                      // per CTA: multicast commit
-    auto full_b = [&](int s) { return bar0 + 8u * (2 * NA + s); };                   // per CTA: bulk-copy transaction bytes
-    auto full_bp = [&](int s) { return bar0 + 8u * (2 * NA + NB + s); };             // leader's: the peer's relay
-    auto empty_b = [&](int s) { return bar0 + 8u * (2 * NA + 2 * NB + s); };         // per CTA: multicast commit
-    auto acc_full = [&](int b) { return bar0 + 8u * (2 * NA + 3 * NB + b); };        // per CTA: multicast commit
-    auto acc_empty = [&](int b) { return bar0 + 8u * (2 * NA + 3 * NB + NACC + b); };   // leader's: 16 drain warps of both CTAs
-    auto meta_full = [&](int b) { return bar0 + 8u * (2 * NA + 3 * NB + 2 * NACC + b); };
-    auto meta_empty = [&](int b) { return bar0 + 8u * (2 * NA + 3 * NB + 2 * NACC + META + b); };
+    auto full_a = [&](int s) { return bar0 + 8u * s; };                              // per CTA: its 128 producer threads (cp.async completion)
+    auto full_ap = [&](int s) { return bar0 + 8u * (NA + s); };                      // leader's: the peer's relay
+    auto empty_a = [&](int s) { return bar0 + 8u * (2 * NA + s); };                  // per CTA: multicast commit
+    auto full_b = [&](int s) { return bar0 + 8u * (3 * NA + s); };                   // per CTA: bulk-copy transaction bytes
+    auto full_bp = [&](int s) { return bar0 + 8u * (3 * NA + NB + s); };             // leader's: the peer's relay
+    auto empty_b = [&](int s) { return bar0 + 8u * (3 * NA + 2 * NB + s); };         // per CTA: multicast commit
+    auto acc_full = [&](int b) { return bar0 + 8u * (3 * NA + 3 * NB + b); };        // per CTA: multicast commit
+    auto acc_empty = [&](int b) { return bar0 + 8u * (3 * NA + 3 * NB + NACC + b); };   // leader's: 16 drain warps of both CTAs
+    auto meta_full = [&](int b) { return bar0 + 8u * (3 * NA + 3 * NB + 2 * NACC + b); };
+    auto meta_empty = [&](int b) { return bar0 + 8u * (3 * NA + 3 * NB + 2 * NACC + META + b); };
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NA; ++s) { mbar_init(full_a(s), 256); mbar_init(empty_a(s), 1); }
+        for (int s = 0; s < NA; ++s) { mbar_init(full_a(s), 128); mbar_init(full_ap(s), 1); mbar_init(empty_a(s), 1); }
         for (int s = 0; s < NB; ++s) { mbar_init(full_b(s), 1); mbar_init(full_bp(s), 1); mbar_init(empty_b(s), 1); }
         for (int b = 0; b < NACC; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), 16); }
         for (int b = 0; b < META; ++b) { mbar_init(meta_full(b), 1); mbar_init(meta_empty(b), 258); }   // warp 4 + loader + 256 drain threads
@@ -152,12 +158,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_spconv
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         const int t = threadIdx.x;
         const int sub = t & 3, rbase = t >> 2;                          // 16-byte chunk inside the half row / first of this thread's 4 rows
-        int it = 0, arrived = 0, j = 0;
-        Ring ri{0, 0u, NA}, ra{0, 0u, NA};
-        const uint32_t leader_full_a0 = map_to_cta(full_a(0), 0);
+        int j = 0;
+        Ring ri{0, 0u, NA};
         auto fetch_row = [&](int item, uint32_t r) {                    // output row of slot t of CTA r's tile in work item `item`
             if (item >= total) return -1;
-            const int slot = ((item >= n_stiles) ? item - n_stiles : item) * 2 * BM + (int)r * BM + t;
+            const int slot = item_tile(item) * 2 * BM + (int)r * BM + t;
             return (slot < M) ? (p.row_perm ? __ldg(p.row_perm + slot) : slot) : -1;
         };
         auto fetch_mask = [&](int row) -> uint32_t {                   // offsets a row has a neighbour at
@@ -169,7 +174,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_spconv
         uint32_t next_mask = fetch_mask(next_row), next_mask_p = fetch_mask(next_row_p);
         for (int item = pair; item < total; item += npairs, ++j) {
             const int b = j % META;
-            const int pass = (item >= n_stiles) ? 1 : 0;
+            const int pass = item_pass(item);
             const lb2_conv_io io = p.io[pass];
             if (j >= META) mbar_wait(meta_empty(b), ((j / META) - 1) & 1);
             {
@@ -204,14 +209,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_spconv
             while (km) {
                 km &= km - 1;
                 if (km) load_src(__ffs(km) - 1, nxt);                 // prefetch the next offset's rows behind this offset's copies
-                for (int c2 = 0; c2 < 2 * p.nchunks; ++c2, ++it, ri.next()) {      // c2 = 2 * chunk + half
-                    if (it >= A_LAG) {                                  // publish the slot issued A_LAG iterations ago BEFORE waiting for a free one
-                        cp_async_wait<A_LAG - 1>();
-                        fence_proxy_async();
-                        mbar_arrive_cluster(leader_full_a0 + 8u * ra.s);
-                        ra.next();
-                        ++arrived;
-                    }
+                for (int c2 = 0; c2 < 2 * p.nchunks; ++c2, ri.next()) {            // c2 = 2 * chunk + half
                     const int s = ri.s;
                     mbar_wait(empty_a(s), ri.par ^ 1u);
                     const uint32_t a_hi_u = base + (uint32_t)(s >> 1) * a_stage;
@@ -229,15 +227,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_spconv
                         cp_async16(a_hi_u + off, rp, ok ? 16u : 0u);
                         cp_async16(a_hi_u + A_TILE + off, rp + (ok ? cw : 0), ok ? 16u : 0u);
                     }
-                    cp_async_commit();
+                    cp_async_arrive_on(full_a(s));                      // published by the hardware when this thread's copies have landed
                 }
 #pragma unroll
                 for (int q = 0; q < 4; ++q) src[q] = nxt[q];
             }
         }
-        cp_async_wait<0>();
-        fence_proxy_async();
-        for (; arrived < it; ++arrived, ra.next()) mbar_arrive_cluster(leader_full_a0 + 8u * ra.s);
     } else if (warp < 8) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         if (warp == 4 && rank == 0) {
@@ -267,7 +262,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_spconv
 #pragma unroll
                         for (int half = 0; half < 2; ++half, rq.next()) {
                             const int sa = rq.s;
-                            mbar_wait_cluster(full_a(sa), rq.par);
+                            mbar_wait(full_a(sa), rq.par);                  // my gathered rows
+                            mbar_wait_cluster(full_ap(sa), rq.par);         // the peer's
                             tc_fence_after();
                             const uint32_t a_hi = base + (uint32_t)(sa >> 1) * a_stage, a_lo = a_hi + A_TILE;
                             const uint64_t dah0 = make_desc(a_hi) + 4u * (uint32_t)(sa & 1), dal0 = make_desc(a_lo) + 4u * (uint32_t)(sa & 1);
@@ -298,10 +294,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_spconv
                 __syncwarp();
             }
         } else if (warp == 4 && lane == 0) {
-            // =========================== rank 1: relay of "my weight half has landed" to the leader ===========================
+            // =========================== rank 1: relay of "my weight half / my gathered rows have landed" to the leader,
+            //                             in the order the MMA warp consumes them ===========================
             int j = 0;
-            Ring r{0, 0u, NB};
-            const uint32_t leader_full_bp0 = map_to_cta(full_bp(0), 0);
+            Ring r{0, 0u, NB}, ra{0, 0u, NA};
+            const uint32_t leader_full_bp0 = map_to_cta(full_bp(0), 0), leader_full_ap0 = map_to_cta(full_ap(0), 0);
             for (int item = pair; item < total; item += npairs, ++j) {
                 const int b = j % META;
                 mbar_wait(meta_full(b), (j / META) & 1);
@@ -310,6 +307,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_spconv
                     for (int c = 0; c < p.nchunks; ++c, r.next()) {
                         mbar_wait(full_b(r.s), r.par);
                         mbar_arrive_cluster(leader_full_bp0 + 8u * r.s);
+#pragma unroll
+                        for (int half = 0; half < 2; ++half, ra.next()) {
+                            mbar_wait(full_a(ra.s), ra.par);
+                            mbar_arrive_cluster(leader_full_ap0 + 8u * ra.s);
+                        }
                     }
                 }
                 mbar_arrive(meta_empty(b));
@@ -354,7 +356,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_spconv
         int gcount = 0, j = 0;
         for (int item = pair; item < total; item += npairs, ++j) {
             const int b = j % META;
-            const int pass = (item >= n_stiles) ? 1 : 0;
+            const int pass = item_pass(item);
             const lb2_conv_io io = p.io[pass];
             mbar_wait(meta_full(b), (j / META) & 1);
             const uint32_t kmask = tile_kmask(b);

@@ -147,6 +147,12 @@ __device__ __forceinline__ float4 load_residual4(const float* res, const void* r
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
+// the calling thread's arrival on `bar` is triggered by the hardware once all its prior cp.async copies have landed (counts against the
+// barrier's expected arrivals): a stage is published the moment its last byte arrives, without the issuing thread waiting for it.
+// CUTLASS' own cp.async -> UMMA mainloop (sm100_mma_cpasync_warpspecialized.hpp) pairs exactly this with tcgen05.mma.
+__device__ __forceinline__ void cp_async_arrive_on(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }

@@ -265,6 +265,7 @@ class DenoiseEngine:
         self._eager_steps = 0
         self.graph_replays = 0
         self.replayed_launches = 0       # kernels launched through graph replays (the library's own counter only sees eager launches)
+        self._captured_launches = 0
         self._prepare_time_tables()
         self._prepare_uncond()
 
@@ -631,6 +632,7 @@ class DenoiseEngine:
                 with torch.cuda.graph(g):
                     self.step(i, st["xa"], st["xb"], st["ca"], st["cb"], st["x_init"], noise_i, st["x0s"])
                 ent = self._graphs[key] = (g, self.h.launch_count() - l0)
+                self._captured_launches += ent[1]                      # counted by the library although capture executes nothing
                 self._have_x0 = have                                   # capture does not execute: the replay below is this step
             ent[0].replay()
             self._have_x0 = True
@@ -643,18 +645,20 @@ class DenoiseEngine:
 
     def launches(self) -> int:
         """kernels launched on behalf of this engine's handle: eager launches counted by the library + graph-replayed ones"""
-        return self.h.launch_count() + self.replayed_launches
+        return self.h.launch_count() - self._captured_launches + self.replayed_launches
 
     def run(self, x_init: torch.Tensor, x_feats: torch.Tensor, step_noise=None, n_steps=None, return_device=False, fresh=True):
         """x_init (1,N,3) fp64 conditioning scan, x_feats (1,N,3) noisy start.  Returns final x_t.F (N,3)."""
         dev, N = self.device, self.N
         st = self.start(x_init, x_feats, fresh=fresh)
         T = self.T if n_steps is None else n_steps
-        if step_noise is None:
-            step_noise = torch.randn((T, N, 3), device=dev)
-        step_noise = step_noise.reshape(-1, N, 3).to(device=dev, dtype=torch.float32).contiguous()
+        if step_noise is not None:
+            step_noise = step_noise.reshape(-1, N, 3).to(device=dev, dtype=torch.float32).contiguous()
         for i in range(T):
-            self.advance(st, step_noise[i])
+            # without injected noise: one fp32 draw per step, in the order diffusers' step() draws it (the operator path and the
+            # reference consume the torch RNG stream identically); no (T, N, 3) tensor is materialised (2.2 GB at T = 1000)
+            nz = step_noise[i] if step_noise is not None else torch.randn((1, N, 3), device=dev, dtype=torch.float32)[0]
+            self.advance(st, nz)
         if return_device:
             return st["xa"]
         out = st["xa"].cpu().numpy()

@@ -67,7 +67,9 @@ class CoordinateManager:
         d_n = torch.zeros(1, dtype=torch.int32, device=dev)
         h.unique_build(in_f, in_i, None, n_in, ts_floor, grid, out, inv, d_n, h.unique_scratch(n_in))
         n = int(d_n.item())
-        if h.read_status() & 1:
+        # only the level-0 insertion can leave the key range (coarser levels floor coordinates that are already in range): one status
+        # read per TensorField, right behind the build that could have raised it (the word is per device and cleared by the read)
+        if ts_floor == 0 and (h.read_status() & 1):
             raise RuntimeError("lidiff_b200.me: coordinate outside the supported key range (|x| < 131072 voxels, batch < 1024)")
         return _Level(out[:n], n, d_n, grid, inv)
 

@@ -34,7 +34,8 @@ class PointCloud:
 
     def farthest_point_down_sample(self, num_samples):
         """open3d 0.17 semantics: start at index 0, repeatedly add the point farthest from the selected set (first index on
-        ties), return the selected points in selection order.  GPU only (lb2_farthest_point_sample); no CPU fallback."""
+        ties); like open3d's SelectByIndex the result lists the selected points in ORIGINAL index order.  GPU only
+        (lb2_farthest_point_sample); no CPU fallback."""
         import torch
         from lidiff_b200.preprocess import farthest_point_sample
         if not torch.cuda.is_available():
@@ -49,8 +50,11 @@ class PointCloud:
         return out
 
     def estimate_normals(self, search_param=None, fast_normal_computation=True):
-        """PCA normal of the k nearest neighbours (k = 30 as open3d's default KNN search), sign left unoriented.  Brute-force
-        k-NN in chunks with torch (on the GPU when there is one); post-processing only, not on the timed path."""
+        """PCA normal of the k nearest neighbours (k = 30 as open3d's default KNN search), sign left unoriented.  Post-processing
+        only, not on the timed path.  The k-NN search is bucketed: points are sorted into cells of the k-th-neighbour scale and
+        every query chunk (the points of a block of consecutive cells in sorted order) searches only the candidates of its own
+        bounding box grown by the current search radius; a chunk whose k-th distance exceeds the margin is redone with a larger one.
+        Exact (same neighbours as a brute-force search), O(n * local density) instead of O(n^2) distance evaluations."""
         import torch
         k = getattr(search_param, "knn", None) or getattr(search_param, "max_nn", None) or 30
         dev = "cuda" if torch.cuda.is_available() else "cpu"
@@ -59,13 +63,33 @@ class PointCloud:
         k = min(k, n)
         out = torch.zeros((n, 3), dtype=torch.float32, device=dev)
         if n >= 3:
-            chunk = max(1, min(n, (1 << 26) // max(n, 1)))
+            lo, hi = p.min(0).values, p.max(0).values
+            vol = float(torch.clamp(hi - lo, min=1e-3).prod())
+            cell = max((vol * k / n) ** (1.0 / 3.0), 1e-3)                      # a cell holds ~k points at the mean density
+            ijk = torch.floor((p - lo) / cell).long()
+            dims = ijk.max(0).values + 1
+            key = (ijk[:, 2] * dims[1] + ijk[:, 1]) * dims[0] + ijk[:, 0]
+            order = torch.argsort(key)
+            ps = p[order]
+            chunk = 4096
             for a in range(0, n, chunk):
-                q = p[a:a + chunk]
-                idx = torch.cdist(q, p).topk(k, dim=1, largest=False).indices         # (c, k)
-                nb = p[idx]                                                           # (c, k, 3)
+                q = ps[a:a + chunk]
+                qlo, qhi = q.min(0).values, q.max(0).values
+                margin = 2.0 * cell
+                while True:
+                    m = ((ps >= qlo - margin) & (ps <= qhi + margin)).all(1)
+                    cand = ps[m]
+                    if cand.shape[0] >= k:
+                        d, idx = torch.cdist(q, cand).topk(k, dim=1, largest=False)
+                        if float(d[:, -1].max()) <= margin or cand.shape[0] == n:    # every k-th neighbour lies inside the searched box
+                            break
+                    if cand.shape[0] == n:
+                        d, idx = torch.cdist(q, cand).topk(k, dim=1, largest=False)
+                        break
+                    margin *= 2.0
+                nb = cand[idx]                                                        # (c, k, 3)
                 c = nb - nb.mean(1, keepdim=True)
                 cov = c.transpose(1, 2) @ c
-                out[a:a + chunk] = torch.linalg.eigh(cov.double())[1][:, :, 0].float()     # eigenvector of the smallest eigenvalue
+                out[order[a:a + chunk]] = torch.linalg.eigh(cov.double())[1][:, :, 0].float()   # eigenvector of the smallest eigenvalue
         self._normals = Vector3dVector(out.cpu().numpy())
         return True

@@ -136,6 +136,10 @@ def test_pipeline_paths_agree_and_complete_scan_runs(setup):
     b = pipe.engine().run(dscan, x_feats, noise)
     d = np.abs(a - b).max(1)
     print(f"operator path vs engine after 4 steps: median {np.median(d):.2e}, 99% {np.quantile(d, 0.99):.2e}, max {d.max():.2e}")
-    assert np.median(d) < 1e-4 and (d > 1e-2).mean() < 0.02      # voxel flips make a few points diverge
+    # Two fp32 paths over a 4-step (250 timesteps per step) trajectory: a point whose coordinate sits within rounding distance of a
+    # voxel boundary lands in another voxel on one path, which changes that voxel's mean feature and then the trajectory of its
+    # members.  Stated bound: half of the points within 5e-5 m, 90 % within 1 mm, fewer than 1 % further than 1 cm apart.
+    # (Per-step agreement on identical inputs is asserted in test_engine_step_matches_oracle.)
+    assert np.median(d) < 5e-5 and np.quantile(d, 0.9) < 1e-3 and (d > 1e-2).mean() < 0.01
     refined, post = pipe.complete_scan(scan, start_noise=start, step_noise=noise, preprocessed=True)
     assert refined.shape[0] == 6 * post.shape[0] and np.isfinite(refined).all()
