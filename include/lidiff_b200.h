@@ -53,7 +53,9 @@ int64_t     lb2_launch_count(void* handle);
 #define LB2_OPT_TC_PERSISTENT 3   /* persistent kernels for LB2_ALGO_TC (default 1; 0 = one CTA per tile) */
 #define LB2_OPT_TC_FULL_LAG   4   /* generic persistent kernel: S-1 gather lookahead (default 0) */
 #define LB2_OPT_TC_NSPLIT     5   /* per-tile kernel: split Cout 256 over two CTAs (default 0) */
-#define LB2_OPT_COUNT         6
+#define LB2_OPT_STREAM_STORES 6   /* conv epilogues store with the evict-first policy (st.global.cs): outputs stream through L2 instead of
+                                     displacing the feature rows the gathers re-read (default 1) */
+#define LB2_OPT_COUNT         7
 int         lb2_set_option(void* handle, int option, int value);
 int         lb2_get_option(void* handle, int option);   /* value, or a negative LB2_ERR_* */
 /* synchronising read-and-clear of the device status word; bit0 = a coordinate fell outside the key
@@ -107,10 +109,13 @@ int lb2_kernel_map(void* h, void* stream, lb2_grid grid_in, const int32_t* out_c
 /* Execution order of the output rows for lb2_spconv_forward (no reference counterpart: scheduling only).
  * perm[0..n) = the rows 0..n-1 sorted by their neighbour mask (kvol 27: centre-only rows, rows with one neighbour grouped
  * by it, then the rest in mask order; kvol <= 8: by the 8-bit mask) so that 128-row tiles skip unpopulated kernel offsets.
- * Results do not depend on the order.  scratch >= lb2_row_order_scratch_bytes(n_cap). */
+ * Results do not depend on the order.  scratch >= lb2_row_order_scratch_bytes(n_cap).
+ * coords (optional, kvol 27 only): the rows' int32 [b,x,y,z] coordinates; rows of equal mask are then ordered by the Morton code of
+ * (x,y,z) >> coord_shift (coord_shift = log2 of the level's tensor stride), which makes the tiles of large mask groups spatially
+ * compact (L2 locality of the gathers). */
 size_t lb2_row_order_scratch_bytes(int32_t n_cap);
 int lb2_row_order(void* h, void* stream, const uint32_t* row_mask, const int32_t* d_n, int32_t n_cap,
-                  int32_t kvol, int32_t* perm, void* scratch);
+                  int32_t kvol, int32_t* perm, void* scratch, const int32_t* coords, int32_t coord_shift);
 
 /* ---- sparse convolution  — replaces ME.MinkowskiConvolution(+Transpose) forward, with the
  * MinkowskiBatchNorm(eval)/MinkowskiReLU/residual-add/ME.cat/gate-multiply that follow it in

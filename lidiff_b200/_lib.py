@@ -15,7 +15,7 @@ import torch
 _SO = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_C", "liblidiff_b200.so")
 
 ALGO_AUTO, ALGO_FFMA, ALGO_TC, ALGO_TC_TILE = 0, 1, 2, 3
-OPT_TC_PAIR, OPT_TC_N256, OPT_TC_SMALL, OPT_TC_PERSISTENT, OPT_TC_FULL_LAG, OPT_TC_NSPLIT = range(6)
+OPT_TC_PAIR, OPT_TC_N256, OPT_TC_SMALL, OPT_TC_PERSISTENT, OPT_TC_FULL_LAG, OPT_TC_NSPLIT, OPT_STREAM_STORES = range(7)
 
 
 class Grid(C.Structure):
@@ -105,7 +105,7 @@ class Lib:
         d.lb2_unique_build.argtypes = [vp, vp, vp, vp, vp, i32, i32, Grid, vp, vp, vp, vp]
         d.lb2_voxel_mean.argtypes = [vp, vp, vp, vp, i32, i32, vp, i32, vp, vp]
         d.lb2_kernel_map.argtypes = [vp, vp, Grid, vp, vp, i32, i32, i32, vp, i64, vp, vp]
-        d.lb2_row_order.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp]
+        d.lb2_row_order.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, vp, i32]
         d.lb2_row_order_scratch_bytes.restype = C.c_size_t
         d.lb2_row_order_scratch_bytes.argtypes = [i32]
         d.lb2_spconv_forward.argtypes = [vp, vp, C.POINTER(ConvDesc), C.c_int]
@@ -209,9 +209,9 @@ class Handle:
     def row_order_scratch_bytes(self, n_cap) -> int:
         return int(self.dll.lb2_row_order_scratch_bytes(int(n_cap)))
 
-    def row_order(self, row_mask, d_n, n_cap, kvol, perm, scratch):
-        self._check(self.dll.lb2_row_order(self.hp, self._stream(), _ptr(row_mask), _ptr(d_n), int(n_cap), int(kvol), _ptr(perm), _ptr(scratch)),
-                    "lb2_row_order")
+    def row_order(self, row_mask, d_n, n_cap, kvol, perm, scratch, coords=None, coord_shift=0):
+        self._check(self.dll.lb2_row_order(self.hp, self._stream(), _ptr(row_mask), _ptr(d_n), int(n_cap), int(kvol), _ptr(perm), _ptr(scratch),
+                                           _ptr(coords), int(coord_shift)), "lb2_row_order")
 
     # -- conv ----------------------------------------------------------------------------------------
     def spconv(self, desc: ConvDesc, algo: int = ALGO_AUTO):

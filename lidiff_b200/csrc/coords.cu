@@ -34,6 +34,7 @@ extern "C" int lb2_create(int device, void** handle) {
         const char* lag = getenv("LB2_TC_LAG");
         h->opt[LB2_OPT_TC_FULL_LAG] = (lag && lag[0] == 'f') ? 1 : 0;
         h->opt[LB2_OPT_TC_NSPLIT] = env("LB2_TC_NSPLIT", 0);
+        h->opt[LB2_OPT_STREAM_STORES] = env("LB2_STREAM_STORES", 1);
     }
     if (cudaMalloc(&h->d_status, sizeof(int32_t)) != cudaSuccess) { delete h; return LB2_ERR_CUDA; }
     cudaMemset(h->d_status, 0, sizeof(int32_t));
@@ -428,20 +429,45 @@ __device__ __forceinline__ unsigned ro_key27(unsigned mask) {
     return ((__popc(extras) >= 2) ? (1u << 26) : 0u) | k26;
 }
 
-// pass 0 reads the masks (key computed on the fly, value = row index), later passes read the ping-pong buffers
-__device__ __forceinline__ unsigned rs_key(const unsigned* __restrict__ keys_in, const unsigned* __restrict__ mask, int i) {
-    return keys_in ? keys_in[i] : ro_key27(mask[i]);
+// 27-bit Morton code of a row's voxel coordinate (9 bits per axis of coord >> shift; wraps beyond 512 cells: locality hint only)
+__device__ __forceinline__ unsigned ro_part9(unsigned v) {           // 9 bits -> every third bit
+    v &= 0x1ffu;
+    v = (v | (v << 16)) & 0x030000ffu;
+    v = (v | (v << 8)) & 0x0300f00fu;
+    v = (v | (v << 4)) & 0x030c30c3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+__device__ __forceinline__ unsigned ro_morton(const int4 c, int shift) {
+    return ro_part9((unsigned)(c.y >> shift)) | (ro_part9((unsigned)(c.z >> shift)) << 1) | (ro_part9((unsigned)(c.w >> shift)) << 2);
 }
 
-__global__ void __launch_bounds__(256) k_rs_hist(const unsigned* __restrict__ keys_in, const unsigned* __restrict__ mask,
-                                                 const int* __restrict__ d_n, int n_cap, int shift, int* __restrict__ hist,
+// where a pass takes its sort key from
+struct RsSrc {
+    const unsigned* keys;        // mode 0: keys[i] (ping-pong buffer of the previous pass)
+    const unsigned* mask;        // mode 1: ro_key27(mask[i])            (first pass of a mask-only sort, value = i)
+                                 // mode 3: ro_key27(mask[vals_in[i]])   (first mask pass behind the Morton passes)
+    const int4* coords;          // mode 2: ro_morton(coords[i])          (first Morton pass, value = i)
+    const int* vals;             // values of the previous pass or NULL (value = i)
+    int mode, coord_shift;
+};
+__device__ __forceinline__ unsigned rs_key(const RsSrc& s, int i) {
+    switch (s.mode) {
+        case 0: return s.keys[i];
+        case 1: return ro_key27(s.mask[i]);
+        case 2: return ro_morton(s.coords[i], s.coord_shift);
+        default: return ro_key27(s.mask[s.vals[i]]);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_rs_hist(const RsSrc src, const int* __restrict__ d_n, int n_cap, int shift, int* __restrict__ hist,
                                                  int* __restrict__ total) {
     __shared__ int sh[RS_BINS];
     for (int i = threadIdx.x; i < RS_BINS; i += blockDim.x) sh[i] = 0;
     __syncthreads();
     const int n = d_n ? min(*d_n, n_cap) : n_cap;
     const int lo = blockIdx.x * RS_CHUNK, hi = min(lo + RS_CHUNK, n);
-    for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) atomicAdd(&sh[(rs_key(keys_in, mask, i) >> shift) & (RS_BINS - 1)], 1);
+    for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) atomicAdd(&sh[(rs_key(src, i) >> shift) & (RS_BINS - 1)], 1);
     __syncthreads();
     for (int i = threadIdx.x; i < RS_BINS; i += blockDim.x) {
         hist[blockIdx.x * RS_BINS + i] = sh[i];                                                        // block-major: coalesced both ways
@@ -450,10 +476,10 @@ __global__ void __launch_bounds__(256) k_rs_hist(const unsigned* __restrict__ ke
 }
 
 // stable scatter: warp w of block b owns rows [b*2048 + w*256, +256) and walks them in order, 32 at a time
-__global__ void __launch_bounds__(32 * RS_WARPS) k_rs_scatter(const unsigned* __restrict__ keys_in, const int* __restrict__ vals_in,
-                                                              const unsigned* __restrict__ mask, const int* __restrict__ d_n, int n_cap,
+__global__ void __launch_bounds__(32 * RS_WARPS) k_rs_scatter(const RsSrc src, const int* __restrict__ d_n, int n_cap,
                                                               int shift, const int* __restrict__ hist, const int* __restrict__ total,
                                                               unsigned* __restrict__ keys_out, int* __restrict__ vals_out) {
+    const int* __restrict__ vals_in = src.vals;
     __shared__ int cnt[RS_WARPS][RS_BINS];
     __shared__ int first[RS_BINS];                 // global position of the first row of (bin, this block)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -485,7 +511,7 @@ __global__ void __launch_bounds__(32 * RS_WARPS) k_rs_scatter(const unsigned* __
     const int w0 = blockIdx.x * RS_CHUNK + warp * (RS_CHUNK / RS_WARPS);
     for (int g = 0; g < RS_CHUNK / RS_WARPS / 32; ++g) {                       // this warp's digit histogram
         const int i = w0 + g * 32 + lane;
-        if (i < n) atomicAdd(&cnt[warp][(rs_key(keys_in, mask, i) >> shift) & (RS_BINS - 1)], 1);
+        if (i < n) atomicAdd(&cnt[warp][(rs_key(src, i) >> shift) & (RS_BINS - 1)], 1);
     }
     __syncthreads();
     for (int bin = threadIdx.x; bin < RS_BINS; bin += blockDim.x) {            // -> first position of (bin, warp)
@@ -498,7 +524,7 @@ __global__ void __launch_bounds__(32 * RS_WARPS) k_rs_scatter(const unsigned* __
         const bool ok = i < n;
         const unsigned active = __ballot_sync(0xffffffffu, ok);
         if (ok) {
-            const unsigned key = rs_key(keys_in, mask, i);
+            const unsigned key = rs_key(src, i);
             const int val = vals_in ? vals_in[i] : i;
             const int d = (key >> shift) & (RS_BINS - 1);
             const unsigned peers = __match_any_sync(active, d);
@@ -561,37 +587,45 @@ __global__ void k_ro_scatter(const unsigned* __restrict__ mask, const int* __res
 
 static int rs_blocks(int n_cap) { return cdiv(n_cap, RS_CHUNK); }
 
-// scratch layout: [nblk][RS_BINS] histogram, [3][RS_BINS] per-pass bin totals, then keys A, keys B, vals A (n_cap each);
+// scratch layout: [nblk][RS_BINS] histogram, [6][RS_BINS] per-pass bin totals, then keys A, keys B, vals A (n_cap each);
 // kvol <= 8 uses the first RO_BINS ints only
 extern "C" size_t lb2_row_order_scratch_bytes(int32_t n_cap) {
-    return ((size_t)RS_BINS * (rs_blocks(n_cap) + 3) + 3 * (size_t)n_cap) * sizeof(int);
+    return ((size_t)RS_BINS * (rs_blocks(n_cap) + 6) + 3 * (size_t)n_cap) * sizeof(int);
 }
 
 extern "C" int lb2_row_order(void* handle, void* stream, const uint32_t* row_mask, const int32_t* d_n, int32_t n_cap,
-                             int32_t kvol, int32_t* perm, void* scratch) {
+                             int32_t kvol, int32_t* perm, void* scratch, const int32_t* coords, int32_t coord_shift) {
     Lb2Handle* h = (Lb2Handle*)handle;
     LB2_REQUIRE(h, h && row_mask && perm && scratch && n_cap > 0 && (kvol == 27 || (kvol >= 1 && kvol <= 8)), "row_order");
+    LB2_REQUIRE(h, coord_shift >= 0 && coord_shift < 24, "row_order coord_shift");
     cudaStream_t s = (cudaStream_t)stream;
     if (kvol == 27) {
         const int nblk = rs_blocks(n_cap);
         int* hist = (int*)scratch;
         int* total = hist + (size_t)RS_BINS * nblk;
-        unsigned* keys_a = (unsigned*)(total + 3 * RS_BINS);
-        if (cudaMemsetAsync(total, 0, 3 * RS_BINS * sizeof(int), s) != cudaSuccess) return lb2_fail(h, LB2_ERR_CUDA, "row_order memset%s", "");
+        unsigned* keys_a = (unsigned*)(total + 6 * RS_BINS);
+        if (cudaMemsetAsync(total, 0, 6 * RS_BINS * sizeof(int), s) != cudaSuccess) return lb2_fail(h, LB2_ERR_CUDA, "row_order memset%s", "");
         unsigned* keys_b = keys_a + n_cap;
         int* vals_a = (int*)(keys_b + n_cap);
-        // pass 0: masks -> (keys_a, vals_a); pass 1: -> (keys_b, perm); pass 2: -> (none, vals_a)?  keep the final values in perm:
-        //   0: mask   -> keys_a, perm        1: keys_a, perm -> keys_b, vals_a        2: keys_b, vals_a -> perm
-        const unsigned* kin[3] = {nullptr, keys_a, keys_b};
-        const int* vin[3] = {nullptr, perm, vals_a};
-        unsigned* kout[3] = {keys_a, keys_b, nullptr};
-        int* vout[3] = {perm, vals_a, perm};
-        for (int pass = 0; pass < 3; ++pass) {
-            const int shift = pass * RS_BITS;
-            k_rs_hist<<<nblk, 256, 0, s>>>(kin[pass], row_mask, d_n, n_cap, shift, hist, total + pass * RS_BINS);
+        // LSD radix sort, 9 bits per pass.  Without coordinates: 3 passes on the mask key, values perm -> vals_a -> perm.
+        // With coordinates: 3 passes on the rows' Morton code first (values vals_a -> perm -> vals_a), then the 3 mask passes
+        // (perm -> vals_a -> perm): rows of equal mask end up in Morton order, i.e. a 128-row tile of a large mask group covers a
+        // compact block of voxels whose gathers re-hit the same input rows in L2.
+        const int npass = coords ? 6 : 3;
+        for (int pass = 0; pass < npass; ++pass) {
+            const int mp = coords ? pass - 3 : pass;                    // index among the mask passes (< 0: Morton pass)
+            const bool to_perm = coords ? (pass & 1) : !(pass & 1);
+            RsSrc src;
+            src.mask = row_mask; src.coords = (const int4*)coords; src.coord_shift = coord_shift;
+            src.keys = (pass & 1) ? keys_a : keys_b;
+            src.vals = (pass == 0) ? nullptr : (to_perm ? vals_a : perm);
+            src.mode = (pass == 0) ? (coords ? 2 : 1) : ((coords && pass == 3) ? 3 : 0);
+            unsigned* kout = (pass == npass - 1 || (coords && pass == 2)) ? nullptr : ((pass & 1) ? keys_b : keys_a);
+            int* vout = to_perm ? perm : vals_a;
+            const int shift = (mp >= 0 ? mp : pass) * RS_BITS;
+            k_rs_hist<<<nblk, 256, 0, s>>>(src, d_n, n_cap, shift, hist, total + pass * RS_BINS);
             LB2_POST_LAUNCH(h, "k_rs_hist");
-            k_rs_scatter<<<nblk, 32 * RS_WARPS, 0, s>>>(kin[pass], vin[pass], row_mask, d_n, n_cap, shift, hist, total + pass * RS_BINS,
-                                                        kout[pass], vout[pass]);
+            k_rs_scatter<<<nblk, 32 * RS_WARPS, 0, s>>>(src, d_n, n_cap, shift, hist, total + pass * RS_BINS, kout, vout);
             LB2_POST_LAUNCH(h, "k_rs_scatter");
         }
         return LB2_OK;
@@ -747,10 +781,11 @@ extern "C" int lb2_nn_tree_build(void* handle, void* stream, const int32_t* k_co
     unsigned* kout[3] = {keys_b, codes, nullptr};
     int* vout[3] = {vals_a, vals_b, vals_a};
     for (int pass = 0; pass < 3; ++pass) {
-        k_rs_hist<<<nblk, 256, 0, s>>>(kin[pass], nullptr, d_nk, nk_cap, pass * RS_BITS, hist, total + pass * RS_BINS);
+        RsSrc src;
+        src.keys = kin[pass]; src.mask = nullptr; src.coords = nullptr; src.vals = vin[pass]; src.mode = 0; src.coord_shift = 0;
+        k_rs_hist<<<nblk, 256, 0, s>>>(src, d_nk, nk_cap, pass * RS_BITS, hist, total + pass * RS_BINS);
         LB2_POST_LAUNCH(h, "k_rs_hist");
-        k_rs_scatter<<<nblk, 32 * RS_WARPS, 0, s>>>(kin[pass], vin[pass], nullptr, d_nk, nk_cap, pass * RS_BITS, hist, total + pass * RS_BINS,
-                                                    kout[pass], vout[pass]);
+        k_rs_scatter<<<nblk, 32 * RS_WARPS, 0, s>>>(src, d_nk, nk_cap, pass * RS_BITS, hist, total + pass * RS_BINS, kout[pass], vout[pass]);
         LB2_POST_LAUNCH(h, "k_rs_scatter");
     }
     k_nt_gather<<<cdiv(slots, 256), 256, 0, s>>>((const int4*)k_coords, d_nk, nk_cap, vals_a, slots, skeys, sbatch);

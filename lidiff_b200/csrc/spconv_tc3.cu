@@ -46,6 +46,7 @@ struct Params {
     const int* row_perm;
     const unsigned* row_mask;
     int nchunks, group, npass;
+    int cs;                     // evict-first epilogue stores
     lb2_conv_io io[2];
 };
 
@@ -55,9 +56,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_n256(const Params p) {
     const int n_tiles = (M + BM - 1) / BM;
     const int total = n_tiles * p.npass;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int pshift = (p.npass == 2) ? 1 : 0;                  // work item -> (tile, pass): heaviest tiles first, passes adjacent (see spconv_tc4.cu)
-    auto item_tile = [&](int item) { return n_tiles - 1 - (item >> pshift); };
-    auto item_pass = [&](int item) { return item & pshift; };
+    // work item -> (tile, pass): pass-major (the two guidance passes read different feature tensors: one pass at a time keeps the
+    // gathered working set inside the 126 MB L2), inside a pass the heaviest tiles first (the row order sorts rows by neighbour
+    // mask, light to heavy), so the last, partially filled round of the persistent loop holds the cheapest tiles
+    auto item_pass = [&](int item) { return item >= n_tiles ? 1 : 0; };
+    auto item_tile = [&](int item) { return n_tiles - 1 - (item >= n_tiles ? item - n_tiles : item); };
+    // round j of the persistent loop in snake order (even rounds left to right, odd rounds right to left over the CTAs): with the
+    // items sorted by cost every CTA alternates between a dearer and a cheaper item, so the per-CTA sums stay balanced (static LPT);
+    // an item index >= total (last, partial round) is an empty tile for every role
+    auto slot_item = [&](int jj) { return jj * (int)gridDim.x + ((jj & 1) ? (int)gridDim.x - 1 - (int)blockIdx.x : (int)blockIdx.x); };
 
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -121,10 +128,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_n256(const Params p) {
             if (row < 0) return 0u;
             return p.row_mask ? __ldg(p.row_mask + row) : ((p.kvol >= 32) ? 0xffffffffu : ((1u << p.kvol) - 1u));
         };
-        int next_row = fetch_row(blockIdx.x);
-        int next2_row = fetch_row(blockIdx.x + gridDim.x);
+        int next_row = fetch_row(slot_item(0));
+        int next2_row = fetch_row(slot_item(1));
         uint32_t next_mask = fetch_mask(next_row);
-        for (int item = blockIdx.x; item < total; item += gridDim.x, ++j) {
+        for (; j * (int)gridDim.x < total; ++j) {
+            const int item = slot_item(j);
             const int b = j % META;
             const int pass = item_pass(item);
             const lb2_conv_io io = p.io[pass];
@@ -133,7 +141,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_n256(const Params p) {
                 const int row = next_row;
                 const uint32_t have = next_mask;
                 next_row = next2_row;
-                next2_row = fetch_row(item + 2 * gridDim.x);            // prefetch two tiles ahead (row), one tile ahead (its mask)
+                next2_row = fetch_row(slot_item(j + 2));            // prefetch two tiles ahead (row), one tile ahead (its mask)
                 next_mask = fetch_mask(next_row);
                 row_s[b * BM + t] = row;
                 uint32_t found = have;
@@ -207,7 +215,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_n256(const Params p) {
             const uint32_t idesc = make_idesc(NCOLS);
             int gcount = 0, j = 0;
             Ring rq{0, 0u, NA}, rb{0, 0u, NB};
-            for (int item = blockIdx.x; item < total; item += gridDim.x, ++j) {
+            for (; j * (int)gridDim.x < total; ++j) {
+            const int item = slot_item(j);
                 const int b = j % META;
                 mbar_wait(meta_full(b), (j / META) & 1);
                 const uint32_t kmask = tile_kmask(b);
@@ -262,7 +271,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_n256(const Params p) {
             // =========================== weight loader ===========================
             int j = 0;
             Ring r{0, 0u, NB};
-            for (int item = blockIdx.x; item < total; item += gridDim.x, ++j) {
+            for (; j * (int)gridDim.x < total; ++j) {
+            const int item = slot_item(j);
                 const int b = j % META;
                 mbar_wait(meta_full(b), (j / META) & 1);
                 const uint32_t kmask = tile_kmask(b);
@@ -290,7 +300,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_n256(const Params p) {
         float* myslab = slab + (size_t)(warp - 8) * 32 * SLAB_PITCH;
         float tot[128];
         int gcount = 0, j = 0;
-        for (int item = blockIdx.x; item < total; item += gridDim.x, ++j) {
+        for (; j * (int)gridDim.x < total; ++j) {
+            const int item = slot_item(j);
             const int b = j % META;
             const int pass = item_pass(item);
             const lb2_conv_io io = p.io[pass];
@@ -332,14 +343,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_n256(const Params p) {
             }
             // ---- epilogue from registers, 16 channels at a time through the warp's slab (coalesced global accesses) ----
             const int lc4 = (lane & 3) * 4;
-#pragma unroll
-            for (int cs = 0; cs < 8; ++cs) {
+#pragma unroll 1
+            for (int cs = 0; cs < 8; ++cs) {                 // run-time loop: one copy of the global-memory code (see slab_write_switch)
                 __syncwarp();
-                float* srow = myslab + lane * SLAB_PITCH;
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    *reinterpret_cast<float4*>(srow + q * 4) = make_float4(tot[cs * 16 + q * 4] * out_scale, tot[cs * 16 + q * 4 + 1] * out_scale,
-                                                                           tot[cs * 16 + q * 4 + 2] * out_scale, tot[cs * 16 + q * 4 + 3] * out_scale);
+                slab_write_switch<128>(cs, tot, myslab + lane * SLAB_PITCH, out_scale);
                 __syncwarp();
                 const int col = cb + cs * 16 + lc4;
                 float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f), h4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -373,12 +380,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_n256(const Params p) {
 #pragma unroll
                             for (int q = 0; q < 4; ++q) y[q] = fmaxf(y[q], 0.f);
                         }
-                        if (io.out) *reinterpret_cast<float4*>(io.out + ro) = make_float4(y[0], y[1], y[2], y[3]);
-                        if (io.out_h) store_split4(io.out_h, orow, NCOLS, col, y);
+                        if (io.out) store_f4(io.out + ro, y, p.cs);
+                        if (io.out_h) store_split4(io.out_h, orow, NCOLS, col, y, p.cs);
                         if (io.out_gated || io.out_gated_h) {
                             y[0] *= gat[u].x; y[1] *= gat[u].y; y[2] *= gat[u].z; y[3] *= gat[u].w;
-                            if (io.out_gated) *reinterpret_cast<float4*>(io.out_gated + ro) = make_float4(y[0], y[1], y[2], y[3]);
-                            if (io.out_gated_h) store_split4(io.out_gated_h, orow, NCOLS, col, y);
+                            if (io.out_gated) store_f4(io.out_gated + ro, y, p.cs);
+                            if (io.out_gated_h) store_split4(io.out_gated_h, orow, NCOLS, col, y, p.cs);
                         }
                     }
                 }
@@ -418,6 +425,7 @@ int lb2_spconv_tc3_launch(Lb2Handle* h, cudaStream_t s, const lb2_conv_desc* d, 
     const int steps_per_offset = 3 * ((d->c1 + d->c2 + 15) / 16);
     p.group = std::max(1, step_budget / steps_per_offset);
     p.io[0] = d->io[0]; p.io[1] = d->io[d->npass > 1 ? 1 : 0];
+    p.cs = h->opt[LB2_OPT_STREAM_STORES] ? 1 : 0;
     const size_t smem = tc3::smem_bytes();
     {
         cudaError_t e = lb2_configure_smem(h, LB2_K_TC3, tc3::k_spconv_tc_n256, (int)(227 * 1024));

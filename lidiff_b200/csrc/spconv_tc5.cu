@@ -58,6 +58,7 @@ struct Params {
     const int* row_perm;
     const unsigned* row_mask;
     int nchunks, group, npass;
+    int cs;                     // evict-first epilogue stores
     lb2_conv_io io[2];
 };
 
@@ -104,12 +105,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_spconv
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_rank();
     const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-    // work item -> (super-tile, pass): heaviest super-tiles first (the row order sorts rows by neighbour mask, light to heavy), the
-    // two guidance passes of a super-tile adjacent: the last, partially filled round of the persistent loop then holds the cheapest
-    // tiles (centre-only rows) instead of the most expensive ones
-    const int pshift = (p.npass == 2) ? 1 : 0;
-    auto item_tile = [&](int item) { return n_stiles - 1 - (item >> pshift); };
-    auto item_pass = [&](int item) { return item & pshift; };
+    // work item -> (tile, pass): pass-major (the two guidance passes read different feature tensors: one pass at a time keeps the
+    // gathered working set inside the 126 MB L2), inside a pass the heaviest tiles first (the row order sorts rows by neighbour
+    // mask, light to heavy), so the last, partially filled round of the persistent loop holds the cheapest tiles
+    auto item_pass = [&](int item) { return item >= n_stiles ? 1 : 0; };
+    auto item_tile = [&](int item) { return n_stiles - 1 - (item >= n_stiles ? item - n_stiles : item); };
+    // round j of the persistent loop in snake order (even rounds left to right, odd rounds right to left over the CTAs): with the
+    // items sorted by cost every CTA alternates between a dearer and a cheaper item, so the per-CTA sums stay balanced (static LPT);
+    // an item index >= total (last, partial round) is an empty tile for every role
+    auto slot_item = [&](int jj) { return jj * npairs + ((jj & 1) ? npairs - 1 - pair : pair); };
 
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;               // same offset in both CTAs (same kernel, same dynamic size)
@@ -169,10 +173,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_spconv
             if (row < 0) return 0u;
             return p.row_mask ? __ldg(p.row_mask + row) : ((1u << p.kvol) - 1u);
         };
-        int next_row = fetch_row(pair, rank), next_row_p = fetch_row(pair, rank ^ 1u);
-        int next2_row = fetch_row(pair + npairs, rank), next2_row_p = fetch_row(pair + npairs, rank ^ 1u);
+        int next_row = fetch_row(slot_item(0), rank), next_row_p = fetch_row(slot_item(0), rank ^ 1u);
+        int next2_row = fetch_row(slot_item(1), rank), next2_row_p = fetch_row(slot_item(1), rank ^ 1u);
         uint32_t next_mask = fetch_mask(next_row), next_mask_p = fetch_mask(next_row_p);
-        for (int item = pair; item < total; item += npairs, ++j) {
+        for (; j * npairs < total; ++j) {
+            const int item = slot_item(j);
             const int b = j % META;
             const int pass = item_pass(item);
             const lb2_conv_io io = p.io[pass];
@@ -181,8 +186,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_spconv
                 const int row = next_row;
                 const uint32_t own = next_mask, both = next_mask | next_mask_p;
                 next_row = next2_row; next_row_p = next2_row_p;
-                next2_row = fetch_row(item + 2 * npairs, rank);         // prefetch two tiles ahead (rows), one tile ahead (masks)
-                next2_row_p = fetch_row(item + 2 * npairs, rank ^ 1u);
+                next2_row = fetch_row(slot_item(j + 2), rank);         // prefetch two tiles ahead (rows), one tile ahead (masks)
+                next2_row_p = fetch_row(slot_item(j + 2), rank ^ 1u);
                 next_mask = fetch_mask(next_row); next_mask_p = fetch_mask(next_row_p);
                 row_s[b * BM + t] = row;
                 mask_s[b * BM + t] = own;
@@ -240,7 +245,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_spconv
             const uint32_t idesc = make_idesc2(NCOLS);
             int gcount = 0, j = 0;
             Ring rq{0, 0u, NA}, rb{0, 0u, NB};
-            for (int item = pair; item < total; item += npairs, ++j) {
+            for (; j * npairs < total; ++j) {
+            const int item = slot_item(j);
                 const int b = j % META;
                 mbar_wait(meta_full(b), (j / META) & 1);
                 const uint32_t kmask = tile_kmask(b);
@@ -299,7 +305,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_spconv
             int j = 0;
             Ring r{0, 0u, NB}, ra{0, 0u, NA};
             const uint32_t leader_full_bp0 = map_to_cta(full_bp(0), 0), leader_full_ap0 = map_to_cta(full_ap(0), 0);
-            for (int item = pair; item < total; item += npairs, ++j) {
+            for (; j * npairs < total; ++j) {
+            const int item = slot_item(j);
                 const int b = j % META;
                 mbar_wait(meta_full(b), (j / META) & 1);
                 const uint32_t kmask = tile_kmask(b);
@@ -321,7 +328,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_spconv
             int j = 0;
             Ring r{0, 0u, NB};
             const uint32_t self_full_bp0 = full_bp(0);
-            for (int item = pair; item < total; item += npairs, ++j) {
+            for (; j * npairs < total; ++j) {
+            const int item = slot_item(j);
                 const int b = j % META;
                 mbar_wait(meta_full(b), (j / META) & 1);
                 const uint32_t kmask = tile_kmask(b);
@@ -354,7 +362,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_spconv
         const uint32_t leader_acc_empty0 = map_to_cta(acc_empty(0), 0);
         float tot[TOT];
         int gcount = 0, j = 0;
-        for (int item = pair; item < total; item += npairs, ++j) {
+        for (; j * npairs < total; ++j) {
+            const int item = slot_item(j);
             const int b = j % META;
             const int pass = item_pass(item);
             const lb2_conv_io io = p.io[pass];
@@ -397,14 +406,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_spconv
             }
             // ---- epilogue from registers, 16 channels at a time through the warp's slab (coalesced global accesses) ----
             const int lc4 = (lane & 3) * 4;
-#pragma unroll
-            for (int cs = 0; cs < TOT / 16; ++cs) {
+#pragma unroll 1
+            for (int cs = 0; cs < TOT / 16; ++cs) {                 // run-time loop: one copy of the global-memory code (see slab_write_switch)
                 __syncwarp();
-                float* srow = myslab + lane * SLAB_PITCH;
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    *reinterpret_cast<float4*>(srow + q * 4) = make_float4(tot[cs * 16 + q * 4] * out_scale, tot[cs * 16 + q * 4 + 1] * out_scale,
-                                                                           tot[cs * 16 + q * 4 + 2] * out_scale, tot[cs * 16 + q * 4 + 3] * out_scale);
+                slab_write_switch<TOT>(cs, tot, myslab + lane * SLAB_PITCH, out_scale);
                 __syncwarp();
                 const int col = cb + cs * 16 + lc4;
                 float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f), h4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -438,12 +443,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_spconv
 #pragma unroll
                             for (int q = 0; q < 4; ++q) y[q] = fmaxf(y[q], 0.f);
                         }
-                        if (io.out) *reinterpret_cast<float4*>(io.out + ro) = make_float4(y[0], y[1], y[2], y[3]);
-                        if (io.out_h) store_split4(io.out_h, orow, NCOLS, col, y);
+                        if (io.out) store_f4(io.out + ro, y, p.cs);
+                        if (io.out_h) store_split4(io.out_h, orow, NCOLS, col, y, p.cs);
                         if (io.out_gated || io.out_gated_h) {
                             y[0] *= gat[u].x; y[1] *= gat[u].y; y[2] *= gat[u].z; y[3] *= gat[u].w;
-                            if (io.out_gated) *reinterpret_cast<float4*>(io.out_gated + ro) = make_float4(y[0], y[1], y[2], y[3]);
-                            if (io.out_gated_h) store_split4(io.out_gated_h, orow, NCOLS, col, y);
+                            if (io.out_gated) store_f4(io.out_gated + ro, y, p.cs);
+                            if (io.out_gated_h) store_split4(io.out_gated_h, orow, NCOLS, col, y, p.cs);
                         }
                     }
                 }
@@ -495,5 +500,6 @@ int lb2_spconv_tc5_launch(Lb2Handle* h, cudaStream_t s, const lb2_conv_desc* d, 
     const int steps_per_offset = 3 * ((d->c1 + d->c2 + 15) / 16);
     p.group = std::max(1, step_budget / steps_per_offset);
     p.io[0] = d->io[0]; p.io[1] = d->io[d->npass > 1 ? 1 : 0];
+    p.cs = h->opt[LB2_OPT_STREAM_STORES] ? 1 : 0;
     return d->cout == 256 ? launch_pair<256>(h, s, p, d->mout_cap, d->npass) : launch_pair<128>(h, s, p, d->mout_cap, d->npass);
 }

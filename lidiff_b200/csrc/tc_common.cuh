@@ -123,14 +123,24 @@ __device__ __forceinline__ void split1(float x, __half& hi, __half& lo) {
     hi = __float2half_rn(x);
     lo = __float2half_rn(x - __half2float(hi));
 }
-// write 4 consecutive channels of a split companion row: hi halfs at row[col], lo halfs at row[c + col]
-__device__ __forceinline__ void store_split4(void* base, long long row, int c, int col, const float (&y)[4]) {
+// write 4 consecutive channels of a split companion row: hi halfs at row[col], lo halfs at row[c + col].
+// cs: evict-first stores (st.global.cs) — an epilogue's output streams through L2 instead of displacing gathered input rows
+__device__ __forceinline__ void store_split4(void* base, long long row, int c, int col, const float (&y)[4], bool cs = false) {
     __half* rp = reinterpret_cast<__half*>(base) + row * 2 * c;
     uint2 uh, ul;
     split2(y[0], y[1], uh.x, ul.x);
     split2(y[2], y[3], uh.y, ul.y);
-    *reinterpret_cast<uint2*>(rp + col) = uh;
-    *reinterpret_cast<uint2*>(rp + c + col) = ul;
+    if (cs) {
+        __stcs(reinterpret_cast<uint2*>(rp + col), uh);
+        __stcs(reinterpret_cast<uint2*>(rp + c + col), ul);
+    } else {
+        *reinterpret_cast<uint2*>(rp + col) = uh;
+        *reinterpret_cast<uint2*>(rp + c + col) = ul;
+    }
+}
+__device__ __forceinline__ void store_f4(float* p, const float (&y)[4], bool cs) {
+    const float4 v = make_float4(y[0], y[1], y[2], y[3]);
+    if (cs) __stcs(reinterpret_cast<float4*>(p), v); else *reinterpret_cast<float4*>(p) = v;
 }
 
 // 4 consecutive channels of a residual row: from the fp32 tensor, else from its split companion (hi + lo), else zero
@@ -142,6 +152,31 @@ __device__ __forceinline__ float4 load_residual4(const float* res, const void* r
     const float2 h0 = __half22float2(*reinterpret_cast<const __half2*>(&uh.x)), h1 = __half22float2(*reinterpret_cast<const __half2*>(&uh.y));
     const float2 l0 = __half22float2(*reinterpret_cast<const __half2*>(&ul.x)), l1 = __half22float2(*reinterpret_cast<const __half2*>(&ul.y));
     return make_float4(h0.x + l0.x, h0.y + l0.y, h1.x + l1.x, h1.y + l1.y);
+}
+
+// One 16-channel slab of a drain thread's register-resident totals -> its row of the warp's staging slab, scaled.  The slab index is a
+// template parameter (registers are addressed statically); the epilogue loops over the slabs at run time and dispatches through
+// slab_write_switch, so the global-memory part of the epilogue exists ONCE in the binary instead of once per slab (the fully unrolled
+// form made the kernels 85-185 KB of SASS and the drain warps stalled on instruction fetch, ncu: 'no_inst').
+template <int C, int TOT>
+__device__ __forceinline__ void slab_write(const float (&tot)[TOT], float* srow, float out_scale) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<float4*>(srow + q * 4) = make_float4(tot[C * 16 + q * 4] * out_scale, tot[C * 16 + q * 4 + 1] * out_scale,
+                                                               tot[C * 16 + q * 4 + 2] * out_scale, tot[C * 16 + q * 4 + 3] * out_scale);
+}
+template <int TOT>
+__device__ __forceinline__ void slab_write_switch(int cs, const float (&tot)[TOT], float* srow, float out_scale) {
+    switch (cs) {
+        case 0: slab_write<0, TOT>(tot, srow, out_scale); break;
+        case 1: if constexpr (TOT > 16) slab_write<1, TOT>(tot, srow, out_scale); break;
+        case 2: if constexpr (TOT > 32) slab_write<2, TOT>(tot, srow, out_scale); break;
+        case 3: if constexpr (TOT > 48) slab_write<3, TOT>(tot, srow, out_scale); break;
+        case 4: if constexpr (TOT > 64) slab_write<4, TOT>(tot, srow, out_scale); break;
+        case 5: if constexpr (TOT > 80) slab_write<5, TOT>(tot, srow, out_scale); break;
+        case 6: if constexpr (TOT > 96) slab_write<6, TOT>(tot, srow, out_scale); break;
+        default: if constexpr (TOT > 112) slab_write<7, TOT>(tot, srow, out_scale); break;
+    }
 }
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {

@@ -137,6 +137,7 @@ class Geometry:
         self.perm_up = [torch.zeros(n_cap, **i32) for _ in range(levels - 1)] + [None] if with_up else None
         self.perm_of = {}
         # per-offset (in,out) pair lists of the 3^3 maps of the sparse levels (gather-GEMM-scatter form)
+        self.morton_levels = set(int(c) for c in os.environ.get("LB2_MORTON_LEVELS", "") if c.isdigit())
         self.pair_levels = min(3, levels)
         self.pair_level_set = set(int(c) for c in os.environ.get("LB2_SCATTER_LEVELS", "") if c.isdigit())
         self.pairs_of = {}
@@ -164,7 +165,9 @@ class Geometry:
             if mask is None:
                 mask = self.mask_of[nbr.data_ptr()] = torch.zeros(N, dtype=torch.int32, device=nbr.device)
             h.kernel_map(grid, self.C[l_out], self.d_n[l_out], N, ks, step, nbr, N, self.pairs[slot:slot + 1], mask)
-            h.row_order(mask, self.d_n[l_out], N, ks ** 3, perm, self.ro_scratch)
+            # 3^3 maps of the levels with many neighbours per row: rows of equal mask in Morton order (compact tiles, L2 locality)
+            morton = ks == 3 and l_out in self.morton_levels
+            h.row_order(mask, self.d_n[l_out], N, ks ** 3, perm, self.ro_scratch, self.C[l_out] if morton else None, l_out)
             self.map_id[nbr.data_ptr()] = slot
             self.perm_of[nbr.data_ptr()] = perm
 

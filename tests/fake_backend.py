@@ -139,7 +139,7 @@ class FakeHandle:
     def row_order_scratch_bytes(self, n_cap):
         return 1024
 
-    def row_order(self, row_mask, d_n, n_cap, kvol, perm, scratch):
+    def row_order(self, row_mask, d_n, n_cap, kvol, perm, scratch, coords=None, coord_shift=0):
         self.launches += 3 if kvol <= 8 else 6
         n = self._n(d_n, n_cap)
         m = row_mask[:n].long() & 0xFFFFFFFF

@@ -299,6 +299,18 @@ def test_row_order_is_a_permutation_and_does_not_change_results(spread, algo):
             extras = ms & ~(1 << 13)
             key = ((np.array([bin(int(v)).count("1") for v in extras]) >= 2).astype(np.int64) << 26) | ((ms >> 14) << 13) | (ms & 0x1FFF)
             assert (np.diff(key) >= 0).all(), "27-bit masks must come out sorted by [>=2 neighbours | mask]"
+            if lvl in g.morton_levels:          # rows of equal mask in Morton order of (x,y,z) >> level (9 bits per axis)
+                C = g.C[lvl][:M].cpu().numpy().astype(np.int64)[p]
+
+                def part(v):
+                    v = v & 0x1FF
+                    out = np.zeros_like(v)
+                    for b in range(9):
+                        out |= ((v >> b) & 1) << (3 * b)
+                    return out
+                code = part(C[:, 1] >> lvl) | (part(C[:, 2] >> lvl) << 1) | (part(C[:, 3] >> lvl) << 2)
+                same = np.diff(key) == 0
+                assert (np.diff(code)[same] >= 0).all(), "rows of equal mask must be in Morton order"
         cin, cout = 32, 64
         W = (torch.randn(kvol, cin, cout, generator=gen) * 0.1).to(DEV)
         x = torch.randn(N, cin, generator=gen).to(DEV)
