@@ -22,13 +22,16 @@ using namespace tc;
 
 constexpr int THREADS = 512;
 constexpr int MAX_KVOL = 27;
-constexpr int NA = 4;                                 // A slots (32 K-columns each; two per 128-byte row image)
+constexpr int NA_MAX = 6;
+__host__ __device__ constexpr int na_of(int ncc) { return ncc <= 3 ? 6 : 4; }   // A slots (32 K-columns each; two per 128-byte row image):
+                                                      // the sparse levels' layers (Cout <= 96) are bound by gather latency, their
+                                                      // smaller weight slots leave room for a deeper gather ring
 constexpr int NB = 3;                                 // weight slots (64 K-columns each)
 constexpr int NACC = 4;                               // TMEM accumulators
 constexpr int SLAB_PITCH = 20;                        // floats per slab row (16 + 4: conflict-free 16-byte accesses)
 constexpr int SLAB_BYTES = 8 * 32 * SLAB_PITCH * 4;   // 8 drain warps x 32 rows
 constexpr int META = 4;                               // ring of per-tile metadata; must exceed the gather lookahead in tiles (<= 1)
-constexpr int NBAR = 2 * NA + 2 * NB + 2 * NACC + 2 * META;
+constexpr int NBAR = 2 * NA_MAX + 2 * NB + 2 * NACC + 2 * META;
 
 struct Params {
     int c1, c2, cout, kvol;
@@ -55,6 +58,7 @@ struct Ring {                                             // position in a ring 
 template <int NCC>                                        // NCC = Cout / 32: sizes the register-resident running total
 __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_small(const Params p) {
     extern __shared__ unsigned char smem_raw[];
+    constexpr int NA = na_of(NCC);
     const int M = p.d_mout ? min(*p.d_mout, p.mout_cap) : p.mout_cap;
     const int n_tiles = (M + BM - 1) / BM;
     const int total = n_tiles * p.npass;
@@ -338,6 +342,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_small(const Params p) 
                 grow[lane] = (io.gate_table && io.gate_idx && r >= 0) ? __ldg(io.gate_idx + r) : 0;
                 __syncwarp();
             }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {                          // this lane's 4 epilogue rows: L2 prefetch of their operands
+                const int rr = (lane >> 2) + 8 * u;
+                const int orow = rows[rr];
+                if (orow < 0) continue;
+                prefetch_row_f32(io.residual, orow, p.cout, cb, TOT, lane & 3);
+                if (!io.residual) prefetch_row_split(io.residual_h, orow, p.cout, cb, TOT, lane & 3);
+                prefetch_row_f32(io.pre_add, orow, p.cout, cb, TOT, lane & 3);
+                if (io.gate_table && io.gate_idx) prefetch_row_f32(io.gate_table, grow[rr], p.cout, cb, TOT, lane & 3);
+            }
             if (n_groups == 0) {
 #pragma unroll
                 for (int q = 0; q < TOT; ++q) tot[q] = 0.f;
@@ -373,39 +387,43 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_small(const Params p) 
                 const int col = cb + cs * 16 + lc4;
                 float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f), h4 = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (p.scale) { s4 = __ldg(reinterpret_cast<const float4*>(p.scale + col)); h4 = __ldg(reinterpret_cast<const float4*>(p.shift + col)); }
-                float4 pre[4], res[4], gat[4];                      // this lane's 4 rows: all loads first, then math + stores
+                constexpr int RB = (TOT >= 64) ? 2 : 4;             // rows per batch (loads first, then math + stores); 2 where the totals fill the registers
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int rr = (lane >> 2) + 8 * u;
-                    const int orow = rows[rr];
-                    pre[u] = make_float4(0.f, 0.f, 0.f, 0.f); res[u] = pre[u]; gat[u] = make_float4(1.f, 1.f, 1.f, 1.f);
-                    if (orow >= 0) {
+                for (int u0 = 0; u0 < 4; u0 += RB) {
+                    float4 pre[RB], res[RB], gat[RB];
+#pragma unroll
+                    for (int v = 0; v < RB; ++v) {
+                        const int rr = (lane >> 2) + 8 * (u0 + v);
+                        const int orow = rows[rr];
+                        pre[v] = make_float4(0.f, 0.f, 0.f, 0.f); res[v] = pre[v]; gat[v] = make_float4(1.f, 1.f, 1.f, 1.f);
+                        if (orow >= 0) {
+                            const long long ro = (long long)orow * p.cout + col;
+                            if (io.pre_add) pre[v] = __ldg(reinterpret_cast<const float4*>(io.pre_add + ro));
+                            res[v] = load_residual4(io.residual, io.residual_h, orow, p.cout, col);
+                            if (io.gate_table) gat[v] = __ldg(reinterpret_cast<const float4*>(io.gate_table + (long long)grow[rr] * p.cout + col));
+                        }
+                    }
+#pragma unroll
+                    for (int v = 0; v < RB; ++v) {
+                        const int rr = (lane >> 2) + 8 * (u0 + v);
+                        const int orow = rows[rr];
+                        if (orow < 0) continue;
                         const long long ro = (long long)orow * p.cout + col;
-                        if (io.pre_add) pre[u] = __ldg(reinterpret_cast<const float4*>(io.pre_add + ro));
-                        res[u] = load_residual4(io.residual, io.residual_h, orow, p.cout, col);
-                        if (io.gate_table) gat[u] = __ldg(reinterpret_cast<const float4*>(io.gate_table + (long long)grow[rr] * p.cout + col));
-                    }
-                }
+                        const float4 a4 = *reinterpret_cast<const float4*>(myslab + rr * SLAB_PITCH + lc4);
+                        float y[4] = {a4.x + pre[v].x, a4.y + pre[v].y, a4.z + pre[v].z, a4.w + pre[v].w};
+                        y[0] = fmaf(y[0], s4.x, h4.x) + res[v].x; y[1] = fmaf(y[1], s4.y, h4.y) + res[v].y;
+                        y[2] = fmaf(y[2], s4.z, h4.z) + res[v].z; y[3] = fmaf(y[3], s4.w, h4.w) + res[v].w;
+                        if (p.relu) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int rr = (lane >> 2) + 8 * u;
-                    const int orow = rows[rr];
-                    if (orow < 0) continue;
-                    const long long ro = (long long)orow * p.cout + col;
-                    const float4 a4 = *reinterpret_cast<const float4*>(myslab + rr * SLAB_PITCH + lc4);
-                    float y[4] = {a4.x + pre[u].x, a4.y + pre[u].y, a4.z + pre[u].z, a4.w + pre[u].w};
-                    y[0] = fmaf(y[0], s4.x, h4.x) + res[u].x; y[1] = fmaf(y[1], s4.y, h4.y) + res[u].y;
-                    y[2] = fmaf(y[2], s4.z, h4.z) + res[u].z; y[3] = fmaf(y[3], s4.w, h4.w) + res[u].w;
-                    if (p.relu) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) y[q] = fmaxf(y[q], 0.f);
-                    }
-                    if (io.out) store_f4(io.out + ro, y, p.cs);
-                    if (io.out_h) store_split4(io.out_h, orow, p.cout, col, y, p.cs);
-                    if (io.out_gated || io.out_gated_h) {
-                        y[0] *= gat[u].x; y[1] *= gat[u].y; y[2] *= gat[u].z; y[3] *= gat[u].w;
-                        if (io.out_gated) store_f4(io.out_gated + ro, y, p.cs);
-                        if (io.out_gated_h) store_split4(io.out_gated_h, orow, p.cout, col, y, p.cs);
+                            for (int q = 0; q < 4; ++q) y[q] = fmaxf(y[q], 0.f);
+                        }
+                        if (io.out) store_f4(io.out + ro, y, p.cs);
+                        if (io.out_h) store_split4(io.out_h, orow, p.cout, col, y, p.cs);
+                        if (io.out_gated || io.out_gated_h) {
+                            y[0] *= gat[v].x; y[1] *= gat[v].y; y[2] *= gat[v].z; y[3] *= gat[v].w;
+                            if (io.out_gated) store_f4(io.out_gated + ro, y, p.cs);
+                            if (io.out_gated_h) store_split4(io.out_gated_h, orow, p.cout, col, y, p.cs);
+                        }
                     }
                 }
             }
@@ -418,7 +436,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_small(const Params p) 
 }
 
 static size_t smem_bytes(int cout) {
-    return 1024 + (size_t)(NA / 2) * 2 * A_TILE + (size_t)NB * 2 * cout * 128 + SLAB_BYTES + MAX_KVOL * BM * sizeof(int) + META * BM * sizeof(int) +
+    return 1024 + (size_t)(na_of(cout / 32) / 2) * 2 * A_TILE + (size_t)NB * 2 * cout * 128 + SLAB_BYTES + MAX_KVOL * BM * sizeof(int) + META * BM * sizeof(int) +
            8 * 32 * sizeof(int) + 4 * META * sizeof(uint32_t) + NBAR * 8 + 64;
 }
 

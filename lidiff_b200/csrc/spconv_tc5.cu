@@ -378,6 +378,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_spconv
                 orows[i] = rows[(lane >> 2) + 8 * i];
                 gidx[i] = (io.gate_table && io.gate_idx && orows[i] >= 0) ? __ldg(io.gate_idx + orows[i]) : 0;
             }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {                           // L2 prefetch of the epilogue operands of this lane's 4 rows
+                if (orows[i] < 0) continue;
+                prefetch_row_f32(io.residual, orows[i], NCOLS, cb, TOT, lane & 3);
+                if (!io.residual) prefetch_row_split(io.residual_h, orows[i], NCOLS, cb, TOT, lane & 3);
+                prefetch_row_f32(io.pre_add, orows[i], NCOLS, cb, TOT, lane & 3);
+                if (io.gate_table && io.gate_idx) prefetch_row_f32(io.gate_table, gidx[i], NCOLS, cb, TOT, lane & 3);
+            }
             if (n_groups == 0) {
 #pragma unroll
                 for (int q = 0; q < TOT; ++q) tot[q] = 0.f;

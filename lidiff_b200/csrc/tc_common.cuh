@@ -143,6 +143,21 @@ __device__ __forceinline__ void store_f4(float* p, const float (&y)[4], bool cs)
     if (cs) __stcs(reinterpret_cast<float4*>(p), v); else *reinterpret_cast<float4*>(p) = v;
 }
 
+// Ask L2 for the 128-byte lines of the epilogue operands of one output row (channels [c0, c0 + n) of a (rows, c) tensor): issued by
+// the drain warps when a tile's rows are known, long before the accumulator they belong to is complete, so the epilogue's loads hit L2
+// instead of paying the DRAM latency once per 16-channel slab.  `line` = which 128-byte line of the segment this lane asks for.
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_row_f32(const float* base, long long row, int c, int c0, int n, int line) {
+    if (base && line * 32 < n) prefetch_l2(base + row * c + c0 + line * 32);
+}
+__device__ __forceinline__ void prefetch_row_split(const void* base_h, long long row, int c, int c0, int n, int line) {
+    if (base_h && line * 64 < n) {                       // hi and lo halves: n halfs each
+        const __half* rp = reinterpret_cast<const __half*>(base_h) + row * 2 * c + c0 + line * 64;
+        prefetch_l2(rp);
+        prefetch_l2(rp + c);
+    }
+}
+
 // 4 consecutive channels of a residual row: from the fp32 tensor, else from its split companion (hi + lo), else zero
 __device__ __forceinline__ float4 load_residual4(const float* res, const void* res_h, long long row, int c, int col) {
     if (res) return __ldg(reinterpret_cast<const float4*>(res + row * c + col));
