@@ -47,7 +47,7 @@ int         lb2_version(void);
 int64_t     lb2_launch_count(void* handle);
 /* Kernel-selection options of a handle (development / A-B knobs; every setting computes the same results and is exercised by
  * the GPU tests).  Defaults come from the environment variable of the same name (LB2_TC_PAIR, ...) at lb2_create. */
-#define LB2_OPT_TC_PAIR       0   /* CTA-pair cta_group::2 conv kernel: 0 off, 1 = Cout 256, 2 = Cout 256 and 128 (default 1) */
+#define LB2_OPT_TC_PAIR       0   /* CTA-pair cta_group::2 conv kernel: 0 off, 1 = Cout 256, 2 = Cout 256 and 128 (default 2) */
 #define LB2_OPT_TC_N256       1   /* single-CTA register-total kernel for Cout 256 (default 1) */
 #define LB2_OPT_TC_SMALL      2   /* two-drain-warpgroup kernel for Cout <= 128 (default 1) */
 #define LB2_OPT_TC_PERSISTENT 3   /* persistent kernels for LB2_ALGO_TC (default 1; 0 = one CTA per tile) */

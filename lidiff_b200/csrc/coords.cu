@@ -27,7 +27,7 @@ extern "C" int lb2_create(int device, void** handle) {
     h->device = device; h->num_sms = prop.multiProcessorCount; h->launches = 0; h->err[0] = 0; h->configured = 0;
     {
         auto env = [](const char* name, int dflt) { const char* e = getenv(name); return (e && e[0]) ? atoi(e) : dflt; };
-        h->opt[LB2_OPT_TC_PAIR] = env("LB2_TC_PAIR", 1);
+        h->opt[LB2_OPT_TC_PAIR] = env("LB2_TC_PAIR", 2);
         h->opt[LB2_OPT_TC_N256] = env("LB2_TC_N256", 1);
         h->opt[LB2_OPT_TC_SMALL] = env("LB2_TC_SMALL", 1);
         h->opt[LB2_OPT_TC_PERSISTENT] = env("LB2_TC_PERSISTENT", 1);

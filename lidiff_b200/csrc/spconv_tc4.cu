@@ -379,6 +379,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_small(const Params p) 
             }
             // ---- epilogue from registers, 16 channels at a time through the warp's slab (coalesced global accesses) ----
             const int lc4 = (lane & 3) * 4;
+            // which operands / outputs this pass has: decided once per tile (predicates), not per element
+            const bool has_pre = io.pre_add != nullptr, has_res32 = io.residual != nullptr, has_resh = !has_res32 && io.residual_h != nullptr;
+            const bool has_gate = io.gate_table != nullptr, w_out = io.out != nullptr, w_outh = io.out_h != nullptr;
+            const bool w_g = io.out_gated != nullptr, w_gh = io.out_gated_h != nullptr;
+            const bool cs_st = p.cs != 0, has_aff = p.scale != nullptr, do_relu = p.relu != 0;
+            const int C = p.cout;
 #pragma unroll 1
             for (int cs = 0; cs < TOT / 16; ++cs) {                 // run-time loop: one copy of the global-memory code (see slab_write_switch)
                 __syncwarp();
@@ -386,43 +392,44 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_small(const Params p) 
                 __syncwarp();
                 const int col = cb + cs * 16 + lc4;
                 float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f), h4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (p.scale) { s4 = __ldg(reinterpret_cast<const float4*>(p.scale + col)); h4 = __ldg(reinterpret_cast<const float4*>(p.shift + col)); }
+                if (has_aff) { s4 = __ldg(reinterpret_cast<const float4*>(p.scale + col)); h4 = __ldg(reinterpret_cast<const float4*>(p.shift + col)); }
                 constexpr int RB = (TOT >= 64) ? 2 : 4;             // rows per batch (loads first, then math + stores); 2 where the totals fill the registers
 #pragma unroll
                 for (int u0 = 0; u0 < 4; u0 += RB) {
                     float4 pre[RB], res[RB], gat[RB];
+                    long long ro[RB];                               // element offset of (row, col) in a (rows, C) fp32 tensor; < 0: no row
 #pragma unroll
                     for (int v = 0; v < RB; ++v) {
                         const int rr = (lane >> 2) + 8 * (u0 + v);
                         const int orow = rows[rr];
                         pre[v] = make_float4(0.f, 0.f, 0.f, 0.f); res[v] = pre[v]; gat[v] = make_float4(1.f, 1.f, 1.f, 1.f);
+                        ro[v] = orow >= 0 ? (long long)orow * C + col : -1;
                         if (orow >= 0) {
-                            const long long ro = (long long)orow * p.cout + col;
-                            if (io.pre_add) pre[v] = __ldg(reinterpret_cast<const float4*>(io.pre_add + ro));
-                            res[v] = load_residual4(io.residual, io.residual_h, orow, p.cout, col);
-                            if (io.gate_table) gat[v] = __ldg(reinterpret_cast<const float4*>(io.gate_table + (long long)grow[rr] * p.cout + col));
+                            if (has_pre) pre[v] = __ldg(reinterpret_cast<const float4*>(io.pre_add + ro[v]));
+                            if (has_res32) res[v] = __ldg(reinterpret_cast<const float4*>(io.residual + ro[v]));
+                            else if (has_resh) res[v] = load_residual4(nullptr, io.residual_h, orow, C, col);
+                            if (has_gate) gat[v] = __ldg(reinterpret_cast<const float4*>(io.gate_table + (long long)grow[rr] * C + col));
                         }
                     }
 #pragma unroll
                     for (int v = 0; v < RB; ++v) {
+                        if (ro[v] < 0) continue;
                         const int rr = (lane >> 2) + 8 * (u0 + v);
-                        const int orow = rows[rr];
-                        if (orow < 0) continue;
-                        const long long ro = (long long)orow * p.cout + col;
                         const float4 a4 = *reinterpret_cast<const float4*>(myslab + rr * SLAB_PITCH + lc4);
                         float y[4] = {a4.x + pre[v].x, a4.y + pre[v].y, a4.z + pre[v].z, a4.w + pre[v].w};
                         y[0] = fmaf(y[0], s4.x, h4.x) + res[v].x; y[1] = fmaf(y[1], s4.y, h4.y) + res[v].y;
                         y[2] = fmaf(y[2], s4.z, h4.z) + res[v].z; y[3] = fmaf(y[3], s4.w, h4.w) + res[v].w;
-                        if (p.relu) {
+                        if (do_relu) {
 #pragma unroll
                             for (int q = 0; q < 4; ++q) y[q] = fmaxf(y[q], 0.f);
                         }
-                        if (io.out) store_f4(io.out + ro, y, p.cs);
-                        if (io.out_h) store_split4(io.out_h, orow, p.cout, col, y, p.cs);
-                        if (io.out_gated || io.out_gated_h) {
+                        const long long roh = 2 * ro[v] - col;       // (row, col) in a (rows, 2C) companion: row * 2C + col
+                        if (w_out) store_f4(io.out + ro[v], y, cs_st);
+                        if (w_outh) store_split4_at(reinterpret_cast<__half*>(io.out_h) + roh, C, y, cs_st);
+                        if (w_g || w_gh) {
                             y[0] *= gat[v].x; y[1] *= gat[v].y; y[2] *= gat[v].z; y[3] *= gat[v].w;
-                            if (io.out_gated) store_f4(io.out_gated + ro, y, p.cs);
-                            if (io.out_gated_h) store_split4(io.out_gated_h, orow, p.cout, col, y, p.cs);
+                            if (w_g) store_f4(io.out_gated + ro[v], y, cs_st);
+                            if (w_gh) store_split4_at(reinterpret_cast<__half*>(io.out_gated_h) + roh, C, y, cs_st);
                         }
                     }
                 }

@@ -414,6 +414,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_spconv
             }
             // ---- epilogue from registers, 16 channels at a time through the warp's slab (coalesced global accesses) ----
             const int lc4 = (lane & 3) * 4;
+            // which operands / outputs this pass has: decided once per tile (predicates), not per element
+            const bool has_pre = io.pre_add != nullptr, has_res32 = io.residual != nullptr, has_resh = !has_res32 && io.residual_h != nullptr;
+            const bool has_gate = io.gate_table != nullptr, w_out = io.out != nullptr, w_outh = io.out_h != nullptr;
+            const bool w_g = io.out_gated != nullptr, w_gh = io.out_gated_h != nullptr;
+            const bool cs_st = p.cs != 0, has_aff = p.scale != nullptr, do_relu = p.relu != 0;
 #pragma unroll 1
             for (int cs = 0; cs < TOT / 16; ++cs) {                 // run-time loop: one copy of the global-memory code (see slab_write_switch)
                 __syncwarp();
@@ -421,42 +426,42 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_spconv
                 __syncwarp();
                 const int col = cb + cs * 16 + lc4;
                 float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f), h4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (p.scale) { s4 = __ldg(reinterpret_cast<const float4*>(p.scale + col)); h4 = __ldg(reinterpret_cast<const float4*>(p.shift + col)); }
+                if (has_aff) { s4 = __ldg(reinterpret_cast<const float4*>(p.scale + col)); h4 = __ldg(reinterpret_cast<const float4*>(p.shift + col)); }
 #pragma unroll
                 for (int i0 = 0; i0 < 4; i0 += 2) {                 // two rows per batch: loads first, then math + stores
                     float4 pre[2], res[2], gat[2];
+                    long long ro[2];                                // element offset of (row, col) in a (rows, NCOLS) fp32 tensor; < 0: no row
 #pragma unroll
                     for (int u = 0; u < 2; ++u) {
                         const int i = i0 + u;
                         pre[u] = make_float4(0.f, 0.f, 0.f, 0.f); res[u] = pre[u]; gat[u] = make_float4(1.f, 1.f, 1.f, 1.f);
+                        ro[u] = orows[i] >= 0 ? (long long)orows[i] * NCOLS + col : -1;
                         if (orows[i] >= 0) {
-                            const long long ro = (long long)orows[i] * NCOLS + col;
-                            if (io.pre_add) pre[u] = __ldg(reinterpret_cast<const float4*>(io.pre_add + ro));
-                            res[u] = load_residual4(io.residual, io.residual_h, orows[i], NCOLS, col);
-                            if (io.gate_table) gat[u] = __ldg(reinterpret_cast<const float4*>(io.gate_table + (long long)gidx[i] * NCOLS + col));
+                            if (has_pre) pre[u] = __ldg(reinterpret_cast<const float4*>(io.pre_add + ro[u]));
+                            if (has_res32) res[u] = __ldg(reinterpret_cast<const float4*>(io.residual + ro[u]));
+                            else if (has_resh) res[u] = load_residual4(nullptr, io.residual_h, orows[i], NCOLS, col);
+                            if (has_gate) gat[u] = __ldg(reinterpret_cast<const float4*>(io.gate_table + (long long)gidx[i] * NCOLS + col));
                         }
                     }
 #pragma unroll
                     for (int u = 0; u < 2; ++u) {
-                        const int i = i0 + u;
-                        const int orow = orows[i];
-                        if (orow < 0) continue;
-                        const int rr = (lane >> 2) + 8 * i;
-                        const long long ro = (long long)orow * NCOLS + col;
+                        if (ro[u] < 0) continue;
+                        const int rr = (lane >> 2) + 8 * (i0 + u);
                         const float4 a4 = *reinterpret_cast<const float4*>(myslab + rr * SLAB_PITCH + lc4);
                         float y[4] = {a4.x + pre[u].x, a4.y + pre[u].y, a4.z + pre[u].z, a4.w + pre[u].w};
                         y[0] = fmaf(y[0], s4.x, h4.x) + res[u].x; y[1] = fmaf(y[1], s4.y, h4.y) + res[u].y;
                         y[2] = fmaf(y[2], s4.z, h4.z) + res[u].z; y[3] = fmaf(y[3], s4.w, h4.w) + res[u].w;
-                        if (p.relu) {
+                        if (do_relu) {
 #pragma unroll
                             for (int q = 0; q < 4; ++q) y[q] = fmaxf(y[q], 0.f);
                         }
-                        if (io.out) store_f4(io.out + ro, y, p.cs);
-                        if (io.out_h) store_split4(io.out_h, orow, NCOLS, col, y, p.cs);
-                        if (io.out_gated || io.out_gated_h) {
+                        const long long roh = 2 * ro[u] - col;       // (row, col) in a (rows, 2 NCOLS) companion
+                        if (w_out) store_f4(io.out + ro[u], y, cs_st);
+                        if (w_outh) store_split4_at(reinterpret_cast<__half*>(io.out_h) + roh, NCOLS, y, cs_st);
+                        if (w_g || w_gh) {
                             y[0] *= gat[u].x; y[1] *= gat[u].y; y[2] *= gat[u].z; y[3] *= gat[u].w;
-                            if (io.out_gated) store_f4(io.out_gated + ro, y, p.cs);
-                            if (io.out_gated_h) store_split4(io.out_gated_h, orow, NCOLS, col, y, p.cs);
+                            if (w_g) store_f4(io.out_gated + ro[u], y, cs_st);
+                            if (w_gh) store_split4_at(reinterpret_cast<__half*>(io.out_gated_h) + roh, NCOLS, y, cs_st);
                         }
                     }
                 }

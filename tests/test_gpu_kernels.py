@@ -541,6 +541,9 @@ def test_persistent_kernel_equals_per_tile_kernel(c1, c2, cout, lvl, kind):
         return xh
     A_h, B_h = split_of(A), split_of(B)                # with companions the 256-channel layers take the register-total kernel
     res = []
+    old_pair = h.get_option(_lib.OPT_TC_PAIR)
+    h.set_option(_lib.OPT_TC_PAIR, 0)          # the single-CTA persistent kernels; the CTA-pair kernel runs the union of two tiles' offsets
+                                               # (other accumulation grouping) and has its own oracle test (test_gpu_conv_pair.py)
     for algo in (_lib.ALGO_TC_TILE, _lib.ALGO_TC):
         out, outg = torch.zeros(2, N, cout, device=DEV), torch.zeros(2, N, cout, device=DEV)
         out_h = torch.zeros(2, N, 2 * cout, dtype=torch.float16, device=DEV)
@@ -558,6 +561,7 @@ def test_persistent_kernel_equals_per_tile_kernel(c1, c2, cout, lvl, kind):
                               A_h[p_].data_ptr(), B_h[p_].data_ptr() if B_h is not None else None, out_h[p_].data_ptr(), None)
         h.spconv(d, algo)
         res.append((out[:, :M].clone(), outg[:, :M].clone(), out_h[:, :M].clone()))
+    h.set_option(_lib.OPT_TC_PAIR, old_pair)
     for a, b in zip(res[0], res[1]):
         assert torch.equal(a, b)
     assert res[0][0].abs().sum() > 0
