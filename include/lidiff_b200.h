@@ -117,6 +117,14 @@ size_t lb2_row_order_scratch_bytes(int32_t n_cap);
 int lb2_row_order(void* h, void* stream, const uint32_t* row_mask, const int32_t* d_n, int32_t n_cap,
                   int32_t kvol, int32_t* perm, void* scratch, const int32_t* coords, int32_t coord_shift);
 
+/* Cost order of the tiles of a map (scheduling only; results do not depend on it): order128[i] / order256[i] = index of the i-th most
+ * expensive 128-row tile / 256-row super-tile of the row order `row_perm`, cost = number of kernel offsets the tile has to run (popcount of
+ * the OR of its rows' masks); entries beyond the live tile count are -1.  The persistent convolution kernels deal tiles to their CTAs in
+ * snake order over this sequence (lb2_conv_desc.tile_order128 / tile_order256), which balances a static assignment to within 1-3 %.
+ * order128: cdiv(n_cap,128) ints, order256: cdiv(n_cap,256) ints, scratch: cdiv(n_cap,128) * 4 bytes. */
+int lb2_tile_order(void* h, void* stream, const uint32_t* row_mask, const int32_t* row_perm, const int32_t* d_n, int32_t n_cap,
+                   int32_t* order128, int32_t* order256, void* scratch);
+
 /* ---- sparse convolution  — replaces ME.MinkowskiConvolution(+Transpose) forward, with the
  * MinkowskiBatchNorm(eval)/MinkowskiReLU/residual-add/ME.cat/gate-multiply that follow it in
  * minkunet.py:13-80,431,464 fused as prologue/epilogue.
@@ -162,6 +170,8 @@ typedef struct {
                                    A hint: lets the kernels skip the index loads of absent offsets */
     int32_t        npass;       /* 1 or 2 */
     lb2_conv_io    io[2];
+    const int32_t* tile_order128;  /* from lb2_tile_order or NULL (tiles in row-order sequence, heaviest-looking last) */
+    const int32_t* tile_order256;
 } lb2_conv_desc;
 
 #define LB2_ALGO_AUTO  0

@@ -796,3 +796,68 @@ extern "C" int lb2_nn_tree_build(void* handle, void* stream, const int32_t* k_co
     LB2_POST_LAUNCH(h, "k_nt_internal");
     return LB2_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// tile order: the persistent convolution kernels assign tiles to CTAs statically (snake order).  That is balanced only if the tiles
+// are sorted by cost.  The cost of a tile is the number of kernel offsets it has to run = popcount of the OR of its rows' masks;
+// the mask-sorted row order is not monotone in it.  k_tile_masks ORs the masks of every 128-row tile (one warp per tile),
+// k_tile_sort counting-sorts the 128-row tiles and the 256-row super-tiles (CTA pairs) by descending cost.
+//   order128[i] / order256[i] = index of the i-th most expensive tile; entries beyond the live tile count are -1.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_tile_masks(const unsigned* __restrict__ mask, const int* __restrict__ perm, const int* __restrict__ d_n,
+                                                    int n_cap, unsigned* __restrict__ tmask) {
+    const int n = d_n ? min(*d_n, n_cap) : n_cap;
+    const int nt = (n + 127) >> 7;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= nt) return;
+    unsigned m = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int slot = warp * 128 + q * 32 + lane;
+        if (slot < n) m |= __ldg(mask + (perm ? __ldg(perm + slot) : slot));
+    }
+    m = __reduce_or_sync(0xffffffffu, m);
+    if (lane == 0) tmask[warp] = m;
+}
+
+__global__ void __launch_bounds__(1024) k_tile_sort(const unsigned* __restrict__ tmask, const int* __restrict__ d_n, int n_cap,
+                                                    int* __restrict__ order128, int* __restrict__ order256) {
+    __shared__ int bins[2][33];
+    const int n = d_n ? min(*d_n, n_cap) : n_cap;
+    const int nt128 = (n + 127) >> 7, nt256 = (n + 255) >> 8;
+    const int cap128 = (n_cap + 127) >> 7, cap256 = (n_cap + 255) >> 8;
+    if (threadIdx.x < 66) (&bins[0][0])[threadIdx.x] = 0;
+    __syncthreads();
+    // histogram of costs (0..32), descending order: bin b holds cost 32 - b
+    for (int t = threadIdx.x; t < nt128; t += blockDim.x) atomicAdd(&bins[0][32 - __popc(tmask[t])], 1);
+    for (int u = threadIdx.x; u < nt256; u += blockDim.x) {
+        const unsigned m = tmask[2 * u] | ((2 * u + 1 < nt128) ? tmask[2 * u + 1] : 0u);
+        atomicAdd(&bins[1][32 - __popc(m)], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) {                                   // exclusive scan of 33 bins
+        int run = 0;
+        for (int b = 0; b < 33; ++b) { const int v = bins[threadIdx.x][b]; bins[threadIdx.x][b] = run; run += v; }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < nt128; t += blockDim.x) order128[atomicAdd(&bins[0][32 - __popc(tmask[t])], 1)] = t;
+    for (int u = threadIdx.x; u < nt256; u += blockDim.x) {
+        const unsigned m = tmask[2 * u] | ((2 * u + 1 < nt128) ? tmask[2 * u + 1] : 0u);
+        order256[atomicAdd(&bins[1][32 - __popc(m)], 1)] = u;
+    }
+    for (int t = nt128 + threadIdx.x; t < cap128; t += blockDim.x) order128[t] = -1;
+    for (int u = nt256 + threadIdx.x; u < cap256; u += blockDim.x) order256[u] = -1;
+}
+
+extern "C" int lb2_tile_order(void* handle, void* stream, const uint32_t* row_mask, const int32_t* row_perm, const int32_t* d_n, int32_t n_cap,
+                              int32_t* order128, int32_t* order256, void* scratch) {
+    Lb2Handle* h = (Lb2Handle*)handle;
+    LB2_REQUIRE(h, h && row_mask && order128 && order256 && scratch && n_cap > 0, "tile_order");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int cap128 = cdiv(n_cap, 128);
+    k_tile_masks<<<cdiv(cap128, 8), 256, 0, s>>>(row_mask, row_perm, d_n, n_cap, (unsigned*)scratch);
+    LB2_POST_LAUNCH(h, "k_tile_masks");
+    k_tile_sort<<<1, 1024, 0, s>>>((const unsigned*)scratch, d_n, n_cap, order128, order256);
+    LB2_POST_LAUNCH(h, "k_tile_sort");
+    return LB2_OK;
+}

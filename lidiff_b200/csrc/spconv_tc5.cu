@@ -59,6 +59,7 @@ struct Params {
     const unsigned* row_mask;
     int nchunks, group, npass;
     int cs;                     // evict-first epilogue stores
+    const int* tile_order;      // tiles by descending cost (lb2_tile_order) or NULL
     lb2_conv_io io[2];
 };
 
@@ -105,11 +106,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_spconv
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_rank();
     const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-    // work item -> (tile, pass): pass-major (the two guidance passes read different feature tensors: one pass at a time keeps the
-    // gathered working set inside the 126 MB L2), inside a pass the heaviest tiles first (the row order sorts rows by neighbour
-    // mask, light to heavy), so the last, partially filled round of the persistent loop holds the cheapest tiles
-    auto item_pass = [&](int item) { return item >= n_stiles ? 1 : 0; };
-    auto item_tile = [&](int item) { return n_stiles - 1 - (item >= n_stiles ? item - n_stiles : item); };
+    // work item -> (tile, pass).  With a cost order (lb2_tile_order): item i = pass (i & 1) of the (i >> 1)-th most expensive tile, so the
+    // item sequence is sorted by cost and the snake deal below is balanced to 1-3 %.  Without: pass-major, inside a pass the last
+    // tiles of the mask-sorted row order (roughly the heaviest) first.
+    const int pshift = (p.tile_order && p.npass == 2) ? 1 : 0;
+    auto item_pass = [&](int item) { return p.tile_order ? (item & pshift) : (item >= n_stiles ? 1 : 0); };
+    auto item_tile = [&](int item) {
+        if (p.tile_order) return __ldg(p.tile_order + (item >> pshift));
+        return n_stiles - 1 - (item >= n_stiles ? item - n_stiles : item);
+    };
     // round j of the persistent loop in snake order (even rounds left to right, odd rounds right to left over the CTAs): with the
     // items sorted by cost every CTA alternates between a dearer and a cheaper item, so the per-CTA sums stay balanced (static LPT);
     // an item index >= total (last, partial round) is an empty tile for every role
@@ -514,5 +519,6 @@ int lb2_spconv_tc5_launch(Lb2Handle* h, cudaStream_t s, const lb2_conv_desc* d, 
     p.group = std::max(1, step_budget / steps_per_offset);
     p.io[0] = d->io[0]; p.io[1] = d->io[d->npass > 1 ? 1 : 0];
     p.cs = h->opt[LB2_OPT_STREAM_STORES] ? 1 : 0;
+    p.tile_order = d->tile_order256;
     return d->cout == 256 ? launch_pair<256>(h, s, p, d->mout_cap, d->npass) : launch_pair<128>(h, s, p, d->mout_cap, d->npass);
 }

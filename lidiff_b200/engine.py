@@ -136,6 +136,10 @@ class Geometry:
         self.perm_dn = [None] + [torch.zeros(n_cap, **i32) for _ in range(levels - 1)]
         self.perm_up = [torch.zeros(n_cap, **i32) for _ in range(levels - 1)] + [None] if with_up else None
         self.perm_of = {}
+        # cost order of the 128-row tiles / 256-row super-tiles of every map (static LPT schedule of the persistent conv kernels)
+        self.use_tile_order = os.environ.get("LB2_TILE_ORDER", "1") != "0"
+        self.tile_order_of = {}
+        self.to_scratch = torch.zeros((n_cap + 127) // 128, **i32)
         # per-offset (in,out) pair lists of the 3^3 maps of the sparse levels (gather-GEMM-scatter form)
         self.morton_levels = set(int(c) for c in os.environ.get("LB2_MORTON_LEVELS", "") if c.isdigit())
         self.pair_levels = min(3, levels)
@@ -168,6 +172,12 @@ class Geometry:
             # 3^3 maps of the levels with many neighbours per row: rows of equal mask in Morton order (compact tiles, L2 locality)
             morton = ks == 3 and l_out in self.morton_levels
             h.row_order(mask, self.d_n[l_out], N, ks ** 3, perm, self.ro_scratch, self.C[l_out] if morton else None, l_out)
+            if self.use_tile_order:
+                to = self.tile_order_of.get(nbr.data_ptr())
+                if to is None:
+                    to = self.tile_order_of[nbr.data_ptr()] = (torch.zeros((N + 127) // 128, dtype=torch.int32, device=nbr.device),
+                                                               torch.zeros((N + 255) // 256, dtype=torch.int32, device=nbr.device))
+                h.tile_order(mask, perm, self.d_n[l_out], N, to[0], to[1], self.to_scratch)
             self.map_id[nbr.data_ptr()] = slot
             self.perm_of[nbr.data_ptr()] = perm
 
@@ -242,9 +252,11 @@ class DenoiseEngine:
         self.lean = os.environ.get("LB2_LEAN", "1") != "0" and not os.environ.get("LB2_SCATTER_LEVELS")
         self._acts = {}
         self._perm_lookup = {}
+        self._tile_order_lookup = {}
         self.geom = Geometry(h, self.N, with_up=True)
         self._perm_lookup = self.geom.perm_of
         self._mask_lookup = self.geom.mask_of
+        self._tile_order_lookup = self.geom.tile_order_of
         self._pairs_lookup = _PairLookup(self.geom)
         self.geom_cond = None
         self.part_cap = 0
@@ -254,6 +266,8 @@ class DenoiseEngine:
         if self.use_side_stream:
             self._side = torch.cuda.Stream(device=self.device)
             self._side_done = torch.cuda.Event()
+            self._side2 = torch.cuda.Stream(device=self.device)       # gate tables (depend on the step index only)
+            self._side2_done = torch.cuda.Event()
         # optional instrumentation (bench.py): per-conv CUDA events + layer inventory + pair-count history
         self.conv_events = None          # list of (start, end, layer_index) when enabled
         self.layer_log = None            # list of dict(map, lvl, cin, cout, kvol, npass, tc) recorded during one step
@@ -400,6 +414,9 @@ class DenoiseEngine:
         d.row_perm = perm.data_ptr() if perm is not None else None
         mask = self._mask_lookup.get(nbr.data_ptr()) if nbr is not None else None
         d.row_mask = mask.data_ptr() if mask is not None else None
+        to = self._tile_order_lookup.get(nbr.data_ptr()) if (nbr is not None and perm is not None) else None
+        d.tile_order128 = to[0].data_ptr() if to is not None else None
+        d.tile_order256 = to[1].data_ptr() if to is not None else None
         res_h = hh(residual) if (residual is not None and residual.f is None) else None
         for p in range(npass):
             gt = gi = None
@@ -446,7 +463,7 @@ class DenoiseEngine:
         self._conv(L[f"{p}.net.3"], nbr, d_m, cap, hbuf, None, out=out, residual=sbuf, relu=True, gate=gate, out_gated=og, npass=npass)
         return out, og
 
-    def _encoder(self, L, geom, F0: Act, npass, tag, gates=None, lean=False):
+    def _encoder(self, L, geom, F0: Act, npass, tag, gates=None, lean=False, before_gates=None):
         """stem + 4 stages.  gates: None (MinkGlobalEnc / refinement net) or per-gate list of per-pass (table, idx)."""
         cap = geom.n_cap
         s0 = self.act(f"{tag}.stem0", 1, cap, 32, f32=not lean)
@@ -455,6 +472,8 @@ class DenoiseEngine:
         self._conv(L["stem.3"], geom.nbr3[0], geom.d_n[0], cap, s0, out=x0, npass=1)
         skips = [x0]
         if gates is not None:
+            if before_gates is not None:
+                before_gates()
             cur = self.act(f"{tag}.x0g", npass, cap, 32, f32=not lean)
             for p in range(npass):
                 tb, ix = gates[0][p]
@@ -518,6 +537,7 @@ class DenoiseEngine:
             self.geom_cond = Geometry(self.h, N, with_up=False, use_pairs=False)
             self._perm_lookup = ChainMap(self.geom.perm_of, self.geom_cond.perm_of)
             self._mask_lookup = ChainMap(self.geom.mask_of, self.geom_cond.mask_of)
+            self._tile_order_lookup = ChainMap(self.geom.tile_order_of, self.geom_cond.tile_order_of)
         coords = self.buf("cond.coords", (N, 4))
         coords[:, 0] = 0
         self.h.quantize(pts, self.resolution, self.div_mode, self.buf("cond.q", (N, 3)))
@@ -541,9 +561,21 @@ class DenoiseEngine:
         nn = [None] * 5
         tabs_box = []
 
-        def matches_and_gates():
-            # the NN matches need only the coordinate levels and the gate tables nothing of this step's geometry: both run on a side
-            # stream next to the kernel-map / row-order construction (all of them small latency-bound kernels)
+        def gate_tables():
+            tabs_box.append(self._gate_tables(self.A_cond, self.part_cap, self.part_dn, i, "c"))
+
+        # the gate tables depend on the step index only: third stream, from the start of the step
+        if self.use_side_stream:
+            self._side2.wait_stream(torch.cuda.current_stream())      # the previous step's readers of gate_* are enqueued
+            with torch.cuda.stream(self._side2):
+                gate_tables()
+                self._side2_done.record(self._side2)
+        else:
+            gate_tables()
+
+        def matches():
+            # the NN matches need only the coordinate levels: they run on a side stream next to the kernel-map / row-order
+            # construction (all of them small latency-bound kernels)
             for l in range(4, -1, -1):               # coarse to fine: a voxel's search starts from its parent voxel's answer
                 ix = self.buf(f"nn{l}", (N,), torch.int32)
                 # (the shared-memory-table variant lb2_nn_match_table measured slower: 2.1 vs 1.7 ms for the 5 levels)
@@ -554,20 +586,22 @@ class DenoiseEngine:
                 else:
                     h.nn_match_tree(g.C[l], g.d_n[l], N, self.part_tree, self.part_cap, ix, self.part_C, g.inv[l + 1], nn[l + 1])
                 nn[l] = ix
-            tabs_box.append(self._gate_tables(self.A_cond, self.part_cap, self.part_dn, i, "c"))
 
         def after_levels():
             if not self.use_side_stream:
-                return matches_and_gates()
+                return matches()
             main = torch.cuda.current_stream()
-            self._side.wait_stream(main)             # the levels are enqueued; the previous step's readers of nn*/gate_* too
+            self._side.wait_stream(main)             # the levels are enqueued; the previous step's readers of nn* too
             with torch.cuda.stream(self._side):
-                matches_and_gates()
+                matches()
                 self._side_done.record(self._side)
 
+        def join_sides():                            # called by the encoder behind the stem, in front of the first gate multiply
+            if self.use_side_stream:
+                torch.cuda.current_stream().wait_event(self._side_done)
+                torch.cuda.current_stream().wait_event(self._side2_done)
+
         g.build(coords, N, after_levels)
-        if self.use_side_stream:
-            torch.cuda.current_stream().wait_event(self._side_done)
         if self.pair_hist is not None:
             g.pairs[13:18] = torch.cat(g.d_n).long()
             self.pair_hist[self._hist_row % self.pair_hist.shape[0]] = g.pairs
@@ -576,7 +610,7 @@ class DenoiseEngine:
         g.voxel_mean(x_t, N, F0.f[0])
         tabs_c = tabs_box[0]
         gates = [[(tabs_c[k], nn[GATE_LEVEL[k]]), (self.table_u[k][i:i + 1], None)] for k in range(8)]
-        skips, cur = self._encoder(self.diff, g, F0, 2, "d", gates, lean=self.lean)
+        skips, cur = self._encoder(self.diff, g, F0, 2, "d", gates, lean=self.lean, before_gates=join_sides)
         y4 = self._decoder(self.diff, g, skips, cur, 2, "d", gates, lean=self.lean)
         eps = self.buf("eps_vox", (2, N, 3))
         hid = self.buf("head_h", (N, 20))

@@ -153,6 +153,17 @@ class FakeHandle:
         perm[:n] = torch.flip(order, [0]).int() if n > 3 else order.int()     # any in-bucket order is legal; scramble a bit
         perm[:n] = order.int()
 
+    def tile_order(self, row_mask, row_perm, d_n, n_cap, order128, order256, scratch):
+        self.launches += 2
+        n = self._n(d_n, n_cap)
+        m = (row_mask[:n][row_perm[:n].long()] if row_perm is not None else row_mask[:n]).long() & 0xFFFFFFFF
+        for T, out in ((128, order128), (256, order256)):
+            nt = (n + T - 1) // T
+            cost = torch.tensor([bin(int(torch.tensor(0) if m[t * T:(t + 1) * T].numel() == 0 else
+                                         torch.from_numpy(np.bitwise_or.reduce(m[t * T:(t + 1) * T].numpy(), keepdims=True))[0])).count("1") for t in range(nt)])
+            out[:] = -1
+            out[:nt] = torch.argsort(-cost, stable=True).int()
+
     # conv -----------------------------------------------------------------------------------------
     def packed_weight_bytes(self, kvol, cin, cout):
         return 0

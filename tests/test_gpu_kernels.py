@@ -271,6 +271,29 @@ def test_farthest_point_sampling_bit_exact():
     assert np.array_equal(got, ref)
 
 
+def test_tile_order_sorts_tiles_by_the_offsets_they_run():
+    """lb2_tile_order: order128 / order256 are permutations of the live tiles of the row order, by descending popcount of the OR of
+    the tile's row masks; entries beyond the live tiles are -1"""
+    from lidiff_b200.engine import Geometry
+    h = H()
+    pts, coords = random_field(50_000, 0.5, 23)
+    N = coords.shape[0]
+    g = Geometry(h, N)
+    g.build(coords.to(DEV).contiguous(), N)
+    sizes = g.sizes()
+    for nbr, perm, lvl in ((g.nbr3[1], g.perm3[1], 1), (g.nbr3[3], g.perm3[3], 3), (g.nbr_dn[2], g.perm_dn[2], 2)):
+        M = sizes[lvl]
+        mask = g.mask_of[nbr.data_ptr()][:M].cpu().numpy().astype(np.uint32)
+        pm = mask[perm[:M].cpu().numpy()]
+        o128, o256 = (t.cpu().numpy() for t in g.tile_order_of[nbr.data_ptr()])
+        for T, order in ((128, o128), (256, o256)):
+            nt = (M + T - 1) // T
+            cost = np.array([bin(int(np.bitwise_or.reduce(pm[t * T:(t + 1) * T]))).count("1") for t in range(nt)])
+            assert np.array_equal(np.sort(order[:nt]), np.arange(nt)), "not a permutation of the live tiles"
+            assert (order[nt:] == -1).all()
+            assert (np.diff(cost[order[:nt]]) <= 0).all(), "tiles must come out by descending cost"
+
+
 @pytest.mark.parametrize("spread,algo", [(1.0, 1), (0.1, 2), (1.0, 2)])
 def test_row_order_is_a_permutation_and_does_not_change_results(spread, algo):
     """lb2_row_order only reschedules tiles: perm is a permutation grouped by mask class, conv output identical"""
