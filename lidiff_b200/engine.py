@@ -132,6 +132,7 @@ class Geometry:
         # execution order of the output rows of each map (rows bucketed by neighbour mask, lb2_row_order)
         self.mask_of = {}                                    # map -> its per-row neighbour bit mask (conv kernels skip absent offsets)
         self.ro_scratch = torch.zeros((h.row_order_scratch_bytes(n_cap) + 3) // 4, **i32)
+        self.ro_scratch_late = self.to_scratch_late = None      # second scratch set: maps built on a side stream (build(late_stream=...))
         self.perm3 = [torch.zeros(n_cap, **i32) for _ in range(levels)]
         self.perm_dn = [None] + [torch.zeros(n_cap, **i32) for _ in range(levels - 1)]
         self.perm_up = [torch.zeros(n_cap, **i32) for _ in range(levels - 1)] + [None] if with_up else None
@@ -152,10 +153,13 @@ class Geometry:
         self.koff = [torch.zeros(28, **i32) for _ in range(self.pair_levels)]
         self.tile_off = [torch.zeros(28, **i32) for _ in range(self.pair_levels)]
 
-    def build(self, coords_f: torch.Tensor, n_points: int, after_levels=None):
+    def build(self, coords_f: torch.Tensor, n_points: int, after_levels=None, late_stream=None, late_done=None):
         """coords_f (n_points,4) fp32 integer-valued [b,x,y,z] -> all levels and maps (async).  `after_levels()` is called once the
         coordinate levels (C, inv, d_n, grids) are enqueued and before the kernel maps: work that only needs the levels can be
-        put on another stream there and overlap with the map construction."""
+        put on another stream there and overlap with the map construction.
+        late_stream / late_done: the maps the network needs first (3^3 of levels 0-1, stride-2 into level 1) are built on the current
+        stream, all others on `late_stream` (own scratch buffers), `late_done` recorded behind them: the caller waits for it in front
+        of the first layer of stage 2, so ~0.6 ms of map construction hides behind the stem and stage-1 convolutions."""
         h, N = self.h, self.n_cap
         h.unique_build(coords_f, None, None, n_points, 0, self.grid[0], self.C[0], self.inv[0], self.d_n[0], self.scratch)
         for l in range(1, self.levels):
@@ -164,33 +168,63 @@ class Geometry:
             after_levels()
         self.pairs.zero_()
 
-        def one(grid, l_out, ks, step, nbr, perm, slot):
+        def one(grid, l_out, ks, step, nbr, perm, slot, ro_scratch=None, to_scratch=None):
+            ro_scratch = self.ro_scratch if ro_scratch is None else ro_scratch
+            to_scratch = self.to_scratch if to_scratch is None else to_scratch
             mask = self.mask_of.get(nbr.data_ptr())
             if mask is None:
                 mask = self.mask_of[nbr.data_ptr()] = torch.zeros(N, dtype=torch.int32, device=nbr.device)
             h.kernel_map(grid, self.C[l_out], self.d_n[l_out], N, ks, step, nbr, N, self.pairs[slot:slot + 1], mask)
             # 3^3 maps of the levels with many neighbours per row: rows of equal mask in Morton order (compact tiles, L2 locality)
             morton = ks == 3 and l_out in self.morton_levels
-            h.row_order(mask, self.d_n[l_out], N, ks ** 3, perm, self.ro_scratch, self.C[l_out] if morton else None, l_out)
+            h.row_order(mask, self.d_n[l_out], N, ks ** 3, perm, ro_scratch, self.C[l_out] if morton else None, l_out)
             if self.use_tile_order:
                 to = self.tile_order_of.get(nbr.data_ptr())
                 if to is None:
                     to = self.tile_order_of[nbr.data_ptr()] = (torch.zeros((N + 127) // 128, dtype=torch.int32, device=nbr.device),
                                                                torch.zeros((N + 255) // 256, dtype=torch.int32, device=nbr.device))
-                h.tile_order(mask, perm, self.d_n[l_out], N, to[0], to[1], self.to_scratch)
+                h.tile_order(mask, perm, self.d_n[l_out], N, to[0], to[1], to_scratch)
             self.map_id[nbr.data_ptr()] = slot
             self.perm_of[nbr.data_ptr()] = perm
 
-        for l in range(self.levels):
-            one(self.grid[l], l, 3, 1 << l, self.nbr3[l], self.perm3[l], l)
+        def map3(l, **kw):
+            one(self.grid[l], l, 3, 1 << l, self.nbr3[l], self.perm3[l], l, **kw)
             if l < self.pair_levels and self.use_pairs and l in self.pair_level_set:
                 h.pair_list(self.nbr3[l], N, self.d_n[l], N, 27, 13, self.pair_in[l], self.pair_out[l], self.koff[l], self.tile_off[l], self.pl_scratch)
                 self.pairs_of[self.nbr3[l].data_ptr()] = l
-        for l in range(1, self.levels):
-            one(self.grid[l - 1], l, 2, 1 << (l - 1), self.nbr_dn[l], self.perm_dn[l], 4 + l)
-        if self.nbr_up is not None:
+
+        def map_dn(l, **kw):
+            one(self.grid[l - 1], l, 2, 1 << (l - 1), self.nbr_dn[l], self.perm_dn[l], 4 + l, **kw)
+
+        def map_up(l, **kw):
+            one(self.grid[l + 1], l, 2, -(1 << l), self.nbr_up[l], self.perm_up[l], 9 + l, **kw)
+
+        split = late_stream is not None and self.levels >= 3 and not (self.use_pairs and self.pair_level_set)
+        early3 = (0, 1) if split else tuple(range(self.levels))
+        early_dn = (1,) if split else tuple(range(1, self.levels))
+        if split:
+            if self.ro_scratch_late is None:
+                self.ro_scratch_late, self.to_scratch_late = torch.zeros_like(self.ro_scratch), torch.zeros_like(self.to_scratch)
+            kw = dict(ro_scratch=self.ro_scratch_late, to_scratch=self.to_scratch_late)
+            late_stream.wait_stream(torch.cuda.current_stream())          # levels, grids and the zeroed pair counters
+            with torch.cuda.stream(late_stream):
+                for l in range(2, self.levels):                           # in the order the network needs them
+                    map_dn(l, **kw)
+                    map3(l, **kw)
+                if self.nbr_up is not None:
+                    for l in range(self.levels - 2, -1, -1):
+                        map_up(l, **kw)
+                late_done.record(late_stream)
+        for l in early3:
+            if l >= 1 and l in early_dn:
+                map_dn(l)
+            map3(l)
+        for l in early_dn:
+            if l not in early3:
+                map_dn(l)
+        if not split and self.nbr_up is not None:
             for l in range(self.levels - 1):
-                one(self.grid[l + 1], l, 2, -(1 << l), self.nbr_up[l], self.perm_up[l], 9 + l)
+                map_up(l)
 
     def voxel_mean(self, feats, n_points, out):
         self.h.voxel_mean(feats, self.inv[0], n_points, feats.shape[1], self.d_n[0], self.n_cap, out, self.counts)
@@ -268,6 +302,9 @@ class DenoiseEngine:
             self._side_done = torch.cuda.Event()
             self._side2 = torch.cuda.Stream(device=self.device)       # gate tables (depend on the step index only)
             self._side2_done = torch.cuda.Event()
+            self._side3 = torch.cuda.Stream(device=self.device)       # kernel maps of levels 2-4 + all transposed maps
+            self._side3_done = torch.cuda.Event()
+        self.late_maps = self.use_side_stream and os.environ.get("LB2_LATE_MAPS", "1") != "0"
         # optional instrumentation (bench.py): per-conv CUDA events + layer inventory + pair-count history
         self.conv_events = None          # list of (start, end, layer_index) when enabled
         self.layer_log = None            # list of dict(map, lvl, cin, cout, kvol, npass, tc) recorded during one step
@@ -463,7 +500,7 @@ class DenoiseEngine:
         self._conv(L[f"{p}.net.3"], nbr, d_m, cap, hbuf, None, out=out, residual=sbuf, relu=True, gate=gate, out_gated=og, npass=npass)
         return out, og
 
-    def _encoder(self, L, geom, F0: Act, npass, tag, gates=None, lean=False, before_gates=None):
+    def _encoder(self, L, geom, F0: Act, npass, tag, gates=None, lean=False, before_gates=None, before_stage2=None):
         """stem + 4 stages.  gates: None (MinkGlobalEnc / refinement net) or per-gate list of per-pass (table, idx)."""
         cap = geom.n_cap
         s0 = self.act(f"{tag}.stem0", 1, cap, 32, f32=not lean)
@@ -482,6 +519,8 @@ class DenoiseEngine:
         else:
             cur = x0
         for n in range(1, 5):
+            if n == 2 and before_stage2 is not None:
+                before_stage2()
             a = self.act(f"{tag}.s{n}a", npass, cap, L[f"stage{n}.0.net.0"].cout, f32=not lean)
             self._conv(L[f"stage{n}.0.net.0"], geom.nbr_dn[n], geom.d_n[n], cap, cur, out=a, npass=npass)
             b, _ = self._res(L, f"stage{n}.1", geom, n, a, None, npass, f"{tag}.s{n}r1", lean=lean)
@@ -601,8 +640,17 @@ class DenoiseEngine:
                 torch.cuda.current_stream().wait_event(self._side_done)
                 torch.cuda.current_stream().wait_event(self._side2_done)
 
-        g.build(coords, N, after_levels)
+        def join_late_maps():                        # called by the encoder in front of stage 2 (first user of a late map)
+            if self.late_maps:
+                torch.cuda.current_stream().wait_event(self._side3_done)
+
+        if self.late_maps:
+            g.build(coords, N, after_levels, late_stream=self._side3, late_done=self._side3_done)
+        else:
+            g.build(coords, N, after_levels)
         if self.pair_hist is not None:
+            if self.late_maps:
+                torch.cuda.current_stream().wait_event(self._side3_done)
             g.pairs[13:18] = torch.cat(g.d_n).long()
             self.pair_hist[self._hist_row % self.pair_hist.shape[0]] = g.pairs
             self._hist_row += 1
@@ -610,7 +658,7 @@ class DenoiseEngine:
         g.voxel_mean(x_t, N, F0.f[0])
         tabs_c = tabs_box[0]
         gates = [[(tabs_c[k], nn[GATE_LEVEL[k]]), (self.table_u[k][i:i + 1], None)] for k in range(8)]
-        skips, cur = self._encoder(self.diff, g, F0, 2, "d", gates, lean=self.lean, before_gates=join_sides)
+        skips, cur = self._encoder(self.diff, g, F0, 2, "d", gates, lean=self.lean, before_gates=join_sides, before_stage2=join_late_maps)
         y4 = self._decoder(self.diff, g, skips, cur, 2, "d", gates, lean=self.lean)
         eps = self.buf("eps_vox", (2, N, 3))
         hid = self.buf("head_h", (N, 20))

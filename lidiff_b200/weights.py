@@ -15,7 +15,7 @@ _KINDS = {"enc": (mk.MinkGlobalEnc, {}), "diff": (mk.MinkUNetDiff, {}), "refine"
 def random_state_dict(kind: str, seed: int = 0) -> dict:
     cls, kw = _KINDS[kind]
     g = torch.Generator().manual_seed(seed)
-    with torch.random.fork_rng():
+    with torch.random.fork_rng(devices=[]):          # CPU generator only (the default would initialise every visible GPU)
         torch.manual_seed(seed)
         net = cls(in_channels=3, **kw)
     for m in net.modules():

@@ -95,3 +95,49 @@ def test_reference_pipeline_script_imports_on_the_shims():
         sys.path.remove("/root/reference")
         for m in [k for k in sys.modules if k == "lidiff" or k.startswith("lidiff.")]:
             sys.modules.pop(m)
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/lidiff/utils/metrics.py"), reason="reference tree not mounted")
+def test_reference_metrics_module_runs_on_the_open3d_shim():
+    """/root/reference/lidiff/utils/metrics.py (RMSE, ChamferDistance, PrecisionRecall, CompletionIoU) unchanged on the
+    open3d shim; the nearest-neighbour distances it builds on are checked against scipy's exact k-d tree"""
+    import importlib
+    from scipy.spatial import cKDTree
+    import open3d as o3d
+    sys.path.insert(0, "/root/reference")
+    try:
+        for m in [k for k in sys.modules if k == "lidiff" or k.startswith("lidiff.")]:
+            sys.modules.pop(m)
+        metrics = importlib.import_module("lidiff.utils.metrics")
+        metrics.torch = torch                                     # the module uses `torch.Tensor` without importing torch
+        g = np.random.default_rng(3)
+        gt = g.normal(size=(6000, 3)) * [12, 12, 1.0]
+        pred = gt[g.choice(6000, 4000, replace=False)] + g.normal(size=(4000, 3)) * 0.05
+        pg, pp = o3d.geometry.PointCloud(gt), o3d.geometry.PointCloud(pred)
+        d_pg = np.asarray(pp.compute_point_cloud_distance(pg))
+        d_gp = np.asarray(pg.compute_point_cloud_distance(pp))
+        assert np.allclose(d_pg, cKDTree(gt).query(pred)[0], rtol=0, atol=1e-9) and np.allclose(d_gp, cKDTree(pred).query(gt)[0], rtol=0, atol=1e-9)
+        cd, rm = metrics.ChamferDistance(), metrics.RMSE()
+        cd.update(pg, pp); rm.update(pg, pp)
+        assert abs(cd.compute()[0] - 0.5 * (d_pg.mean() + d_gp.mean())) < 1e-12 and abs(rm.compute()[0] - d_pg.mean()) < 1e-12
+        pr = metrics.PrecisionRecall(0.05, 1.0, 20)
+        pr.update(pg, pp)
+        p, r, f1, t = pr.compute_at_threshold(0.1)
+        assert abs(p - 100.0 * (d_pg < t).mean()) < 1e-9 and abs(r - 100.0 * (d_gp < t).mean()) < 1e-9 and 0 < f1 <= 100
+        assert all(0 <= v <= 100.000001 for v in pr.compute_auc())            # percentages, normalised by the perfect predictor
+        iou = metrics.CompletionIoU()
+        iou.update(pg, pp)
+        res = iou.compute()
+        assert set(res) == {0.5, 0.2, 0.1} and 0 < res[0.1] <= res[0.2] <= res[0.5] <= 1
+        assert not metrics.Metrics3D().prediction_is_empty(pp) and metrics.Metrics3D().prediction_is_empty(np.zeros((0, 3)))
+        assert metrics.Metrics3D.convert_to_pcd(pred).__class__ is o3d.geometry.PointCloud
+        # viewpoint mask of the training collation (collations.py:44-50): voxel-grid membership at 10 m
+        grid = o3d.geometry.VoxelGrid.create_from_point_cloud(pp, voxel_size=10.0)
+        inc = np.array(grid.check_if_included(o3d.utility.Vector3dVector(gt)))
+        org = pred.min(0) - 5.0
+        keys = {tuple(k) for k in np.floor((pred - org) / 10.0).astype(int)}
+        assert np.array_equal(inc, np.array([tuple(k) in keys for k in np.floor((gt - org) / 10.0).astype(int)]))
+    finally:
+        sys.path.remove("/root/reference")
+        for m in [k for k in sys.modules if k == "lidiff" or k.startswith("lidiff.")]:
+            sys.modules.pop(m)
