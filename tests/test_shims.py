@@ -125,10 +125,10 @@ def test_reference_metrics_module_runs_on_the_open3d_shim():
         p, r, f1, t = pr.compute_at_threshold(0.1)
         assert abs(p - 100.0 * (d_pg < t).mean()) < 1e-9 and abs(r - 100.0 * (d_gp < t).mean()) < 1e-9 and 0 < f1 <= 100
         assert all(0 <= v <= 100.000001 for v in pr.compute_auc())            # percentages, normalised by the perfect predictor
-        iou = metrics.CompletionIoU()
+        iou = metrics.CompletionIoU(voxel_sizes=[2.0, 1.0, 0.5])       # (the default 0.1 m grid is a 1000^3 float64 histogram: 8 GB)
         iou.update(pg, pp)
         res = iou.compute()
-        assert set(res) == {0.5, 0.2, 0.1} and 0 < res[0.1] <= res[0.2] <= res[0.5] <= 1
+        assert set(res) == {2.0, 1.0, 0.5} and 0 < res[0.5] <= res[1.0] <= res[2.0] <= 1
         assert not metrics.Metrics3D().prediction_is_empty(pp) and metrics.Metrics3D().prediction_is_empty(np.zeros((0, 3)))
         assert metrics.Metrics3D.convert_to_pcd(pred).__class__ is o3d.geometry.PointCloud
         # viewpoint mask of the training collation (collations.py:44-50): voxel-grid membership at 10 m
