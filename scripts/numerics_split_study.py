@@ -1,4 +1,4 @@
-"""CPU study (not collected by pytest; run `python tests/numerics_split_study.py`) of how the operand split of the tensor-core
+"""CPU study (not collected by pytest; run `python scripts/numerics_split_study.py`) of how the operand split of the tensor-core
 convolution propagates through the 49-layer guided U-Net of the oracle.  Every scheme replaces the per-offset GEMM of
 oracle.me_cpu.conv by an emulation of the products the hardware would form (fp32 accumulation, RN — the TMEM truncation of the
 real kernels is a separate, measured effect), and reports the error of the guided eps against the fp64 network with
