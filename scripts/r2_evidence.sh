@@ -10,7 +10,7 @@ echo "pytest exit $?" >> gpurun_out/pytest_gpu.log; tail -5 gpurun_out/pytest_gp
 cut -c1-260 gpurun_out/bench_n1.json
 timeout 600 python bench.py --gpus 1 --steps 50 --warmup 3 --no-cpu-baseline > gpurun_out/bench_n1_steps50.json 2> gpurun_out/bench_n1_steps50.stderr.log; echo "bench50 exit $?"
 cut -c1-200 gpurun_out/bench_n1_steps50.json
-( time timeout 900 python bench.py --impl reference --gpus 1 --steps 3 --warmup 1 > gpurun_out/bench_reference_arm.json 2> gpurun_out/bench_reference_arm.stderr.log ) 2>&1 | tail -3
+( time timeout 900 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > gpurun_out/bench_reference_arm.json 2> gpurun_out/bench_reference_arm.stderr.log ) 2>&1 | tail -3
 cut -c1-400 gpurun_out/bench_reference_arm.json
 LB2_GRAPHS=0 timeout 900 python bench.py --gpus 1 --T 1000 --steps 20 --warmup 3 --no-cpu-baseline --no-fixed --no-scan > gpurun_out/bench_T1000.json 2> gpurun_out/bench_T1000.stderr.log; echo "T1000 exit $?"
 cut -c1-200 gpurun_out/bench_T1000.json

@@ -78,11 +78,12 @@ def conv_metrics():
     cls = collections.defaultdict(lambda: [0, 0.0, 0.0])
     with open(os.path.join(P, f"{TAG}_ncu_conv_launch_metrics.txt"), "w") as f:
         f.write("# every sparse-convolution launch of one denoising step (schedule position 0), in launch order\n"
-                "#  id kernel                          time[us]  tensor-pipe%  L2->SM[TB/s]  DRAM read[MB]  write[MB]  L2 hit%\n")
+                "# (tensor-pipe activity is a --set full metric: see <tag>_ncu_pair_l3_full_summary.txt; n/a in this metrics-only pass)\n"
+                "#  id kernel                          time[us]  L2->SM[TB/s]  DRAM read[MB]  write[MB]  L2 hit%\n")
         for k, v in per.items():
             tens = [x for kk, x in v.items() if "pipe_tensor_cycles_active" in kk]
             dr, dw = v.get("dram__bytes_read.sum", 0) / 1e6, v.get("dram__bytes_write.sum", 0) / 1e6
-            f.write(f"{k:4d} {short(v['name']):30s} {v.get('gpu__time_duration.sum', 0):9.1f}  {tens[0] if tens else float('nan'):10.1f}  "
+            f.write(f"{k:4d} {short(v['name']):30s} {v.get('gpu__time_duration.sum', 0):9.1f}  "
                     f"{v.get('l1tex__m_xbar2l1tex_read_bytes.sum.per_second', 0):11.2f}  {dr:12.1f}  {dw:9.1f}  {v.get('lts__t_sector_hit_rate.pct', 0):6.1f}\n")
             c = cls[short(v["name"])]
             c[0] += 1
