@@ -25,8 +25,7 @@ constexpr int NCOLS = 256;
 constexpr int MAX_KVOL = 27;
 constexpr int NA = 4;                                 // A slots (half stages, 32 K-columns each)
 constexpr int NB = 2;                                 // B slots (64 K-columns each)
-constexpr int SLAB_COLS = 16;
-constexpr int SLAB_PITCH = SLAB_COLS + 4;             // floats per slab row
+constexpr int SLAB_PITCH = tc::EPI_PITCH;             // floats per slab row
 constexpr int SLAB_BYTES = 8 * 32 * SLAB_PITCH * 4;   // 8 drain warps x 32 rows
 constexpr int META = 4;                               // ring of per-tile metadata (row ids, offset masks).  Must exceed the cp.async
                                                       // lookahead A_LAG: a tile's last full_a arrival is issued up to A_LAG
@@ -341,55 +340,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_n256(const Params p) {
                 mbar_arrive(acc_empty(buf));                       // accumulator free again: the MMA warp runs on while we finish
                 ++gcount;
             }
-            // ---- epilogue from registers, 16 channels at a time through the warp's slab (coalesced global accesses) ----
-            const int lc4 = (lane & 3) * 4;
-#pragma unroll 1
-            for (int cs = 0; cs < 8; ++cs) {                 // run-time loop: one copy of the global-memory code (see slab_write_switch)
-                __syncwarp();
-                slab_write_switch<128>(cs, tot, myslab + lane * SLAB_PITCH, out_scale);
-                __syncwarp();
-                const int col = cb + cs * 16 + lc4;
-                float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f), h4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (p.scale) { s4 = __ldg(reinterpret_cast<const float4*>(p.scale + col)); h4 = __ldg(reinterpret_cast<const float4*>(p.shift + col)); }
-#pragma unroll
-                for (int i0 = 0; i0 < 4; i0 += 2) {                 // two rows per batch: loads first, then math + stores
-                    float4 pre[2], res[2], gat[2];
-#pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        const int i = i0 + u;
-                        pre[u] = make_float4(0.f, 0.f, 0.f, 0.f); res[u] = pre[u]; gat[u] = make_float4(1.f, 1.f, 1.f, 1.f);
-                        if (orows[i] >= 0) {
-                            const long long ro = (long long)orows[i] * NCOLS + col;
-                            if (io.pre_add) pre[u] = __ldg(reinterpret_cast<const float4*>(io.pre_add + ro));
-                            res[u] = load_residual4(io.residual, io.residual_h, orows[i], NCOLS, col);
-                            if (io.gate_table) gat[u] = __ldg(reinterpret_cast<const float4*>(io.gate_table + (long long)gidx[i] * NCOLS + col));
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        const int i = i0 + u;
-                        const int orow = orows[i];
-                        if (orow < 0) continue;
-                        const int rr = (lane >> 2) + 8 * i;
-                        const long long ro = (long long)orow * NCOLS + col;
-                        const float4 a4 = *reinterpret_cast<const float4*>(myslab + rr * SLAB_PITCH + lc4);
-                        float y[4] = {a4.x + pre[u].x, a4.y + pre[u].y, a4.z + pre[u].z, a4.w + pre[u].w};
-                        y[0] = fmaf(y[0], s4.x, h4.x) + res[u].x; y[1] = fmaf(y[1], s4.y, h4.y) + res[u].y;
-                        y[2] = fmaf(y[2], s4.z, h4.z) + res[u].z; y[3] = fmaf(y[3], s4.w, h4.w) + res[u].w;
-                        if (p.relu) {
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) y[q] = fmaxf(y[q], 0.f);
-                        }
-                        if (io.out) store_f4(io.out + ro, y, p.cs);
-                        if (io.out_h) store_split4(io.out_h, orow, NCOLS, col, y, p.cs);
-                        if (io.out_gated || io.out_gated_h) {
-                            y[0] *= gat[u].x; y[1] *= gat[u].y; y[2] *= gat[u].z; y[3] *= gat[u].w;
-                            if (io.out_gated) store_f4(io.out_gated + ro, y, p.cs);
-                            if (io.out_gated_h) store_split4(io.out_gated_h, orow, NCOLS, col, y, p.cs);
-                        }
-                    }
-                }
-            }
+            // ---- epilogue from registers, 16 channels at a time through the warp's slab (tc_common.cuh: epilogue_slabs) ----
+            epilogue_slabs<128, 2>(tot, myslab, lane, orows, gidx, cb, NCOLS, out_scale, epi_flags(io, p.scale, p.relu, p.cs), io, p.scale, p.shift);
             mbar_arrive(meta_empty(b));
         }
     }
@@ -407,6 +359,7 @@ static size_t smem_bytes() {
 
 bool lb2_spconv_tc3_supported(const lb2_conv_desc* d) {
     if (d->cout != 256) return false;
+    if ((long long)d->mout_cap * 2 * d->cout >= (1LL << 32)) return false;   // the epilogue indexes rows with 32-bit element offsets
     for (int p = 0; p < d->npass; ++p) {
         if (!d->io[p].in1_h) return false;
         if (d->c2 > 0 && !d->io[p].in2_h) return false;

@@ -28,7 +28,7 @@ __host__ __device__ constexpr int na_of(int ncc) { return ncc <= 3 ? 6 : 4; }   
                                                       // smaller weight slots leave room for a deeper gather ring
 constexpr int NB = 3;                                 // weight slots (64 K-columns each)
 constexpr int NACC = 4;                               // TMEM accumulators
-constexpr int SLAB_PITCH = 20;                        // floats per slab row (16 + 4: conflict-free 16-byte accesses)
+constexpr int SLAB_PITCH = tc::EPI_PITCH;             // floats per slab row
 constexpr int SLAB_BYTES = 8 * 32 * SLAB_PITCH * 4;   // 8 drain warps x 32 rows
 constexpr int META = 4;                               // ring of per-tile metadata; must exceed the gather lookahead in tiles (<= 1)
 constexpr int NBAR = 2 * NA_MAX + 2 * NB + 2 * NACC + 2 * META;
@@ -340,22 +340,19 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_small(const Params p) 
                 continue;
             }
             const int* rows = row_s + b * BM + q4 * 32;             // this warp's 32 output rows
-            int* grow = gate_s + (warp - 8) * 32;                   // ... and their gate-table rows (kept in shared memory: registers hold the totals)
-            {
-                const int r = rows[lane];
-                __syncwarp();
-                grow[lane] = (io.gate_table && io.gate_idx && r >= 0) ? __ldg(io.gate_idx + r) : 0;
-                __syncwarp();
+            int orows[4], gidx[4];                                  // the 4 rows this lane serves in the epilogue, their gate-table rows
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                orows[i] = rows[(lane >> 2) + 8 * i];
+                gidx[i] = (io.gate_table && io.gate_idx && orows[i] >= 0) ? __ldg(io.gate_idx + orows[i]) : 0;
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {                          // this lane's 4 epilogue rows: L2 prefetch of their operands
-                const int rr = (lane >> 2) + 8 * u;
-                const int orow = rows[rr];
-                if (orow < 0) continue;
-                prefetch_row_f32(io.residual, orow, p.cout, cb, TOT, lane & 3);
-                if (!io.residual) prefetch_row_split(io.residual_h, orow, p.cout, cb, TOT, lane & 3);
-                prefetch_row_f32(io.pre_add, orow, p.cout, cb, TOT, lane & 3);
-                if (io.gate_table && io.gate_idx) prefetch_row_f32(io.gate_table, grow[rr], p.cout, cb, TOT, lane & 3);
+            for (int i = 0; i < 4; ++i) {                           // L2 prefetch of the epilogue operands of this lane's 4 rows
+                if (orows[i] < 0) continue;
+                prefetch_row_f32(io.residual, orows[i], p.cout, cb, TOT, lane & 3);
+                if (!io.residual) prefetch_row_split(io.residual_h, orows[i], p.cout, cb, TOT, lane & 3);
+                prefetch_row_f32(io.pre_add, orows[i], p.cout, cb, TOT, lane & 3);
+                if (io.gate_table && io.gate_idx) prefetch_row_f32(io.gate_table, gidx[i], p.cout, cb, TOT, lane & 3);
             }
             if (n_groups == 0) {
 #pragma unroll
@@ -382,63 +379,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_small(const Params p) 
                 mbar_arrive(acc_empty(buf));                       // accumulator free again: the MMA warp runs on while we finish
                 ++gcount;
             }
-            // ---- epilogue from registers, 16 channels at a time through the warp's slab (coalesced global accesses) ----
-            const int lc4 = (lane & 3) * 4;
-            // which operands / outputs this pass has: decided once per tile (predicates), not per element
-            const bool has_pre = io.pre_add != nullptr, has_res32 = io.residual != nullptr, has_resh = !has_res32 && io.residual_h != nullptr;
-            const bool has_gate = io.gate_table != nullptr, w_out = io.out != nullptr, w_outh = io.out_h != nullptr;
-            const bool w_g = io.out_gated != nullptr, w_gh = io.out_gated_h != nullptr;
-            const bool cs_st = p.cs != 0, has_aff = p.scale != nullptr, do_relu = p.relu != 0;
-            const int C = p.cout;
-#pragma unroll 1
-            for (int cs = 0; cs < TOT / 16; ++cs) {                 // run-time loop: one copy of the global-memory code (see slab_write_switch)
-                __syncwarp();
-                slab_write_switch<TOT>(cs, tot, myslab + lane * SLAB_PITCH, out_scale);
-                __syncwarp();
-                const int col = cb + cs * 16 + lc4;
-                float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f), h4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (has_aff) { s4 = __ldg(reinterpret_cast<const float4*>(p.scale + col)); h4 = __ldg(reinterpret_cast<const float4*>(p.shift + col)); }
-                constexpr int RB = (TOT >= 64) ? 2 : 4;             // rows per batch (loads first, then math + stores); 2 where the totals fill the registers
-#pragma unroll
-                for (int u0 = 0; u0 < 4; u0 += RB) {
-                    float4 pre[RB], res[RB], gat[RB];
-                    long long ro[RB];                               // element offset of (row, col) in a (rows, C) fp32 tensor; < 0: no row
-#pragma unroll
-                    for (int v = 0; v < RB; ++v) {
-                        const int rr = (lane >> 2) + 8 * (u0 + v);
-                        const int orow = rows[rr];
-                        pre[v] = make_float4(0.f, 0.f, 0.f, 0.f); res[v] = pre[v]; gat[v] = make_float4(1.f, 1.f, 1.f, 1.f);
-                        ro[v] = orow >= 0 ? (long long)orow * C + col : -1;
-                        if (orow >= 0) {
-                            if (has_pre) pre[v] = __ldg(reinterpret_cast<const float4*>(io.pre_add + ro[v]));
-                            if (has_res32) res[v] = __ldg(reinterpret_cast<const float4*>(io.residual + ro[v]));
-                            else if (has_resh) res[v] = load_residual4(nullptr, io.residual_h, orow, C, col);
-                            if (has_gate) gat[v] = __ldg(reinterpret_cast<const float4*>(io.gate_table + (long long)grow[rr] * C + col));
-                        }
-                    }
-#pragma unroll
-                    for (int v = 0; v < RB; ++v) {
-                        if (ro[v] < 0) continue;
-                        const int rr = (lane >> 2) + 8 * (u0 + v);
-                        const float4 a4 = *reinterpret_cast<const float4*>(myslab + rr * SLAB_PITCH + lc4);
-                        float y[4] = {a4.x + pre[v].x, a4.y + pre[v].y, a4.z + pre[v].z, a4.w + pre[v].w};
-                        y[0] = fmaf(y[0], s4.x, h4.x) + res[v].x; y[1] = fmaf(y[1], s4.y, h4.y) + res[v].y;
-                        y[2] = fmaf(y[2], s4.z, h4.z) + res[v].z; y[3] = fmaf(y[3], s4.w, h4.w) + res[v].w;
-                        if (do_relu) {
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) y[q] = fmaxf(y[q], 0.f);
-                        }
-                        const long long roh = 2 * ro[v] - col;       // (row, col) in a (rows, 2C) companion: row * 2C + col
-                        if (w_out) store_f4(io.out + ro[v], y, cs_st);
-                        if (w_outh) store_split4_at(reinterpret_cast<__half*>(io.out_h) + roh, C, y, cs_st);
-                        if (w_g || w_gh) {
-                            y[0] *= gat[v].x; y[1] *= gat[v].y; y[2] *= gat[v].z; y[3] *= gat[v].w;
-                            if (w_g) store_f4(io.out_gated + ro[v], y, cs_st);
-                            if (w_gh) store_split4_at(reinterpret_cast<__half*>(io.out_gated_h) + roh, C, y, cs_st);
-                        }
-                    }
-                }
-            }
+            // ---- epilogue from registers, 16 channels at a time through the warp's slab (tc_common.cuh: epilogue_slabs) ----
+            constexpr int RB = (TOT >= 64) ? 2 : 4;                 // rows per load batch; 2 where the totals fill the registers
+            epilogue_slabs<TOT, RB>(tot, myslab, lane, orows, gidx, cb, p.cout, out_scale, epi_flags(io, p.scale, p.relu, p.cs), io, p.scale, p.shift);
             mbar_arrive(meta_empty(b));
         }
     }
@@ -456,6 +399,7 @@ static size_t smem_bytes(int cout) {
 
 bool lb2_spconv_tc4_supported(const lb2_conv_desc* d) {
     if (d->cout > 128 || d->cout % 32 != 0) return false;
+    if ((long long)d->mout_cap * 2 * d->cout >= (1LL << 32)) return false;   // the epilogue indexes rows with 32-bit element offsets
     if ((d->c1 + d->c2) % 32 != 0 || d->c1 % 32 != 0) return false;          // whole 32-column A slots; a slot never straddles in1/in2
     return tc4::smem_bytes(d->cout) <= 227 * 1024;
 }

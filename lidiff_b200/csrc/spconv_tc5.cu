@@ -30,8 +30,7 @@ using namespace tc;
 
 constexpr int THREADS = 512;
 constexpr int NA = 6;                                 // A slots (128 rows x 32 K-columns, hi + lo image: 16 KB each)
-constexpr int SLAB_COLS = 16;
-constexpr int SLAB_PITCH = SLAB_COLS + 4;             // floats per slab row
+constexpr int SLAB_PITCH = tc::EPI_PITCH;             // floats per slab row
 constexpr int SLAB_BYTES = 8 * 32 * SLAB_PITCH * 4;   // 8 drain warps x 32 rows
 constexpr int META = 4;                               // ring of per-tile metadata (row ids, masks); exceeds the gather lookahead in tiles
 
@@ -417,60 +416,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_spconv
                 if (lane == 0) mbar_arrive_cluster(leader_acc_empty0 + 8u * buf);   // accumulator free again: the MMA warp runs on while we finish
                 ++gcount;
             }
-            // ---- epilogue from registers, 16 channels at a time through the warp's slab (coalesced global accesses) ----
-            const int lc4 = (lane & 3) * 4;
-            // which operands / outputs this pass has: decided once per tile (predicates), not per element
-            const bool has_pre = io.pre_add != nullptr, has_res32 = io.residual != nullptr, has_resh = !has_res32 && io.residual_h != nullptr;
-            const bool has_gate = io.gate_table != nullptr, w_out = io.out != nullptr, w_outh = io.out_h != nullptr;
-            const bool w_g = io.out_gated != nullptr, w_gh = io.out_gated_h != nullptr;
-            const bool cs_st = p.cs != 0, has_aff = p.scale != nullptr, do_relu = p.relu != 0;
-#pragma unroll 1
-            for (int cs = 0; cs < TOT / 16; ++cs) {                 // run-time loop: one copy of the global-memory code (see slab_write_switch)
-                __syncwarp();
-                slab_write_switch<TOT>(cs, tot, myslab + lane * SLAB_PITCH, out_scale);
-                __syncwarp();
-                const int col = cb + cs * 16 + lc4;
-                float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f), h4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (has_aff) { s4 = __ldg(reinterpret_cast<const float4*>(p.scale + col)); h4 = __ldg(reinterpret_cast<const float4*>(p.shift + col)); }
-#pragma unroll
-                for (int i0 = 0; i0 < 4; i0 += 2) {                 // two rows per batch: loads first, then math + stores
-                    float4 pre[2], res[2], gat[2];
-                    long long ro[2];                                // element offset of (row, col) in a (rows, NCOLS) fp32 tensor; < 0: no row
-#pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        const int i = i0 + u;
-                        pre[u] = make_float4(0.f, 0.f, 0.f, 0.f); res[u] = pre[u]; gat[u] = make_float4(1.f, 1.f, 1.f, 1.f);
-                        ro[u] = orows[i] >= 0 ? (long long)orows[i] * NCOLS + col : -1;
-                        if (orows[i] >= 0) {
-                            if (has_pre) pre[u] = __ldg(reinterpret_cast<const float4*>(io.pre_add + ro[u]));
-                            if (has_res32) res[u] = __ldg(reinterpret_cast<const float4*>(io.residual + ro[u]));
-                            else if (has_resh) res[u] = load_residual4(nullptr, io.residual_h, orows[i], NCOLS, col);
-                            if (has_gate) gat[u] = __ldg(reinterpret_cast<const float4*>(io.gate_table + (long long)gidx[i] * NCOLS + col));
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        if (ro[u] < 0) continue;
-                        const int rr = (lane >> 2) + 8 * (i0 + u);
-                        const float4 a4 = *reinterpret_cast<const float4*>(myslab + rr * SLAB_PITCH + lc4);
-                        float y[4] = {a4.x + pre[u].x, a4.y + pre[u].y, a4.z + pre[u].z, a4.w + pre[u].w};
-                        y[0] = fmaf(y[0], s4.x, h4.x) + res[u].x; y[1] = fmaf(y[1], s4.y, h4.y) + res[u].y;
-                        y[2] = fmaf(y[2], s4.z, h4.z) + res[u].z; y[3] = fmaf(y[3], s4.w, h4.w) + res[u].w;
-                        if (do_relu) {
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) y[q] = fmaxf(y[q], 0.f);
-                        }
-                        const long long roh = 2 * ro[u] - col;       // (row, col) in a (rows, 2 NCOLS) companion
-                        if (w_out) store_f4(io.out + ro[u], y, cs_st);
-                        if (w_outh) store_split4_at(reinterpret_cast<__half*>(io.out_h) + roh, NCOLS, y, cs_st);
-                        if (w_g || w_gh) {
-                            y[0] *= gat[u].x; y[1] *= gat[u].y; y[2] *= gat[u].z; y[3] *= gat[u].w;
-                            if (w_g) store_f4(io.out_gated + ro[u], y, cs_st);
-                            if (w_gh) store_split4_at(reinterpret_cast<__half*>(io.out_gated_h) + roh, NCOLS, y, cs_st);
-                        }
-                    }
-                }
-            }
+            // ---- epilogue from registers, 16 channels at a time through the warp's slab (tc_common.cuh: epilogue_slabs) ----
+            epilogue_slabs<TOT, 2>(tot, myslab, lane, orows, gidx, cb, NCOLS, out_scale, epi_flags(io, p.scale, p.relu, p.cs), io, p.scale, p.shift);
             mbar_arrive(meta_empty(b));
         }
     }
@@ -483,6 +430,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_spconv
 
 bool lb2_spconv_tc5_supported(const lb2_conv_desc* d) {
     if (d->cout != 256 && d->cout != 128) return false;
+    if ((long long)d->mout_cap * 2 * d->cout >= (1LL << 32)) return false;   // the epilogue indexes rows with 32-bit element offsets
     if (d->nbr != nullptr && d->row_mask == nullptr) return false;           // the pair's offset union is built from the callers' row masks
     if (d->kvol > 27) return false;
     for (int p = 0; p < d->npass; ++p) {

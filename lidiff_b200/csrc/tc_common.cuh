@@ -210,6 +210,108 @@ __device__ __forceinline__ void slab_write_switch(int cs, const float (&tot)[TOT
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// The epilogue of the register-total kernels (k_spconv_tc_small / _n256 / _pair), shared so every kernel rounds identically:
+//   y = ((acc * out_scale + pre_add) * bn_scale + bn_shift + residual), ReLU, then y and / or y * gate, each as fp32 and / or split.
+// A drain warp holds TOT channels of its 32 rows (lane = row) and hands them to the memory system 16 channels at a time through its
+// staging slab, where lane l serves channels 4 (l & 3) .. +3 of rows (l >> 2) + 8 u, u = 0..3: 64 contiguous bytes per row and store.
+// What a pass reads and writes is folded into one flag word per tile; a slab iteration only executes the loads / adds / stores whose
+// flag is set (the common layer has none of the optional operands and one output form).  Offsets are 32-bit element indices: the
+// launchers refuse rows * 2 * Cout >= 2^32.
+// ---------------------------------------------------------------------------------------------------
+constexpr int EPI_PITCH = 20;                         // floats per slab row (16 + 4: conflict-free 16-byte accesses)
+enum : unsigned { EP_PRE = 1u, EP_RES32 = 2u, EP_RESH = 4u, EP_GATE = 8u, EP_OUT = 16u, EP_OUTH = 32u, EP_G = 64u, EP_GH = 128u,
+                  EP_AFF = 256u, EP_RELU = 512u, EP_CS = 1024u };
+__device__ __forceinline__ unsigned epi_flags(const lb2_conv_io& io, const float* scale, int relu, int cs) {
+    unsigned f = 0;
+    if (io.pre_add) f |= EP_PRE;
+    if (io.residual) f |= EP_RES32; else if (io.residual_h) f |= EP_RESH;
+    if (io.out) f |= EP_OUT;
+    if (io.out_h) f |= EP_OUTH;
+    if (io.out_gated) f |= EP_G;
+    if (io.out_gated_h) f |= EP_GH;
+    if (io.gate_table && (f & (EP_G | EP_GH))) f |= EP_GATE;
+    if (scale) f |= EP_AFF;
+    if (relu) f |= EP_RELU;
+    if (cs) f |= EP_CS;
+    return f;
+}
+__device__ __forceinline__ float4 load_split4_at(const __half* rp, int c) {     // hi + lo of 4 consecutive channels of a companion row
+    const uint2 uh = __ldg(reinterpret_cast<const uint2*>(rp)), ul = __ldg(reinterpret_cast<const uint2*>(rp + c));
+    const float2 h0 = __half22float2(*reinterpret_cast<const __half2*>(&uh.x)), h1 = __half22float2(*reinterpret_cast<const __half2*>(&uh.y));
+    const float2 l0 = __half22float2(*reinterpret_cast<const __half2*>(&ul.x)), l1 = __half22float2(*reinterpret_cast<const __half2*>(&ul.y));
+    return make_float4(h0.x + l0.x, h0.y + l0.y, h1.x + l1.x, h1.y + l1.y);
+}
+// tot: this lane's row, channels [cb, cb + TOT) of C; orow / grow: output row and gate-table row of the 4 rows this lane serves
+// (orow < 0: no row).  RB = rows whose loads are in flight together (2 where the totals fill the registers).
+template <int TOT, int RB>
+__device__ __forceinline__ void epilogue_slabs(const float (&tot)[TOT], float* myslab, int lane, const int (&orow)[4], const int (&grow)[4],
+                                               int cb, int C, float out_scale, unsigned fl, const lb2_conv_io& io,
+                                               const float* __restrict__ scale, const float* __restrict__ shift) {
+    const int lc4 = (lane & 3) * 4;
+    const float* srd = myslab + (lane >> 2) * EPI_PITCH + lc4;
+    const bool cs_st = (fl & EP_CS) != 0;
+#pragma unroll 1
+    for (int cs = 0; cs < TOT / 16; ++cs) {                    // run-time loop: one copy of the global-memory code (see slab_write_switch)
+        __syncwarp();
+        slab_write_switch<TOT>(cs, tot, myslab + lane * EPI_PITCH, out_scale);
+        __syncwarp();
+        const unsigned col = (unsigned)(cb + cs * 16 + lc4);
+        float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f), h4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (fl & EP_AFF) { s4 = __ldg(reinterpret_cast<const float4*>(scale + col)); h4 = __ldg(reinterpret_cast<const float4*>(shift + col)); }
+#pragma unroll
+        for (int u0 = 0; u0 < 4; u0 += RB) {                   // loads of RB rows first, then math + stores
+            float4 pre[RB], res[RB], gat[RB];
+            if (fl & EP_PRE) {
+#pragma unroll
+                for (int v = 0; v < RB; ++v)
+                    pre[v] = orow[u0 + v] >= 0 ? __ldg(reinterpret_cast<const float4*>(io.pre_add + ((unsigned)orow[u0 + v] * (unsigned)C + col)))
+                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (fl & EP_RES32) {
+#pragma unroll
+                for (int v = 0; v < RB; ++v)
+                    res[v] = orow[u0 + v] >= 0 ? __ldg(reinterpret_cast<const float4*>(io.residual + ((unsigned)orow[u0 + v] * (unsigned)C + col)))
+                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+            } else if (fl & EP_RESH) {
+#pragma unroll
+                for (int v = 0; v < RB; ++v)
+                    res[v] = orow[u0 + v] >= 0 ? load_split4_at(reinterpret_cast<const __half*>(io.residual_h) + ((unsigned)orow[u0 + v] * (unsigned)(2 * C) + col), C)
+                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (fl & EP_GATE) {
+#pragma unroll
+                for (int v = 0; v < RB; ++v)
+                    gat[v] = orow[u0 + v] >= 0 ? __ldg(reinterpret_cast<const float4*>(io.gate_table + ((unsigned)grow[u0 + v] * (unsigned)C + col)))
+                                               : make_float4(1.f, 1.f, 1.f, 1.f);
+            }
+#pragma unroll
+            for (int v = 0; v < RB; ++v) {
+                const int u = u0 + v;
+                if (orow[u] < 0) continue;
+                const float4 a4 = *reinterpret_cast<const float4*>(srd + 8 * u * EPI_PITCH);
+                float y[4] = {a4.x, a4.y, a4.z, a4.w};
+                if (fl & EP_PRE) { y[0] += pre[v].x; y[1] += pre[v].y; y[2] += pre[v].z; y[3] += pre[v].w; }
+                y[0] = fmaf(y[0], s4.x, h4.x); y[1] = fmaf(y[1], s4.y, h4.y); y[2] = fmaf(y[2], s4.z, h4.z); y[3] = fmaf(y[3], s4.w, h4.w);
+                if (fl & (EP_RES32 | EP_RESH)) { y[0] += res[v].x; y[1] += res[v].y; y[2] += res[v].z; y[3] += res[v].w; }
+                if (fl & EP_RELU) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) y[q] = fmaxf(y[q], 0.f);
+                }
+                const unsigned e = (unsigned)orow[u] * (unsigned)C + col;          // (row, col) of a (rows, C) fp32 tensor
+                const unsigned eh = e + (unsigned)orow[u] * (unsigned)C;           // (row, col) of a (rows, 2C) companion: hi halfs, lo at + C
+                if (fl & EP_OUT) store_f4(io.out + e, y, cs_st);
+                if (fl & EP_OUTH) store_split4_at(reinterpret_cast<__half*>(io.out_h) + eh, C, y, cs_st);
+                if (fl & (EP_G | EP_GH)) {
+                    if (fl & EP_GATE) { y[0] *= gat[v].x; y[1] *= gat[v].y; y[2] *= gat[v].z; y[3] *= gat[v].w; }
+                    if (fl & EP_G) store_f4(io.out_gated + e, y, cs_st);
+                    if (fl & EP_GH) store_split4_at(reinterpret_cast<__half*>(io.out_gated_h) + eh, C, y, cs_st);
+                }
+            }
+        }
+    }
+}
+
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
