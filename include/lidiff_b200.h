@@ -53,9 +53,7 @@ int64_t     lb2_launch_count(void* handle);
 #define LB2_OPT_TC_PERSISTENT 3   /* persistent kernels for LB2_ALGO_TC (default 1; 0 = one CTA per tile) */
 #define LB2_OPT_TC_FULL_LAG   4   /* generic persistent kernel: S-1 gather lookahead (default 0) */
 #define LB2_OPT_TC_NSPLIT     5   /* per-tile kernel: split Cout 256 over two CTAs (default 0) */
-#define LB2_OPT_STREAM_STORES 6   /* conv epilogues store with the evict-first policy (st.global.cs): outputs stream through L2 instead of
-                                     displacing the feature rows the gathers re-read (default 1) */
-#define LB2_OPT_COUNT         7
+#define LB2_OPT_COUNT         6
 int         lb2_set_option(void* handle, int option, int value);
 int         lb2_get_option(void* handle, int option);   /* value, or a negative LB2_ERR_* */
 /* synchronising read-and-clear of the device status word; bit0 = a coordinate fell outside the key

@@ -15,7 +15,7 @@ import torch
 _SO = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_C", "liblidiff_b200.so")
 
 ALGO_AUTO, ALGO_FFMA, ALGO_TC, ALGO_TC_TILE = 0, 1, 2, 3
-OPT_TC_PAIR, OPT_TC_N256, OPT_TC_SMALL, OPT_TC_PERSISTENT, OPT_TC_FULL_LAG, OPT_TC_NSPLIT, OPT_STREAM_STORES = range(7)
+OPT_TC_PAIR, OPT_TC_N256, OPT_TC_SMALL, OPT_TC_PERSISTENT, OPT_TC_FULL_LAG, OPT_TC_NSPLIT = range(6)
 
 
 class Grid(C.Structure):

@@ -34,7 +34,6 @@ extern "C" int lb2_create(int device, void** handle) {
         const char* lag = getenv("LB2_TC_LAG");
         h->opt[LB2_OPT_TC_FULL_LAG] = (lag && lag[0] == 'f') ? 1 : 0;
         h->opt[LB2_OPT_TC_NSPLIT] = env("LB2_TC_NSPLIT", 0);
-        h->opt[LB2_OPT_STREAM_STORES] = env("LB2_STREAM_STORES", 1);
     }
     if (cudaMalloc(&h->d_status, sizeof(int32_t)) != cudaSuccess) { delete h; return LB2_ERR_CUDA; }
     cudaMemset(h->d_status, 0, sizeof(int32_t));

@@ -45,7 +45,6 @@ struct Params {
     const int* row_perm;
     const unsigned* row_mask;
     int nchunks, group, npass;
-    int cs;                     // evict-first epilogue stores
     lb2_conv_io io[2];
 };
 
@@ -341,7 +340,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_n256(const Params p) {
                 ++gcount;
             }
             // ---- epilogue from registers, 16 channels at a time through the warp's slab (tc_common.cuh: epilogue_slabs) ----
-            epilogue_slabs<128, 2>(tot, myslab, lane, orows, gidx, cb, NCOLS, out_scale, epi_flags(io, p.scale, p.relu, p.cs), io, p.scale, p.shift);
+            epilogue_slabs<128, 2>(tot, myslab, lane, orows, gidx, cb, NCOLS, out_scale, epi_flags(io, p.scale, p.relu), io, p.scale, p.shift);
             mbar_arrive(meta_empty(b));
         }
     }
@@ -378,7 +377,6 @@ int lb2_spconv_tc3_launch(Lb2Handle* h, cudaStream_t s, const lb2_conv_desc* d, 
     const int steps_per_offset = 3 * ((d->c1 + d->c2 + 15) / 16);
     p.group = std::max(1, step_budget / steps_per_offset);
     p.io[0] = d->io[0]; p.io[1] = d->io[d->npass > 1 ? 1 : 0];
-    p.cs = h->opt[LB2_OPT_STREAM_STORES] ? 1 : 0;
     const size_t smem = tc3::smem_bytes();
     {
         cudaError_t e = lb2_configure_smem(h, LB2_K_TC3, tc3::k_spconv_tc_n256, (int)(227 * 1024));

@@ -46,7 +46,6 @@ struct Params {
     const int* row_perm;
     const unsigned* row_mask;
     int nchunks, nhalf, tmem_cols, group, acc_stride, npass;
-    int cs;                     // evict-first epilogue stores
     const int* tile_order;      // tiles by descending cost (lb2_tile_order) or NULL
     lb2_conv_io io[2];
 };
@@ -381,7 +380,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_small(const Params p) 
             }
             // ---- epilogue from registers, 16 channels at a time through the warp's slab (tc_common.cuh: epilogue_slabs) ----
             constexpr int RB = (TOT >= 64) ? 2 : 4;                 // rows per load batch; 2 where the totals fill the registers
-            epilogue_slabs<TOT, RB>(tot, myslab, lane, orows, gidx, cb, p.cout, out_scale, epi_flags(io, p.scale, p.relu, p.cs), io, p.scale, p.shift);
+            epilogue_slabs<TOT, RB>(tot, myslab, lane, orows, gidx, cb, p.cout, out_scale, epi_flags(io, p.scale, p.relu), io, p.scale, p.shift);
             mbar_arrive(meta_empty(b));
         }
     }
@@ -417,7 +416,6 @@ int lb2_spconv_tc4_launch(Lb2Handle* h, cudaStream_t s, const lb2_conv_desc* d, 
     const int steps_per_offset = 3 * ((d->c1 + d->c2 + 15) / 16);
     p.group = std::max(1, step_budget / steps_per_offset);
     p.io[0] = d->io[0]; p.io[1] = d->io[d->npass > 1 ? 1 : 0];
-    p.cs = h->opt[LB2_OPT_STREAM_STORES] ? 1 : 0;
     p.tile_order = d->tile_order128;
     const size_t smem = tc4::smem_bytes(d->cout);
     if (!(h->configured & (1u << LB2_K_TC4))) {

@@ -57,7 +57,6 @@ struct Params {
     const int* row_perm;
     const unsigned* row_mask;
     int nchunks, group, npass;
-    int cs;                     // evict-first epilogue stores
     const int* tile_order;      // tiles by descending cost (lb2_tile_order) or NULL
     lb2_conv_io io[2];
 };
@@ -417,7 +416,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_spconv
                 ++gcount;
             }
             // ---- epilogue from registers, 16 channels at a time through the warp's slab (tc_common.cuh: epilogue_slabs) ----
-            epilogue_slabs<TOT, 2>(tot, myslab, lane, orows, gidx, cb, NCOLS, out_scale, epi_flags(io, p.scale, p.relu, p.cs), io, p.scale, p.shift);
+            epilogue_slabs<TOT, 2>(tot, myslab, lane, orows, gidx, cb, NCOLS, out_scale, epi_flags(io, p.scale, p.relu), io, p.scale, p.shift);
             mbar_arrive(meta_empty(b));
         }
     }
@@ -466,7 +465,6 @@ int lb2_spconv_tc5_launch(Lb2Handle* h, cudaStream_t s, const lb2_conv_desc* d, 
     const int steps_per_offset = 3 * ((d->c1 + d->c2 + 15) / 16);
     p.group = std::max(1, step_budget / steps_per_offset);
     p.io[0] = d->io[0]; p.io[1] = d->io[d->npass > 1 ? 1 : 0];
-    p.cs = h->opt[LB2_OPT_STREAM_STORES] ? 1 : 0;
     p.tile_order = d->tile_order256;
     return d->cout == 256 ? launch_pair<256>(h, s, p, d->mout_cap, d->npass) : launch_pair<128>(h, s, p, d->mout_cap, d->npass);
 }

@@ -101,16 +101,18 @@ __device__ __forceinline__ uint32_t sw128(int row, int chunk) {
     return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4));
 }
 
-// two fp32 -> packed (hi, hi) and (lo, lo) fp16 pairs, saturating at the fp16 range; packed converts (F2FP) round each
-// half independently to nearest-even, i.e. the results equal the scalar split1 below bit for bit
+// two fp32 -> packed (hi, hi) and (lo, lo) fp16 pairs.  F2FP.SATFINITE rounds each half independently to nearest-even and clamps to
+// +-65504 instead of producing inf, so inside the fp16 range the results equal the scalar split1 below bit for bit (beyond it hi
+// saturates and lo carries what it can of the rest)
+__device__ __forceinline__ uint32_t cvt_f16x2_sat(float lo_half, float hi_half) {
+    uint32_t d;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi_half), "f"(lo_half));
+    return d;
+}
 __device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-    x0 = fminf(fmaxf(x0, -65504.f), 65504.f);
-    x1 = fminf(fmaxf(x1, -65504.f), 65504.f);
-    const __half2 h = __floats2half2_rn(x0, x1);
-    const float2 f = __half22float2(h);
-    const __half2 l = __floats2half2_rn(x0 - f.x, x1 - f.y);
-    hi = *reinterpret_cast<const uint32_t*>(&h);
-    lo = *reinterpret_cast<const uint32_t*>(&l);
+    hi = cvt_f16x2_sat(x0, x1);
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+    lo = cvt_f16x2_sat(x0 - f.x, x1 - f.y);
 }
 __device__ __forceinline__ void split8(const float4& a, const float4& b, uint4& hi, uint4& lo) {
     split2(a.x, a.y, hi.x, lo.x);
@@ -126,38 +128,26 @@ __device__ __forceinline__ void split1(float x, __half& hi, __half& lo) {
     hi = __float2half_rn(x);
     lo = __float2half_rn(x - __half2float(hi));
 }
-// write 4 consecutive channels of a split companion row: hi halfs at row[col], lo halfs at row[c + col].
-// cs: evict-first stores (st.global.cs) — an epilogue's output streams through L2 instead of displacing gathered input rows
-__device__ __forceinline__ void store_split4(void* base, long long row, int c, int col, const float (&y)[4], bool cs = false) {
+// write 4 consecutive channels of a split companion row: hi halfs at row[col], lo halfs at row[c + col]
+__device__ __forceinline__ void store_split4(void* base, long long row, int c, int col, const float (&y)[4]) {
     __half* rp = reinterpret_cast<__half*>(base) + row * 2 * c;
     uint2 uh, ul;
     split2(y[0], y[1], uh.x, ul.x);
     split2(y[2], y[3], uh.y, ul.y);
-    if (cs) {
-        __stcs(reinterpret_cast<uint2*>(rp + col), uh);
-        __stcs(reinterpret_cast<uint2*>(rp + c + col), ul);
-    } else {
-        *reinterpret_cast<uint2*>(rp + col) = uh;
-        *reinterpret_cast<uint2*>(rp + c + col) = ul;
-    }
+    *reinterpret_cast<uint2*>(rp + col) = uh;
+    *reinterpret_cast<uint2*>(rp + c + col) = ul;
 }
-// same, to a precomputed position (rp = row start + column, in halfs; c = channels of the tensor)
-__device__ __forceinline__ void store_split4_at(__half* rp, int c, const float (&y)[4], bool cs) {
+// write 4 consecutive channels of a split companion row: hi halfs at rp, lo halfs at rp + c (rp = row start + column, in halfs;
+// c = channels of the tensor).  Epilogue stores are evict-first (st.global.cs): an output streams through L2 instead of displacing
+// the feature rows the gathers re-read
+__device__ __forceinline__ void store_split4_at(__half* rp, int c, const float (&y)[4]) {
     uint2 uh, ul;
     split2(y[0], y[1], uh.x, ul.x);
     split2(y[2], y[3], uh.y, ul.y);
-    if (cs) {
-        __stcs(reinterpret_cast<uint2*>(rp), uh);
-        __stcs(reinterpret_cast<uint2*>(rp + c), ul);
-    } else {
-        *reinterpret_cast<uint2*>(rp) = uh;
-        *reinterpret_cast<uint2*>(rp + c) = ul;
-    }
+    __stcs(reinterpret_cast<uint2*>(rp), uh);
+    __stcs(reinterpret_cast<uint2*>(rp + c), ul);
 }
-__device__ __forceinline__ void store_f4(float* p, const float (&y)[4], bool cs) {
-    const float4 v = make_float4(y[0], y[1], y[2], y[3]);
-    if (cs) __stcs(reinterpret_cast<float4*>(p), v); else *reinterpret_cast<float4*>(p) = v;
-}
+__device__ __forceinline__ void store_f4(float* p, const float (&y)[4]) { __stcs(reinterpret_cast<float4*>(p), make_float4(y[0], y[1], y[2], y[3])); }
 
 // Ask L2 for the 128-byte lines of the epilogue operands of one output row (channels [c0, c0 + n) of a (rows, c) tensor): issued by
 // the drain warps when a tile's rows are known, long before the accumulator they belong to is complete, so the epilogue's loads hit L2
@@ -221,8 +211,8 @@ __device__ __forceinline__ void slab_write_switch(int cs, const float (&tot)[TOT
 // ---------------------------------------------------------------------------------------------------
 constexpr int EPI_PITCH = 20;                         // floats per slab row (16 + 4: conflict-free 16-byte accesses)
 enum : unsigned { EP_PRE = 1u, EP_RES32 = 2u, EP_RESH = 4u, EP_GATE = 8u, EP_OUT = 16u, EP_OUTH = 32u, EP_G = 64u, EP_GH = 128u,
-                  EP_AFF = 256u, EP_RELU = 512u, EP_CS = 1024u };
-__device__ __forceinline__ unsigned epi_flags(const lb2_conv_io& io, const float* scale, int relu, int cs) {
+                  EP_AFF = 256u, EP_RELU = 512u, EP_OPERANDS = EP_PRE | EP_RES32 | EP_RESH | EP_GATE };
+__device__ __forceinline__ unsigned epi_flags(const lb2_conv_io& io, const float* scale, int relu) {
     unsigned f = 0;
     if (io.pre_add) f |= EP_PRE;
     if (io.residual) f |= EP_RES32; else if (io.residual_h) f |= EP_RESH;
@@ -233,7 +223,6 @@ __device__ __forceinline__ unsigned epi_flags(const lb2_conv_io& io, const float
     if (io.gate_table && (f & (EP_G | EP_GH))) f |= EP_GATE;
     if (scale) f |= EP_AFF;
     if (relu) f |= EP_RELU;
-    if (cs) f |= EP_CS;
     return f;
 }
 __device__ __forceinline__ float4 load_split4_at(const __half* rp, int c) {     // hi + lo of 4 consecutive channels of a companion row
@@ -242,53 +231,85 @@ __device__ __forceinline__ float4 load_split4_at(const __half* rp, int c) {     
     const float2 l0 = __half22float2(*reinterpret_cast<const __half2*>(&ul.x)), l1 = __half22float2(*reinterpret_cast<const __half2*>(&ul.y));
     return make_float4(h0.x + l0.x, h0.y + l0.y, h1.x + l1.x, h1.y + l1.y);
 }
+// the outputs of one row: y and / or y * gate, each as fp32 (element e of a (rows, C) tensor) and / or split (element eh of (rows, 2C))
+__device__ __forceinline__ void epi_store(float (&y)[4], const float4& gate, unsigned e, unsigned eh, int C, unsigned fl, const lb2_conv_io& io) {
+    if (fl & EP_OUT) store_f4(io.out + e, y);
+    if (fl & EP_OUTH) store_split4_at(reinterpret_cast<__half*>(io.out_h) + eh, C, y);
+    if (fl & (EP_G | EP_GH)) {
+        if (fl & EP_GATE) { y[0] *= gate.x; y[1] *= gate.y; y[2] *= gate.z; y[3] *= gate.w; }
+        if (fl & EP_G) store_f4(io.out_gated + e, y);
+        if (fl & EP_GH) store_split4_at(reinterpret_cast<__half*>(io.out_gated_h) + eh, C, y);
+    }
+}
 // tot: this lane's row, channels [cb, cb + TOT) of C; orow / grow: output row and gate-table row of the 4 rows this lane serves
-// (orow < 0: no row).  RB = rows whose loads are in flight together (2 where the totals fill the registers).
+// (orow < 0: no row).  RB = rows whose operand loads are in flight together (2 where the totals fill the registers).
 template <int TOT, int RB>
 __device__ __forceinline__ void epilogue_slabs(const float (&tot)[TOT], float* myslab, int lane, const int (&orow)[4], const int (&grow)[4],
                                                int cb, int C, float out_scale, unsigned fl, const lb2_conv_io& io,
                                                const float* __restrict__ scale, const float* __restrict__ shift) {
-    const int lc4 = (lane & 3) * 4;
-    const float* srd = myslab + (lane >> 2) * EPI_PITCH + lc4;
-    const bool cs_st = (fl & EP_CS) != 0;
+    constexpr unsigned NOROW = 0xffffffffu;
+    const float* srd = myslab + (lane >> 2) * EPI_PITCH + (lane & 3) * 4;
+    unsigned c0 = (unsigned)(cb + (lane & 3) * 4);                  // this lane's first channel of slab 0
+    unsigned e0[4];                                                 // element offset of (row u, c0) in a (rows, C) tensor
+#pragma unroll
+    for (int u = 0; u < 4; ++u) e0[u] = orow[u] >= 0 ? (unsigned)orow[u] * (unsigned)C + c0 : NOROW;
+    // opaque to the optimiser: under the drain warps' register pressure it otherwise re-derives these from the thread index and the
+    // row (6-10 instructions) in front of every load and store
+    asm volatile("" : "+r"(c0), "+r"(e0[0]), "+r"(e0[1]), "+r"(e0[2]), "+r"(e0[3]));
 #pragma unroll 1
     for (int cs = 0; cs < TOT / 16; ++cs) {                    // run-time loop: one copy of the global-memory code (see slab_write_switch)
         __syncwarp();
         slab_write_switch<TOT>(cs, tot, myslab + lane * EPI_PITCH, out_scale);
         __syncwarp();
-        const unsigned col = (unsigned)(cb + cs * 16 + lc4);
+        const unsigned col = c0 + 16u * (unsigned)cs;
         float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f), h4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (fl & EP_AFF) { s4 = __ldg(reinterpret_cast<const float4*>(scale + col)); h4 = __ldg(reinterpret_cast<const float4*>(shift + col)); }
+        if (!(fl & EP_OPERANDS)) {
+            // ---- the common layer: no pre-add, residual or gate ----
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (e0[u] == NOROW) continue;
+                const float4 a4 = *reinterpret_cast<const float4*>(srd + 8 * u * EPI_PITCH);
+                float y[4] = {fmaf(a4.x, s4.x, h4.x), fmaf(a4.y, s4.y, h4.y), fmaf(a4.z, s4.z, h4.z), fmaf(a4.w, s4.w, h4.w)};
+                if (fl & EP_RELU) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) y[q] = fmaxf(y[q], 0.f);
+                }
+                const unsigned e = e0[u] + 16u * (unsigned)cs;
+                epi_store(y, s4, e, 2u * e - col, C, fl, io);          // no gate on this path (EP_GATE clear): the argument is not read
+            }
+            continue;
+        }
 #pragma unroll
         for (int u0 = 0; u0 < 4; u0 += RB) {                   // loads of RB rows first, then math + stores
             float4 pre[RB], res[RB], gat[RB];
             if (fl & EP_PRE) {
 #pragma unroll
                 for (int v = 0; v < RB; ++v)
-                    pre[v] = orow[u0 + v] >= 0 ? __ldg(reinterpret_cast<const float4*>(io.pre_add + ((unsigned)orow[u0 + v] * (unsigned)C + col)))
-                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+                    pre[v] = e0[u0 + v] != NOROW ? __ldg(reinterpret_cast<const float4*>(io.pre_add + (e0[u0 + v] + 16u * (unsigned)cs)))
+                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
             }
             if (fl & EP_RES32) {
 #pragma unroll
                 for (int v = 0; v < RB; ++v)
-                    res[v] = orow[u0 + v] >= 0 ? __ldg(reinterpret_cast<const float4*>(io.residual + ((unsigned)orow[u0 + v] * (unsigned)C + col)))
-                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+                    res[v] = e0[u0 + v] != NOROW ? __ldg(reinterpret_cast<const float4*>(io.residual + (e0[u0 + v] + 16u * (unsigned)cs)))
+                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
             } else if (fl & EP_RESH) {
 #pragma unroll
                 for (int v = 0; v < RB; ++v)
-                    res[v] = orow[u0 + v] >= 0 ? load_split4_at(reinterpret_cast<const __half*>(io.residual_h) + ((unsigned)orow[u0 + v] * (unsigned)(2 * C) + col), C)
-                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+                    res[v] = e0[u0 + v] != NOROW ? load_split4_at(reinterpret_cast<const __half*>(io.residual_h) + (2u * (e0[u0 + v] + 16u * (unsigned)cs) - col), C)
+                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
             }
             if (fl & EP_GATE) {
 #pragma unroll
                 for (int v = 0; v < RB; ++v)
-                    gat[v] = orow[u0 + v] >= 0 ? __ldg(reinterpret_cast<const float4*>(io.gate_table + ((unsigned)grow[u0 + v] * (unsigned)C + col)))
-                                               : make_float4(1.f, 1.f, 1.f, 1.f);
+                    gat[v] = e0[u0 + v] != NOROW ? __ldg(reinterpret_cast<const float4*>(io.gate_table + ((unsigned)grow[u0 + v] * (unsigned)C + col)))
+                                                 : make_float4(1.f, 1.f, 1.f, 1.f);
             }
 #pragma unroll
             for (int v = 0; v < RB; ++v) {
                 const int u = u0 + v;
-                if (orow[u] < 0) continue;
+                if (e0[u] == NOROW) continue;
                 const float4 a4 = *reinterpret_cast<const float4*>(srd + 8 * u * EPI_PITCH);
                 float y[4] = {a4.x, a4.y, a4.z, a4.w};
                 if (fl & EP_PRE) { y[0] += pre[v].x; y[1] += pre[v].y; y[2] += pre[v].z; y[3] += pre[v].w; }
@@ -298,15 +319,8 @@ __device__ __forceinline__ void epilogue_slabs(const float (&tot)[TOT], float* m
 #pragma unroll
                     for (int q = 0; q < 4; ++q) y[q] = fmaxf(y[q], 0.f);
                 }
-                const unsigned e = (unsigned)orow[u] * (unsigned)C + col;          // (row, col) of a (rows, C) fp32 tensor
-                const unsigned eh = e + (unsigned)orow[u] * (unsigned)C;           // (row, col) of a (rows, 2C) companion: hi halfs, lo at + C
-                if (fl & EP_OUT) store_f4(io.out + e, y, cs_st);
-                if (fl & EP_OUTH) store_split4_at(reinterpret_cast<__half*>(io.out_h) + eh, C, y, cs_st);
-                if (fl & (EP_G | EP_GH)) {
-                    if (fl & EP_GATE) { y[0] *= gat[v].x; y[1] *= gat[v].y; y[2] *= gat[v].z; y[3] *= gat[v].w; }
-                    if (fl & EP_G) store_f4(io.out_gated + e, y, cs_st);
-                    if (fl & EP_GH) store_split4_at(reinterpret_cast<__half*>(io.out_gated_h) + eh, C, y, cs_st);
-                }
+                const unsigned e = e0[u] + 16u * (unsigned)cs;
+                epi_store(y, gat[v], e, 2u * e - col, C, fl, io);
             }
         }
     }
