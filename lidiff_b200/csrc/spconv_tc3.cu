@@ -322,19 +322,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_n256(const Params p) {
                 const int buf = gcount & 1;
                 mbar_wait(acc_full(buf), (gcount >> 1) & 1);
                 tc_fence_after();
-#pragma unroll
-                for (int cc = 0; cc < 4; ++cc) {
-                    uint32_t r[32];
-                    tmem_ld32(tmem_d + lane_base + (uint32_t)(buf * NCOLS + cb + cc * 32), r);
-                    tmem_ld_wait();
-                    if (g == 0) {
-#pragma unroll
-                        for (int q = 0; q < 32; ++q) tot[cc * 32 + q] = __uint_as_float(r[q]);
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < 32; ++q) tot[cc * 32 + q] = __fadd_rn(tot[cc * 32 + q], __uint_as_float(r[q]));
-                    }
-                }
+                drain_acc<128>(tmem_d + lane_base + (uint32_t)(buf * NCOLS + cb), tot, g == 0);
                 tc_fence_before();
                 mbar_arrive(acc_empty(buf));                       // accumulator free again: the MMA warp runs on while we finish
                 ++gcount;

@@ -345,13 +345,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_small(const Params p) 
                 orows[i] = rows[(lane >> 2) + 8 * i];
                 gidx[i] = (io.gate_table && io.gate_idx && orows[i] >= 0) ? __ldg(io.gate_idx + orows[i]) : 0;
             }
+            const unsigned fl = epi_flags(io, p.scale, p.relu);
+            if (fl & EP_OPERANDS) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {                           // L2 prefetch of the epilogue operands of this lane's 4 rows
-                if (orows[i] < 0) continue;
-                prefetch_row_f32(io.residual, orows[i], p.cout, cb, TOT, lane & 3);
-                if (!io.residual) prefetch_row_split(io.residual_h, orows[i], p.cout, cb, TOT, lane & 3);
-                prefetch_row_f32(io.pre_add, orows[i], p.cout, cb, TOT, lane & 3);
-                if (io.gate_table && io.gate_idx) prefetch_row_f32(io.gate_table, gidx[i], p.cout, cb, TOT, lane & 3);
+                for (int i = 0; i < 4; ++i) {                       // L2 prefetch of the epilogue operands of this lane's 4 rows
+                    if (orows[i] < 0) continue;
+                    prefetch_row_f32(io.residual, orows[i], p.cout, cb, TOT, lane & 3);
+                    if (!io.residual) prefetch_row_split(io.residual_h, orows[i], p.cout, cb, TOT, lane & 3);
+                    prefetch_row_f32(io.pre_add, orows[i], p.cout, cb, TOT, lane & 3);
+                    if (io.gate_table && io.gate_idx) prefetch_row_f32(io.gate_table, gidx[i], p.cout, cb, TOT, lane & 3);
+                }
             }
             if (n_groups == 0) {
 #pragma unroll
@@ -361,26 +364,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_small(const Params p) 
                 const int buf = gcount & (NACC - 1);
                 mbar_wait(acc_full(buf), (gcount / NACC) & 1);
                 tc_fence_after();
-#pragma unroll
-                for (int cc = 0; cc < TOT / 16; ++cc) {
-                    uint32_t r[16];
-                    tmem_ld16(tmem_d + lane_base + (uint32_t)(buf * p.acc_stride + cb + cc * 16), r);
-                    tmem_ld_wait();
-                    if (g == 0) {
-#pragma unroll
-                        for (int q = 0; q < 16; ++q) tot[cc * 16 + q] = __uint_as_float(r[q]);
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < 16; ++q) tot[cc * 16 + q] = __fadd_rn(tot[cc * 16 + q], __uint_as_float(r[q]));
-                    }
-                }
+                drain_acc<TOT>(tmem_d + lane_base + (uint32_t)(buf * p.acc_stride + cb), tot, g == 0);
                 tc_fence_before();
                 mbar_arrive(acc_empty(buf));                       // accumulator free again: the MMA warp runs on while we finish
                 ++gcount;
             }
             // ---- epilogue from registers, 16 channels at a time through the warp's slab (tc_common.cuh: epilogue_slabs) ----
             constexpr int RB = (TOT >= 64) ? 2 : 4;                 // rows per load batch; 2 where the totals fill the registers
-            epilogue_slabs<TOT, RB>(tot, myslab, lane, orows, gidx, cb, p.cout, out_scale, epi_flags(io, p.scale, p.relu), io, p.scale, p.shift);
+            epilogue_slabs<TOT, RB>(tot, myslab, lane, orows, gidx, cb, p.cout, out_scale, fl, io, p.scale, p.shift);
             mbar_arrive(meta_empty(b));
         }
     }

@@ -381,13 +381,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_spconv
                 orows[i] = rows[(lane >> 2) + 8 * i];
                 gidx[i] = (io.gate_table && io.gate_idx && orows[i] >= 0) ? __ldg(io.gate_idx + orows[i]) : 0;
             }
+            const unsigned fl = epi_flags(io, p.scale, p.relu);
+            if (fl & EP_OPERANDS) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {                           // L2 prefetch of the epilogue operands of this lane's 4 rows
-                if (orows[i] < 0) continue;
-                prefetch_row_f32(io.residual, orows[i], NCOLS, cb, TOT, lane & 3);
-                if (!io.residual) prefetch_row_split(io.residual_h, orows[i], NCOLS, cb, TOT, lane & 3);
-                prefetch_row_f32(io.pre_add, orows[i], NCOLS, cb, TOT, lane & 3);
-                if (io.gate_table && io.gate_idx) prefetch_row_f32(io.gate_table, gidx[i], NCOLS, cb, TOT, lane & 3);
+                for (int i = 0; i < 4; ++i) {                       // L2 prefetch of the epilogue operands of this lane's 4 rows
+                    if (orows[i] < 0) continue;
+                    prefetch_row_f32(io.residual, orows[i], NCOLS, cb, TOT, lane & 3);
+                    if (!io.residual) prefetch_row_split(io.residual_h, orows[i], NCOLS, cb, TOT, lane & 3);
+                    prefetch_row_f32(io.pre_add, orows[i], NCOLS, cb, TOT, lane & 3);
+                    if (io.gate_table && io.gate_idx) prefetch_row_f32(io.gate_table, gidx[i], NCOLS, cb, TOT, lane & 3);
+                }
             }
             if (n_groups == 0) {
 #pragma unroll
@@ -397,26 +400,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_spconv
                 const int buf = gcount & (NACC - 1);
                 mbar_wait(acc_full(buf), (gcount / NACC) & 1);
                 tc_fence_after();
-#pragma unroll
-                for (int cc = 0; cc < TOT / 32; ++cc) {
-                    uint32_t r[32];
-                    tmem_ld32(tmem_d + lane_base + (uint32_t)(buf * NCOLS + cb + cc * 32), r);
-                    tmem_ld_wait();
-                    if (g == 0) {
-#pragma unroll
-                        for (int q = 0; q < 32; ++q) tot[cc * 32 + q] = __uint_as_float(r[q]);
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < 32; ++q) tot[cc * 32 + q] = __fadd_rn(tot[cc * 32 + q], __uint_as_float(r[q]));
-                    }
-                }
+                drain_acc<TOT>(tmem_d + lane_base + (uint32_t)(buf * NCOLS + cb), tot, g == 0);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(leader_acc_empty0 + 8u * buf);   // accumulator free again: the MMA warp runs on while we finish
                 ++gcount;
             }
             // ---- epilogue from registers, 16 channels at a time through the warp's slab (tc_common.cuh: epilogue_slabs) ----
-            epilogue_slabs<TOT, 2>(tot, myslab, lane, orows, gidx, cb, NCOLS, out_scale, epi_flags(io, p.scale, p.relu), io, p.scale, p.shift);
+            epilogue_slabs<TOT, 2>(tot, myslab, lane, orows, gidx, cb, NCOLS, out_scale, fl, io, p.scale, p.shift);
             mbar_arrive(meta_empty(b));
         }
     }

@@ -175,34 +175,63 @@ __device__ __forceinline__ float4 load_residual4(const float* res, const void* r
     return make_float4(h0.x + l0.x, h0.y + l0.y, h1.x + l1.x, h1.y + l1.y);
 }
 
-// One 16-channel slab of a drain thread's register-resident totals -> its row of the warp's staging slab, scaled.  The slab index is a
+// One 16-channel slab of a drain thread's register-resident totals -> its row of the warp's staging slab (raw accumulator units).  The slab index is a
 // template parameter (registers are addressed statically); the epilogue loops over the slabs at run time and dispatches through
 // slab_write_switch, so the global-memory part of the epilogue exists ONCE in the binary instead of once per slab (the fully unrolled
 // form made the kernels 85-185 KB of SASS and the drain warps stalled on instruction fetch, ncu: 'no_inst').
 template <int C, int TOT>
-__device__ __forceinline__ void slab_write(const float (&tot)[TOT], float* srow, float out_scale) {
+__device__ __forceinline__ void slab_write(const float (&tot)[TOT], float* srow) {
 #pragma unroll
     for (int q = 0; q < 4; ++q)
-        *reinterpret_cast<float4*>(srow + q * 4) = make_float4(tot[C * 16 + q * 4] * out_scale, tot[C * 16 + q * 4 + 1] * out_scale,
-                                                               tot[C * 16 + q * 4 + 2] * out_scale, tot[C * 16 + q * 4 + 3] * out_scale);
+        *reinterpret_cast<float4*>(srow + q * 4) = make_float4(tot[C * 16 + q * 4], tot[C * 16 + q * 4 + 1], tot[C * 16 + q * 4 + 2], tot[C * 16 + q * 4 + 3]);
 }
 template <int TOT>
-__device__ __forceinline__ void slab_write_switch(int cs, const float (&tot)[TOT], float* srow, float out_scale) {
+__device__ __forceinline__ void slab_write_switch(int cs, const float (&tot)[TOT], float* srow) {
     switch (cs) {
-        case 0: slab_write<0, TOT>(tot, srow, out_scale); break;
-        case 1: if constexpr (TOT > 16) slab_write<1, TOT>(tot, srow, out_scale); break;
-        case 2: if constexpr (TOT > 32) slab_write<2, TOT>(tot, srow, out_scale); break;
-        case 3: if constexpr (TOT > 48) slab_write<3, TOT>(tot, srow, out_scale); break;
-        case 4: if constexpr (TOT > 64) slab_write<4, TOT>(tot, srow, out_scale); break;
-        case 5: if constexpr (TOT > 80) slab_write<5, TOT>(tot, srow, out_scale); break;
-        case 6: if constexpr (TOT > 96) slab_write<6, TOT>(tot, srow, out_scale); break;
-        default: if constexpr (TOT > 112) slab_write<7, TOT>(tot, srow, out_scale); break;
+        case 0: slab_write<0, TOT>(tot, srow); break;
+        case 1: if constexpr (TOT > 16) slab_write<1, TOT>(tot, srow); break;
+        case 2: if constexpr (TOT > 32) slab_write<2, TOT>(tot, srow); break;
+        case 3: if constexpr (TOT > 48) slab_write<3, TOT>(tot, srow); break;
+        case 4: if constexpr (TOT > 64) slab_write<4, TOT>(tot, srow); break;
+        case 5: if constexpr (TOT > 80) slab_write<5, TOT>(tot, srow); break;
+        case 6: if constexpr (TOT > 96) slab_write<6, TOT>(tot, srow); break;
+        default: if constexpr (TOT > 112) slab_write<7, TOT>(tot, srow); break;
+    }
+}
+
+// One finished accumulator (this lane's row, TOT columns from taddr) into the drain thread's running total.  First group of a tile:
+// all loads in flight, one wait, the registers simply become the total; later groups: chunk-wise round-to-nearest adds (the second level of
+// the two-level accumulation).
+template <int TOT>
+__device__ __forceinline__ void drain_acc(uint32_t taddr, float (&tot)[TOT], bool first) {
+    constexpr int W = (TOT % 32 == 0) ? 32 : 16;
+    if (first) {
+        uint32_t r[TOT / W][W];
+#pragma unroll
+        for (int cc = 0; cc < TOT / W; ++cc) {
+            if constexpr (W == 32) tmem_ld32(taddr + (uint32_t)(cc * W), r[cc]); else tmem_ld16(taddr + (uint32_t)(cc * W), r[cc]);
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int cc = 0; cc < TOT / W; ++cc)
+#pragma unroll
+            for (int q = 0; q < W; ++q) tot[cc * W + q] = __uint_as_float(r[cc][q]);
+    } else {
+#pragma unroll
+        for (int cc = 0; cc < TOT / W; ++cc) {
+            uint32_t r[W];
+            if constexpr (W == 32) tmem_ld32(taddr + (uint32_t)(cc * W), r); else tmem_ld16(taddr + (uint32_t)(cc * W), r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < W; ++q) tot[cc * W + q] = __fadd_rn(tot[cc * W + q], __uint_as_float(r[q]));
+        }
     }
 }
 
 // ---------------------------------------------------------------------------------------------------
 // The epilogue of the register-total kernels (k_spconv_tc_small / _n256 / _pair), shared so every kernel rounds identically:
-//   y = ((acc * out_scale + pre_add) * bn_scale + bn_shift + residual), ReLU, then y and / or y * gate, each as fp32 and / or split.
+//   y = ((acc * out_scale + pre_add) * bn_scale + bn_shift + residual), ReLU, then y and / or y * gate, each as fp32 and / or split
+//   (out_scale = 2^-k undoes the power-of-two scaling of the packed weights).
 // A drain warp holds TOT channels of its 32 rows (lane = row) and hands them to the memory system 16 channels at a time through its
 // staging slab, where lane l serves channels 4 (l & 3) .. +3 of rows (l >> 2) + 8 u, u = 0..3: 64 contiguous bytes per row and store.
 // What a pass reads and writes is folded into one flag word per tile; a slab iteration only executes the loads / adds / stores whose
@@ -259,13 +288,14 @@ __device__ __forceinline__ void epilogue_slabs(const float (&tot)[TOT], float* m
 #pragma unroll 1
     for (int cs = 0; cs < TOT / 16; ++cs) {                    // run-time loop: one copy of the global-memory code (see slab_write_switch)
         __syncwarp();
-        slab_write_switch<TOT>(cs, tot, myslab + lane * EPI_PITCH, out_scale);
+        slab_write_switch<TOT>(cs, tot, myslab + lane * EPI_PITCH);
         __syncwarp();
         const unsigned col = c0 + 16u * (unsigned)cs;
         float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f), h4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (fl & EP_AFF) { s4 = __ldg(reinterpret_cast<const float4*>(scale + col)); h4 = __ldg(reinterpret_cast<const float4*>(shift + col)); }
         if (!(fl & EP_OPERANDS)) {
-            // ---- the common layer: no pre-add, residual or gate ----
+            // ---- the common layer: no pre-add, residual or gate.  The weights' scale 2^-k (out_scale) goes into the BN scale: exact ----
+            s4.x *= out_scale; s4.y *= out_scale; s4.z *= out_scale; s4.w *= out_scale;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 if (e0[u] == NOROW) continue;
@@ -311,7 +341,7 @@ __device__ __forceinline__ void epilogue_slabs(const float (&tot)[TOT], float* m
                 const int u = u0 + v;
                 if (e0[u] == NOROW) continue;
                 const float4 a4 = *reinterpret_cast<const float4*>(srd + 8 * u * EPI_PITCH);
-                float y[4] = {a4.x, a4.y, a4.z, a4.w};
+                float y[4] = {a4.x * out_scale, a4.y * out_scale, a4.z * out_scale, a4.w * out_scale};
                 if (fl & EP_PRE) { y[0] += pre[v].x; y[1] += pre[v].y; y[2] += pre[v].z; y[3] += pre[v].w; }
                 y[0] = fmaf(y[0], s4.x, h4.x); y[1] = fmaf(y[1], s4.y, h4.y); y[2] = fmaf(y[2], s4.z, h4.z); y[3] = fmaf(y[3], s4.w, h4.w);
                 if (fl & (EP_RES32 | EP_RESH)) { y[0] += res[v].x; y[1] += res[v].y; y[2] += res[v].z; y[3] += res[v].w; }
