@@ -78,6 +78,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_n256(const Params p) {
     uint64_t* bars = reinterpret_cast<uint64_t*>(wmask + 4 * META);
     constexpr int NBAR = 2 * NA + 2 * NB + 4 + 2 * META;
     uint32_t* misc = reinterpret_cast<uint32_t*>(bars + NBAR);
+    float* aff_s = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(misc + 16) + 15) & ~uintptr_t(15));                              // [2][NCOLS] BN scale, shift
     const uint32_t bar0 = smem_u32(bars);
     auto full_a = [&](int s) { return bar0 + 8u * s; };
     auto empty_a = [&](int s) { return bar0 + 8u * (NA + s); };
@@ -95,6 +96,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_n256(const Params p) {
         for (int b = 0; b < META; ++b) { mbar_init(meta_full(b), 1); mbar_init(meta_empty(b), 258); }   // MMA + loader + 256 drain threads
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    stage_affine(aff_s, p.scale, p.shift, NCOLS);
     if (warp == 4) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&misc[0])), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -328,7 +330,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_n256(const Params p) {
                 ++gcount;
             }
             // ---- epilogue from registers, 16 channels at a time through the warp's slab (tc_common.cuh: epilogue_slabs) ----
-            epilogue_slabs<128, 2>(tot, myslab, lane, orows, gidx, cb, NCOLS, out_scale, epi_flags(io, p.scale, p.relu), io, p.scale, p.shift);
+            epilogue_slabs<128, 2>(tot, myslab, lane, orows, gidx, cb, NCOLS, out_scale, epi_flags(io, p.relu), io, aff_s);
             mbar_arrive(meta_empty(b));
         }
     }
@@ -339,7 +341,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_n256(const Params p) {
 
 static size_t smem_bytes() {
     return 1024 + (size_t)(NA / 2) * 2 * A_TILE + (size_t)NB * 2 * NCOLS * 128 + SLAB_BYTES + META * BM * sizeof(int) +
-           META * BM * sizeof(uint32_t) + 4 * META * sizeof(uint32_t) + (2 * NA + 2 * NB + 4 + 2 * META) * 8 + 64;
+           META * BM * sizeof(uint32_t) + 4 * META * sizeof(uint32_t) + (2 * NA + 2 * NB + 4 + 2 * META) * 8 + 64 + 16 + 2 * NCOLS * sizeof(float);
 }
 
 }  // namespace tc3

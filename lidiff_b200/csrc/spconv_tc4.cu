@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_small(const Params p) 
     uint32_t* wmask = reinterpret_cast<uint32_t*>(gate_s + 8 * 32);                  // [META][4] per-warp offset masks
     uint64_t* bars = reinterpret_cast<uint64_t*>(wmask + 4 * META);
     uint32_t* misc = reinterpret_cast<uint32_t*>(bars + NBAR);
+    float* aff_s = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(misc + 16) + 15) & ~uintptr_t(15));                              // [2][cout] BN scale, shift
     const uint32_t bar0 = smem_u32(bars);
     auto full_a = [&](int s) { return bar0 + 8u * s; };
     auto empty_a = [&](int s) { return bar0 + 8u * (NA + s); };
@@ -108,6 +109,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_small(const Params p) 
         for (int b = 0; b < META; ++b) { mbar_init(meta_full(b), 1); mbar_init(meta_empty(b), 258); }   // MMA + loader + both drain warpgroups
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    stage_affine(aff_s, p.scale, p.shift, p.cout);
     if (warp == 4) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&misc[0])), "r"((uint32_t)p.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -345,7 +347,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_small(const Params p) 
                 orows[i] = rows[(lane >> 2) + 8 * i];
                 gidx[i] = (io.gate_table && io.gate_idx && orows[i] >= 0) ? __ldg(io.gate_idx + orows[i]) : 0;
             }
-            const unsigned fl = epi_flags(io, p.scale, p.relu);
+            const unsigned fl = epi_flags(io, p.relu);
             if (fl & EP_OPERANDS) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {                       // L2 prefetch of the epilogue operands of this lane's 4 rows
@@ -371,7 +373,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_small(const Params p) 
             }
             // ---- epilogue from registers, 16 channels at a time through the warp's slab (tc_common.cuh: epilogue_slabs) ----
             constexpr int RB = (TOT >= 64) ? 2 : 4;                 // rows per load batch; 2 where the totals fill the registers
-            epilogue_slabs<TOT, RB>(tot, myslab, lane, orows, gidx, cb, p.cout, out_scale, fl, io, p.scale, p.shift);
+            epilogue_slabs<TOT, RB>(tot, myslab, lane, orows, gidx, cb, p.cout, out_scale, fl, io, aff_s);
             mbar_arrive(meta_empty(b));
         }
     }
@@ -382,7 +384,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_spconv_tc_small(const Params p) 
 
 static size_t smem_bytes(int cout) {
     return 1024 + (size_t)(na_of(cout / 32) / 2) * 2 * A_TILE + (size_t)NB * 2 * cout * 128 + SLAB_BYTES + MAX_KVOL * BM * sizeof(int) + META * BM * sizeof(int) +
-           8 * 32 * sizeof(int) + 4 * META * sizeof(uint32_t) + NBAR * 8 + 64;
+           8 * 32 * sizeof(int) + 4 * META * sizeof(uint32_t) + NBAR * 8 + 64 + 16 + 2 * cout * sizeof(float);
 }
 
 }  // namespace tc4

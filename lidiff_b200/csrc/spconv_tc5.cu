@@ -41,7 +41,7 @@ template <int NCOLS> struct Cfg {
     static constexpr uint32_t B_SLOT = 2u * B_HALF;
     static constexpr int NBAR = 3 * NA + 3 * NB + 2 * NACC + 2 * META;
     static constexpr size_t SMEM = 1024 + (size_t)(NA / 2) * 2 * A_TILE + (size_t)NB * B_SLOT + SLAB_BYTES + META * BM * sizeof(int) +
-                                   META * BM * sizeof(uint32_t) + 4 * META * sizeof(uint32_t) + NBAR * 8 + 64;
+                                   META * BM * sizeof(uint32_t) + 4 * META * sizeof(uint32_t) + NBAR * 8 + 64 + 16 + 2 * NCOLS * sizeof(float);
 };
 
 struct Params {
@@ -130,6 +130,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_spconv
     uint32_t* wmask = mask_s + META * BM;                                            // [META][4] per-warp offset masks (union over the pair)
     uint64_t* bars = reinterpret_cast<uint64_t*>(wmask + 4 * META);
     uint32_t* misc = reinterpret_cast<uint32_t*>(bars + C::NBAR);
+    float* aff_s = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(misc + 16) + 15) & ~uintptr_t(15));                              // [2][NCOLS] BN scale, shift
     const uint32_t bar0 = smem_u32(bars);
     auto full_a = [&](int s) { return bar0 + 8u * s; };                              // per CTA: its 128 producer threads (cp.async completion)
     auto full_ap = [&](int s) { return bar0 + 8u * (NA + s); };                      // leader's: the peer's relay
@@ -149,6 +150,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_spconv
         for (int b = 0; b < META; ++b) { mbar_init(meta_full(b), 1); mbar_init(meta_empty(b), 258); }   // warp 4 + loader + 256 drain threads
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    stage_affine(aff_s, p.scale, p.shift, NCOLS);
     if (warp == 4) {                                                                 // same warp in both CTAs, same destination offset
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&misc[0])), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
@@ -381,7 +383,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_spconv
                 orows[i] = rows[(lane >> 2) + 8 * i];
                 gidx[i] = (io.gate_table && io.gate_idx && orows[i] >= 0) ? __ldg(io.gate_idx + orows[i]) : 0;
             }
-            const unsigned fl = epi_flags(io, p.scale, p.relu);
+            const unsigned fl = epi_flags(io, p.relu);
             if (fl & EP_OPERANDS) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {                       // L2 prefetch of the epilogue operands of this lane's 4 rows
@@ -407,7 +409,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_spconv
                 ++gcount;
             }
             // ---- epilogue from registers, 16 channels at a time through the warp's slab (tc_common.cuh: epilogue_slabs) ----
-            epilogue_slabs<TOT, 2>(tot, myslab, lane, orows, gidx, cb, NCOLS, out_scale, fl, io, p.scale, p.shift);
+            epilogue_slabs<TOT, 2>(tot, myslab, lane, orows, gidx, cb, NCOLS, out_scale, fl, io, aff_s);
             mbar_arrive(meta_empty(b));
         }
     }

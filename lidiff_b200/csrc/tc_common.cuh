@@ -240,8 +240,8 @@ __device__ __forceinline__ void drain_acc(uint32_t taddr, float (&tot)[TOT], boo
 // ---------------------------------------------------------------------------------------------------
 constexpr int EPI_PITCH = 20;                         // floats per slab row (16 + 4: conflict-free 16-byte accesses)
 enum : unsigned { EP_PRE = 1u, EP_RES32 = 2u, EP_RESH = 4u, EP_GATE = 8u, EP_OUT = 16u, EP_OUTH = 32u, EP_G = 64u, EP_GH = 128u,
-                  EP_AFF = 256u, EP_RELU = 512u, EP_OPERANDS = EP_PRE | EP_RES32 | EP_RESH | EP_GATE };
-__device__ __forceinline__ unsigned epi_flags(const lb2_conv_io& io, const float* scale, int relu) {
+                  EP_RELU = 512u, EP_OPERANDS = EP_PRE | EP_RES32 | EP_RESH | EP_GATE };
+__device__ __forceinline__ unsigned epi_flags(const lb2_conv_io& io, int relu) {
     unsigned f = 0;
     if (io.pre_add) f |= EP_PRE;
     if (io.residual) f |= EP_RES32; else if (io.residual_h) f |= EP_RESH;
@@ -250,7 +250,6 @@ __device__ __forceinline__ unsigned epi_flags(const lb2_conv_io& io, const float
     if (io.out_gated) f |= EP_G;
     if (io.out_gated_h) f |= EP_GH;
     if (io.gate_table && (f & (EP_G | EP_GH))) f |= EP_GATE;
-    if (scale) f |= EP_AFF;
     if (relu) f |= EP_RELU;
     return f;
 }
@@ -270,12 +269,19 @@ __device__ __forceinline__ void epi_store(float (&y)[4], const float4& gate, uns
         if (fl & EP_GH) store_split4_at(reinterpret_cast<__half*>(io.out_gated_h) + eh, C, y);
     }
 }
+// The per-channel affine (eval-mode BN: scale, shift; identity when the caller passes none) staged once per CTA in shared memory as
+// aff_s[0..C) = scale, aff_s[C..2C) = shift: the epilogue reads it with LDS instead of a global load per 16-channel slab.
+__device__ __forceinline__ void stage_affine(float* aff_s, const float* __restrict__ scale, const float* __restrict__ shift, int C) {
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+        aff_s[i] = scale ? __ldg(scale + i) : 1.f;
+        aff_s[C + i] = shift ? __ldg(shift + i) : 0.f;
+    }
+}
 // tot: this lane's row, channels [cb, cb + TOT) of C; orow / grow: output row and gate-table row of the 4 rows this lane serves
 // (orow < 0: no row).  RB = rows whose operand loads are in flight together (2 where the totals fill the registers).
 template <int TOT, int RB>
 __device__ __forceinline__ void epilogue_slabs(const float (&tot)[TOT], float* myslab, int lane, const int (&orow)[4], const int (&grow)[4],
-                                               int cb, int C, float out_scale, unsigned fl, const lb2_conv_io& io,
-                                               const float* __restrict__ scale, const float* __restrict__ shift) {
+                                               int cb, int C, float out_scale, unsigned fl, const lb2_conv_io& io, const float* aff_s) {
     constexpr unsigned NOROW = 0xffffffffu;
     const float* srd = myslab + (lane >> 2) * EPI_PITCH + (lane & 3) * 4;
     unsigned c0 = (unsigned)(cb + (lane & 3) * 4);                  // this lane's first channel of slab 0
@@ -291,8 +297,8 @@ __device__ __forceinline__ void epilogue_slabs(const float (&tot)[TOT], float* m
         slab_write_switch<TOT>(cs, tot, myslab + lane * EPI_PITCH);
         __syncwarp();
         const unsigned col = c0 + 16u * (unsigned)cs;
-        float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f), h4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (fl & EP_AFF) { s4 = __ldg(reinterpret_cast<const float4*>(scale + col)); h4 = __ldg(reinterpret_cast<const float4*>(shift + col)); }
+        float4 s4 = *reinterpret_cast<const float4*>(aff_s + col);                  // BN scale and shift of these 4 channels (stage_affine)
+        const float4 h4 = *reinterpret_cast<const float4*>(aff_s + C + col);
         if (!(fl & EP_OPERANDS)) {
             // ---- the common layer: no pre-add, residual or gate.  The weights' scale 2^-k (out_scale) goes into the BN scale: exact ----
             s4.x *= out_scale; s4.y *= out_scale; s4.z *= out_scale; s4.w *= out_scale;
