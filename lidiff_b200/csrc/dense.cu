@@ -154,13 +154,17 @@ extern "C" int lb2_nn_match_grid(void* handle, void* stream, const int32_t* q_co
 #define NT_HDR 16
 #define NT_STACK 48
 
+// squared length of an integer offset whose components fit 32 bits (coordinates are 18-bit signed): three 32 x 32 -> 64 bit multiplies
+__device__ __forceinline__ unsigned long long nt_sq3(int ex, int ey, int ez) {
+    const unsigned ax = (unsigned)abs(ex), ay = (unsigned)abs(ey), az = (unsigned)abs(ez);
+    return (unsigned long long)ax * ax + (unsigned long long)ay * ay + (unsigned long long)az * az;
+}
 __device__ __forceinline__ unsigned long long nt_box_dist(const int* __restrict__ n, const int4 c) {
-    if (n[0] > n[3]) return ~0ull;                                   // empty node
-    const long long dx = max(max((long long)n[0] - c.y, (long long)c.y - n[3]), 0ll);
-    const long long dy = max(max((long long)n[1] - c.z, (long long)c.z - n[4]), 0ll);
-    const long long dz = max(max((long long)n[2] - c.w, (long long)c.w - n[5]), 0ll);
-    unsigned long long d = (unsigned long long)(dx * dx + dy * dy + dz * dz);
-    if (c.x < n[6] || c.x > n[7]) d += 1ull << 62;                   // no key of the query's batch in this subtree
+    const int4 lo = __ldg(reinterpret_cast<const int4*>(n)), hi = __ldg(reinterpret_cast<const int4*>(n) + 1);   // {min xyz, max x} {max yz, batch lo, hi}
+    if (lo.x > lo.w) return ~0ull;                                   // empty node
+    const int dx = max(max(lo.x - c.y, c.y - lo.w), 0), dy = max(max(lo.y - c.z, c.z - hi.x), 0), dz = max(max(lo.z - c.w, c.w - hi.y), 0);
+    unsigned long long d = nt_sq3(dx, dy, dz);
+    if (c.x < hi.z || c.x > hi.w) d += 1ull << 62;                   // no key of the query's batch in this subtree
     return d;
 }
 
@@ -181,8 +185,7 @@ __global__ void __launch_bounds__(128) k_nn_match_tree(const int4* __restrict__ 
     if (hint_idx) {                                                  // start from a key that is probably close (a coarser voxel's answer):
         const int j = __ldg(hint_idx + (hint_of ? __ldg(hint_of + i) : i));    // any key is a valid upper bound, so the result is unchanged
         const int4 kc = __ldg(keys + j);
-        const long long ex = (long long)c.y - kc.y, ey = (long long)c.z - kc.z, ez = (long long)c.w - kc.w;
-        best = (unsigned long long)(ex * ex + ey * ey + ez * ez);
+        best = nt_sq3(c.y - kc.y, c.z - kc.z, c.w - kc.w);
         if (kc.x != c.x) best += 1ull << 62;
         best_j = j;
     }
@@ -201,8 +204,7 @@ __global__ void __launch_bounds__(128) k_nn_match_tree(const int4* __restrict__ 
             for (int t = 0; t < NT_LEAF; ++t) {
                 const int4 kc = __ldg(skeys + k0 + t);
                 const int kb = __ldg(sbatch + k0 + t);
-                const long long ex = (long long)c.y - kc.x, ey = (long long)c.z - kc.y, ez = (long long)c.w - kc.z;
-                unsigned long long d = (unsigned long long)(ex * ex + ey * ey + ez * ez);
+                unsigned long long d = nt_sq3(c.y - kc.x, c.z - kc.y, c.w - kc.z);
                 if (kb != c.x) d += 1ull << 62;
                 const bool valid = kc.w >= 0;                          // slots past the last key hold row -1
                 if (valid && (d < best || (d == best && kc.w < best_j))) { best = d; best_j = kc.w; }
