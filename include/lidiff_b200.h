@@ -257,6 +257,14 @@ int lb2_linear(void* h, void* stream, const float* x, int64_t ldx, const float* 
                int32_t n_in, int32_t n_out, int32_t act, float* y, int64_t ldy,
                const float* prebias, int32_t pre_act);
 
+/* The head of the U-Nets in one pass over the rows — `last` of MinkUNetDiff / MinkUNet (minkunet.py:376-380, :585-588):
+ * y = out_act(W1 . LeakyReLU_0.1(W0 . x + b0) + b1), W0 (n_hid, n_in), W1 (n_out, n_hid) in torch layout; out_act as lb2_linear.
+ * npass (1 or 2) row blocks x + p * x_pass_stride -> y + p * y_pass_stride (floats) share the weights and the launch.
+ * n_in: multiple of 16, <= 128; n_hid <= 64; n_out <= 24; ldx a multiple of 4. */
+int lb2_head_mlp(void* h, void* stream, const float* x, int64_t ldx, int64_t x_pass_stride, const float* w0, const float* b0,
+                 const float* w1, const float* b1, int32_t m_cap, const int32_t* d_m, int32_t n_in, int32_t n_hid,
+                 int32_t n_out, int32_t out_act, int32_t npass, float* y, int64_t ldy, int64_t y_pass_stride);
+
 /* x * w row-gather multiply (`x0*w0`, minkunet.py:431...): out[r] = x[r] * table[idx ? idx[r] : 0];
  * out_h: optional fp16 split companion of out (see lb2_conv_io); out may be NULL when out_h is given. */
 int lb2_gate_mul(void* h, void* stream, const float* x, const float* table, const int32_t* idx,

@@ -61,7 +61,7 @@ EXPORTS = [
     "lb2_set_option", "lb2_get_option", "lb2_tile_order",
     "lb2_quantize", "lb2_unique_scratch_bytes", "lb2_unique_build", "lb2_voxel_mean", "lb2_kernel_map",
     "lb2_spconv_forward", "lb2_packed_weight_bytes", "lb2_pack_weights", "lb2_nn_match", "lb2_linear",
-    "lb2_gate_mul", "lb2_gather_rows", "lb2_guidance_dpm_step", "lb2_farthest_point_sample",
+    "lb2_gate_mul", "lb2_gather_rows", "lb2_head_mlp", "lb2_guidance_dpm_step", "lb2_farthest_point_sample",
     "lb2_row_order", "lb2_row_order_scratch_bytes", "lb2_nn_match_grid",
     "lb2_nn_table_bytes", "lb2_nn_table_build", "lb2_nn_match_table",
     "lb2_nn_tree_bytes", "lb2_nn_tree_build", "lb2_nn_match_tree",
@@ -129,6 +129,7 @@ class Lib:
                                  vp, i32]
         d.lb2_gate_mul.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, vp, vp]
         d.lb2_gather_rows.argtypes = [vp, vp, vp, vp, i32, i32, vp]
+        d.lb2_head_mlp.argtypes = [vp, vp, vp, i64, i64, vp, vp, vp, vp, i32, vp, i32, i32, i32, i32, i32, vp, i64, i64]
         d.lb2_guidance_dpm_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, DpmCoef, vp, vp, vp, vp]
         d.lb2_farthest_point_sample.argtypes = [vp, vp, vp, i32, i32, vp, vp]
         self._handles = {}
@@ -278,6 +279,11 @@ class Handle:
     def linear(self, x, ldx, w, b, addend, ld_add, m_cap, d_m, n_in, n_out, act, y, ldy, prebias=None, pre_act=0):
         self._check(self.dll.lb2_linear(self.hp, self._stream(), _ptr(x), int(ldx), _ptr(w), _ptr(b), _ptr(addend), int(ld_add), int(m_cap),
                                         _ptr(d_m), int(n_in), int(n_out), int(act), _ptr(y), int(ldy), _ptr(prebias), int(pre_act)), "lb2_linear")
+
+    def head_mlp(self, x, ldx, x_pass_stride, w0, b0, w1, b1, m_cap, d_m, n_in, n_hid, n_out, out_act, npass, y, ldy, y_pass_stride):
+        self._check(self.dll.lb2_head_mlp(self.hp, self._stream(), _ptr(x), int(ldx), int(x_pass_stride), _ptr(w0), _ptr(b0), _ptr(w1), _ptr(b1),
+                                          int(m_cap), _ptr(d_m), int(n_in), int(n_hid), int(n_out), int(out_act), int(npass), _ptr(y), int(ldy),
+                                          int(y_pass_stride)), "lb2_head_mlp")
 
     def gate_mul(self, x, table, idx, d_m, m_cap, c, out, out_h=None):
         self._check(self.dll.lb2_gate_mul(self.hp, self._stream(), _ptr(x), _ptr(table), _ptr(idx), _ptr(d_m), int(m_cap), int(c), _ptr(out),

@@ -448,6 +448,84 @@ extern "C" int lb2_linear(void* handle, void* stream, const float* x, int64_t ld
 }
 
 // ---------------------------------------------------------------------------------------------------
+// head MLP of the U-Nets (minkunet.py:376-380, :585-588): y = out_act(W1 . leaky_relu(W0 . x + b0, 0.1) + b1) in one pass over the rows,
+// the hidden vector never leaves the registers.  Four lanes share a row (each n_in / 4 input channels, coalesced 64-byte pieces),
+// the weights sit in shared memory; blockIdx.y = guidance pass.  Memory-bound: one read of x (rows x n_in fp32).
+// ---------------------------------------------------------------------------------------------------
+template <int NOUT_MAX>
+__global__ void __launch_bounds__(256) k_head_mlp(const float* __restrict__ x, long long ldx, long long x_pass_stride,
+                                                  const float* __restrict__ w0, const float* __restrict__ b0,
+                                                  const float* __restrict__ w1, const float* __restrict__ b1, int m_cap,
+                                                  const int* __restrict__ d_m, int n_in, int n_hid, int n_out, int out_act,
+                                                  float* __restrict__ y, long long ldy, long long y_pass_stride) {
+    extern __shared__ float hm_s[];
+    float* w0s = hm_s;                                   // [n_hid][n_in]
+    float* b0s = w0s + n_hid * n_in;                     // [n_hid]
+    float* w1s = b0s + n_hid;                            // [n_out][n_hid]
+    float* b1s = w1s + n_out * n_hid;                    // [n_out]
+    for (int i = threadIdx.x; i < n_hid * n_in; i += blockDim.x) w0s[i] = __ldg(w0 + i);
+    for (int i = threadIdx.x; i < n_hid; i += blockDim.x) b0s[i] = b0 ? __ldg(b0 + i) : 0.f;
+    for (int i = threadIdx.x; i < n_out * n_hid; i += blockDim.x) w1s[i] = __ldg(w1 + i);
+    for (int i = threadIdx.x; i < n_out; i += blockDim.x) b1s[i] = b1 ? __ldg(b1 + i) : 0.f;
+    __syncthreads();
+    const int M = d_m ? min(*d_m, m_cap) : m_cap;
+    x += (long long)blockIdx.y * x_pass_stride;
+    y += (long long)blockIdx.y * y_pass_stride;
+    const int q = threadIdx.x & 3, nk = n_in >> 4;       // this lane's 16-byte piece of every 64 input bytes; pieces per row (<= 8)
+    for (long long row = (long long)blockIdx.x * (blockDim.x >> 2) + (threadIdx.x >> 2); row < (long long)((M + 7) & ~7);
+         row += (long long)gridDim.x * (blockDim.x >> 2)) {                      // whole groups of 8 rows per warp: the shuffles need every lane
+        const bool live = row < M;
+        float4 v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            v[k] = (live && k < nk) ? __ldg(reinterpret_cast<const float4*>(x + row * ldx + k * 16 + q * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float o[NOUT_MAX];
+#pragma unroll
+        for (int c = 0; c < NOUT_MAX; ++c) o[c] = 0.f;
+        for (int j = 0; j < n_hid; ++j) {
+            const float* wr = w0s + j * n_in + q * 4;
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (k < nk) {
+                    const float4 w = *reinterpret_cast<const float4*>(wr + k * 16);
+                    s = fmaf(v[k].x, w.x, s); s = fmaf(v[k].y, w.y, s); s = fmaf(v[k].z, w.z, s); s = fmaf(v[k].w, w.w, s);
+                }
+            }
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            s += b0s[j];
+            s = s > 0.f ? s : 0.1f * s;                  // LeakyReLU(0.1)
+#pragma unroll
+            for (int c = 0; c < NOUT_MAX; ++c)
+                if (c < n_out) o[c] = fmaf(w1s[c * n_hid + j], s, o[c]);
+        }
+        if (live && q == 0) {
+#pragma unroll
+            for (int c = 0; c < NOUT_MAX; ++c)
+                if (c < n_out) y[row * ldy + c] = lb2_act(o[c] + b1s[c], out_act);
+        }
+    }
+}
+
+extern "C" int lb2_head_mlp(void* handle, void* stream, const float* x, int64_t ldx, int64_t x_pass_stride, const float* w0, const float* b0,
+                            const float* w1, const float* b1, int32_t m_cap, const int32_t* d_m, int32_t n_in, int32_t n_hid,
+                            int32_t n_out, int32_t out_act, int32_t npass, float* y, int64_t ldy, int64_t y_pass_stride) {
+    Lb2Handle* h = (Lb2Handle*)handle;
+    LB2_REQUIRE(h, h && x && w0 && w1 && y && m_cap > 0 && npass >= 1 && npass <= 2, "head_mlp");
+    LB2_REQUIRE(h, n_in >= 16 && n_in <= 128 && n_in % 16 == 0 && n_hid >= 1 && n_hid <= 64 && n_out >= 1 && n_out <= 24 && ldx >= n_in &&
+                   ldx % 4 == 0 && ldy >= n_out, "head_mlp shape");
+    const size_t smem = ((size_t)n_hid * n_in + n_hid + (size_t)n_out * n_hid + n_out) * sizeof(float);
+    const dim3 grid((unsigned)std::min<long long>(cdiv(m_cap, 64), (long long)h->num_sms * 8), (unsigned)npass);
+    if (n_out <= 4)
+        k_head_mlp<4><<<grid, 256, smem, (cudaStream_t)stream>>>(x, ldx, x_pass_stride, w0, b0, w1, b1, m_cap, d_m, n_in, n_hid, n_out, out_act, y, ldy, y_pass_stride);
+    else
+        k_head_mlp<24><<<grid, 256, smem, (cudaStream_t)stream>>>(x, ldx, x_pass_stride, w0, b0, w1, b1, m_cap, d_m, n_in, n_hid, n_out, out_act, y, ldy, y_pass_stride);
+    LB2_POST_LAUNCH(h, "k_head_mlp");
+    return LB2_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // gate multiply / row gather
 // ---------------------------------------------------------------------------------------------------
 __global__ void k_gate_mul(const float* __restrict__ x, const float* __restrict__ table, const int* __restrict__ idx,

@@ -365,6 +365,13 @@ class DenoiseEngine:
                       out, out.stride(0), prebias, pre_act)
         return out
 
+    def _head(self, x, head, out, out_act, d_m):
+        """`last` of the U-Nets (minkunet.py:376-380, :585-588) on voxel rows: Linear + LeakyReLU(0.1) + Linear (+ tanh) in one launch
+        for all passes; x (npass, cap, n_in), out (npass, cap, n_out)."""
+        l0, l1 = head
+        self.h.head_mlp(x, x.stride(1), x.stride(0), l0.w, l0.b, l1.w, l1.b, x.shape[1], d_m, l0.n_in, l0.n_out, l1.n_out, out_act,
+                        x.shape[0], out, out.stride(1), out.stride(0))
+
     def _timestep_embedding(self, ts: torch.Tensor) -> torch.Tensor:
         """MinkUNetDiff.get_timestep_embedding (minkunet.py:390-401) for all T steps at once."""
         half = 48
@@ -661,10 +668,7 @@ class DenoiseEngine:
         skips, cur = self._encoder(self.diff, g, F0, 2, "d", gates, lean=self.lean, before_gates=join_sides, before_stage2=join_late_maps)
         y4 = self._decoder(self.diff, g, skips, cur, 2, "d", gates, lean=self.lean)
         eps = self.buf("eps_vox", (2, N, 3))
-        hid = self.buf("head_h", (N, 20))
-        for p in range(2):
-            self._linear(y4.f[p], self.head[0], hid, act=1, m_cap=N, d_m=g.d_n[0])
-            self._linear(hid, self.head[1], eps[p], m_cap=N, d_m=g.d_n[0])
+        self._head(y4.f, self.head, eps, 0, g.d_n[0])
         c = self.sched.coefficients(i)
         # diffusers: second order once one x0 prediction is stored (lower_order_nums >= 1), also at step 0 of a later scan
         second = self._have_x0 and not (i == self.T - 1 and self.T < 15)
@@ -786,10 +790,9 @@ class DenoiseEngine:
         g.voxel_mean(pts, n, F0.f[0])
         skips, cur = self._encoder(self.refine, g, F0, 1, "r", lean=self.lean)
         y4 = self._decoder(self.refine, g, skips, cur, 1, "r", None, lean=self.lean)
-        hid = self.buf("r.head_h", (N, 20))
-        off_v = self.buf("r.off_v", (N, 18))
-        self._linear(y4.f[0], self.refine_head[0], hid, act=1, m_cap=N, d_m=g.d_n[0])
-        self._linear(hid, self.refine_head[1], off_v, act=2, m_cap=N, d_m=g.d_n[0])
+        off_v = self.buf("r.off_v", (1, N, 18))
+        self._head(y4.f, self.refine_head, off_v, 2, g.d_n[0])
+        off_v = off_v[0]
         out = torch.empty((n, 18), device=self.device)
         h.gather_rows(off_v, g.inv[0], n, 18, out)
         return out

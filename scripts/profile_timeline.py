@@ -77,6 +77,12 @@ def main():
         print(f"  {v / 1e6 / count:7.3f} ms/step  {n}")
     nnk = [(a, b - a, s_) for a, b, n, s_ in ev if "nn_match" in n or "compose" in n]
     print("NN kernels of the first profiled step (start ms, us, stream):", [(round((a - t0) / 1e6, 3), round(d / 1e3, 1), s_) for a, d, s_ in nnk[:len(nnk) // count]])
+    nshow = int(os.environ.get("TIMELINE_HEAD", "0"))
+    if nshow:                                                    # the window between the last conv of a step and the first conv after the stem of the next
+        k0 = max(0, next(i for i, e in enumerate(ev) if "guidance_dpm" in e[2]) - 8)
+        print("activities around the end of the first profiled step (start ms, us, stream, name):")
+        for a, b, n, s_ in ev[k0:k0 + nshow]:
+            print(f"  {(a - t0) / 1e6:8.3f} {(b - a) / 1e3:7.1f} {s_:4d} {n.split('(')[0].replace('void ', '')[:50]}")
     print("largest gaps (us, at ms, kernels inside):")
     for d, at, names in sorted(big, reverse=True)[:25]:
         print(f"  {d / 1e3:8.1f} us at {at:8.3f} ms: {names}")

@@ -318,6 +318,15 @@ class FakeHandle:
             hi = y.half()
             out_h[:M] = torch.cat([hi, (y - hi.float()).half()], 1)
 
+    def head_mlp(self, x, ldx, x_pass_stride, w0, b0, w1, b1, m_cap, d_m, n_in, n_hid, n_out, out_act, npass, y, ldy, y_pass_stride):
+        self.launches += 1
+        M = self._n(d_m, m_cap)
+        for p in range(npass):
+            xs = torch.as_strided(x, (M, n_in), (ldx, 1), x.storage_offset() + p * x_pass_stride).double()
+            hid = torch.nn.functional.leaky_relu(xs @ w0.double().t() + (b0.double() if b0 is not None else 0), 0.1)
+            v = hid @ w1.double().t() + (b1.double() if b1 is not None else 0)
+            torch.as_strided(y, (M, n_out), (ldy, 1), y.storage_offset() + p * y_pass_stride).copy_(self._act(v, out_act).float())
+
     def gather_rows(self, src, idx, n, c, out):
         self.launches += 1
         out[:n] = src[idx[:n].long()]

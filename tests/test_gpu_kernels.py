@@ -271,6 +271,27 @@ def test_farthest_point_sampling_bit_exact():
     assert np.array_equal(got, ref)
 
 
+@pytest.mark.parametrize("n_out,out_act,npass", [(3, 0, 2), (18, 2, 1)])
+def test_head_mlp_matches_torch(n_out, out_act, npass):
+    """lb2_head_mlp: Linear(96,20) + LeakyReLU(0.1) + Linear(20,n_out) (+ tanh) per row, rows from a device count, both passes in one launch"""
+    h = H()
+    g = torch.Generator().manual_seed(3)
+    cap, m = 5000, 4321
+    x = torch.randn(npass, cap, 96, generator=g)
+    w0, b0 = torch.randn(20, 96, generator=g) / 10, torch.randn(20, generator=g)
+    w1, b1 = torch.randn(n_out, 20, generator=g) / 4, torch.randn(n_out, generator=g)
+    dx, dw0, db0, dw1, db1 = (t.to(DEV).contiguous() for t in (x, w0, b0, w1, b1))
+    y = torch.full((npass, cap, n_out), 7.0, device=DEV)
+    d_m = torch.tensor([m], dtype=torch.int32, device=DEV)
+    h.head_mlp(dx, 96, cap * 96, dw0, db0, dw1, db1, cap, d_m, 96, 20, n_out, out_act, npass, y, n_out, cap * n_out)
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.leaky_relu(x[:, :m].double() @ w0.double().t() + b0.double(), 0.1) @ w1.double().t() + b1.double()
+    if out_act == 2:
+        ref = torch.tanh(ref)
+    assert (y[:, :m].double().cpu() - ref).abs().max().item() < 2e-5
+    assert (y[:, m:] == 7.0).all(), "rows beyond the live count must stay untouched"
+
+
 def test_tile_order_sorts_tiles_by_the_offsets_they_run():
     """lb2_tile_order: order128 / order256 are permutations of the live tiles of the row order, by descending popcount of the OR of
     the tile's row masks; entries beyond the live tiles are -1"""
