@@ -104,6 +104,12 @@ int lb2_kernel_map(void* h, void* stream, lb2_grid grid_in, const int32_t* out_c
                    const int32_t* d_nout, int32_t nout_cap, int32_t ks, int32_t step,
                    int32_t* nbr, int64_t nbr_stride, uint64_t* pair_count, uint32_t* row_mask);
 
+/* The 3^3 stride-1 map of a coordinate set onto itself (`grid` was built from exactly `coords`; step = the level's tensor stride):
+ * same table and row masks as lb2_kernel_map(ks = 3), with half the hash probes (the pair set is symmetric: row j at offset k of row o
+ * <=> o at offset 26 - k of j). */
+int lb2_kernel_map_self(void* h, void* stream, lb2_grid grid, const int32_t* coords, const int32_t* d_n, int32_t n_cap,
+                        int32_t step, int32_t* nbr, int64_t nbr_stride, uint64_t* pair_count, uint32_t* row_mask);
+
 /* Execution order of the output rows for lb2_spconv_forward (no reference counterpart: scheduling only).
  * perm[0..n) = the rows 0..n-1 sorted by their neighbour mask (kvol 27: centre-only rows, rows with one neighbour grouped
  * by it, then the rest in mask order; kvol <= 8: by the 8-bit mask) so that 128-row tiles skip unpopulated kernel offsets.

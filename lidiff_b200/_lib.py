@@ -61,7 +61,7 @@ EXPORTS = [
     "lb2_set_option", "lb2_get_option", "lb2_tile_order",
     "lb2_quantize", "lb2_unique_scratch_bytes", "lb2_unique_build", "lb2_voxel_mean", "lb2_kernel_map",
     "lb2_spconv_forward", "lb2_packed_weight_bytes", "lb2_pack_weights", "lb2_nn_match", "lb2_linear",
-    "lb2_gate_mul", "lb2_gather_rows", "lb2_head_mlp", "lb2_guidance_dpm_step", "lb2_farthest_point_sample",
+    "lb2_gate_mul", "lb2_gather_rows", "lb2_head_mlp", "lb2_kernel_map_self", "lb2_guidance_dpm_step", "lb2_farthest_point_sample",
     "lb2_row_order", "lb2_row_order_scratch_bytes", "lb2_nn_match_grid",
     "lb2_nn_table_bytes", "lb2_nn_table_build", "lb2_nn_match_table",
     "lb2_nn_tree_bytes", "lb2_nn_tree_build", "lb2_nn_match_tree",
@@ -106,6 +106,7 @@ class Lib:
         d.lb2_unique_build.argtypes = [vp, vp, vp, vp, vp, i32, i32, Grid, vp, vp, vp, vp]
         d.lb2_voxel_mean.argtypes = [vp, vp, vp, vp, i32, i32, vp, i32, vp, vp]
         d.lb2_kernel_map.argtypes = [vp, vp, Grid, vp, vp, i32, i32, i32, vp, i64, vp, vp]
+        d.lb2_kernel_map_self.argtypes = [vp, vp, Grid, vp, vp, i32, i32, vp, i64, vp, vp]
         d.lb2_row_order.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, vp, i32]
         d.lb2_tile_order.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp, vp]
         d.lb2_row_order_scratch_bytes.restype = C.c_size_t
@@ -208,6 +209,10 @@ class Handle:
     def kernel_map(self, grid_in, out_coords, d_nout, nout_cap, ks, step, nbr, nbr_stride, pair_count=None, row_mask=None):
         self._check(self.dll.lb2_kernel_map(self.hp, self._stream(), self._grid(grid_in), _ptr(out_coords), _ptr(d_nout), int(nout_cap),
                                             int(ks), int(step), _ptr(nbr), int(nbr_stride), _ptr(pair_count), _ptr(row_mask)), "lb2_kernel_map")
+
+    def kernel_map_self(self, grid, coords, d_n, n_cap, step, nbr, nbr_stride, pair_count=None, row_mask=None):
+        self._check(self.dll.lb2_kernel_map_self(self.hp, self._stream(), self._grid(grid), _ptr(coords), _ptr(d_n), int(n_cap), int(step),
+                                                 _ptr(nbr), int(nbr_stride), _ptr(pair_count), _ptr(row_mask)), "lb2_kernel_map_self")
 
     def row_order_scratch_bytes(self, n_cap) -> int:
         return int(self.dll.lb2_row_order_scratch_bytes(int(n_cap)))

@@ -405,6 +405,87 @@ extern "C" int lb2_kernel_map(void* handle, void* stream, lb2_grid grid_in, cons
 }
 
 // ---------------------------------------------------------------------------------------------------
+// 3^3 map of a coordinate set onto itself (stride-1 convolutions: most of the maps of a U-Net pass).  The pair set is symmetric — row j
+// sits at offset k of row o exactly when o sits at offset 26 - k of j — so every thread probes the 13 offsets below the centre only and
+// writes both directions; the centre is the row itself.  Half the hash probes of k_kernel_map<3>, same table bit for bit.
+// The offsets above the centre and the row masks are pre-set (-1 / 0) by the launcher.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_kernel_map_self(const unsigned long long* __restrict__ keys, const int* __restrict__ rows, unsigned mask,
+                                                         const int4* __restrict__ coords, const int* __restrict__ d_n, int n_cap, int step,
+                                                         int* __restrict__ nbr, long long nbr_stride,
+                                                         unsigned long long* __restrict__ pair_count, unsigned* __restrict__ row_mask) {
+    constexpr int HALF = 13;
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = d_n ? min(*d_n, n_cap) : n_cap;
+    unsigned found = 0;
+    if (o < n) {
+        const int4 c = __ldg(coords + o);
+        int res[HALF];
+        unsigned long long key[HALF], got[HALF];
+        unsigned slot[HALF];
+#pragma unroll
+        for (int k = 0; k < HALF; ++k) {                                // first probe of every offset: independent loads
+            const int kx = k % 3, ky = (k / 3) % 3, kz = k / 9;
+            const int x = c.y + (kx - 1) * step, y = c.z + (ky - 1) * step, z = c.w + (kz - 1) * step;
+            const bool ok = lb2_pack_key(c.x, x, y, z, key[k]);
+            slot[k] = ok ? (lb2_hash(key[k]) & mask) : 0u;
+            got[k] = ok ? __ldg(keys + slot[k]) : LB2_KEY_EMPTY;
+            if (!ok) key[k] = ~LB2_KEY_EMPTY;
+        }
+#pragma unroll
+        for (int k = 0; k < HALF; ++k) {
+            if (got[k] == key[k]) res[k] = __ldg(rows + slot[k]);
+            else if (got[k] == LB2_KEY_EMPTY) res[k] = -1;
+            else {                                                      // collision on the first slot: continue the linear probe
+                unsigned sl = (slot[k] + 1) & mask;
+                res[k] = -1;
+                while (true) {
+                    const unsigned long long kk = __ldg(keys + sl);
+                    if (kk == key[k]) { res[k] = __ldg(rows + sl); break; }
+                    if (kk == LB2_KEY_EMPTY) break;
+                    sl = (sl + 1) & mask;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < HALF; ++k) {
+            nbr[(long long)k * nbr_stride + o] = res[k];
+            if (res[k] >= 0) {
+                found |= 1u << k;
+                nbr[(long long)(26 - k) * nbr_stride + res[k]] = o;     // the mirrored pair: nobody else writes this entry
+                if (row_mask) atomicOr(row_mask + res[k], 1u << (26 - k));
+            }
+        }
+        nbr[(long long)HALF * nbr_stride + o] = o;
+        if (row_mask) atomicOr(row_mask + o, found | (1u << HALF));
+    } else if (o < n_cap) {
+#pragma unroll
+        for (int k = 0; k <= HALF; ++k) nbr[(long long)k * nbr_stride + o] = -1;
+    }
+    if (pair_count) {        // algorithmic work counter for the roofline: one atomic per warp
+        int cnt = (o < n) ? 2 * __popc(found) + 1 : 0;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+        if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(pair_count, (unsigned long long)cnt);
+    }
+}
+
+extern "C" int lb2_kernel_map_self(void* handle, void* stream, lb2_grid grid, const int32_t* coords, const int32_t* d_n, int32_t n_cap,
+                                   int32_t step, int32_t* nbr, int64_t nbr_stride, uint64_t* pair_count, uint32_t* row_mask) {
+    Lb2Handle* h = (Lb2Handle*)handle;
+    LB2_REQUIRE(h, h && grid.keys && grid.vals && coords && nbr, "kernel_map_self null");
+    LB2_REQUIRE(h, step > 0 && n_cap > 0 && nbr_stride >= n_cap, "kernel_map_self args");
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(nbr + 14 * nbr_stride, 0xff, (size_t)13 * nbr_stride * sizeof(int32_t), s);
+    if (e == cudaSuccess && row_mask) e = cudaMemsetAsync(row_mask, 0, (size_t)n_cap * sizeof(uint32_t), s);
+    if (e != cudaSuccess) return lb2_fail(h, LB2_ERR_CUDA, "kernel_map_self memset: %s", cudaGetErrorString(e));
+    k_kernel_map_self<<<cdiv(n_cap, 128), 128, 0, s>>>((const unsigned long long*)grid.keys, grid.vals + grid.cap_table, (unsigned)grid.cap_table - 1u,
+                                                       (const int4*)coords, d_n, n_cap, step, nbr, nbr_stride, (unsigned long long*)pair_count, row_mask);
+    LB2_POST_LAUNCH(h, "k_kernel_map_self");
+    return LB2_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // row order: sort of the output rows by their neighbour mask, so that the 128-row tiles of the convolution
 // kernels are (nearly) homogeneous in which kernel offsets are populated and skip the rest.
 //   kvol <= 8 : one counting-sort pass on the 8-bit mask itself.

@@ -139,6 +139,7 @@ class Geometry:
         self.perm_of = {}
         # cost order of the 128-row tiles / 256-row super-tiles of every map (static LPT schedule of the persistent conv kernels)
         self.use_tile_order = os.environ.get("LB2_TILE_ORDER", "1") != "0"
+        self.map_self = os.environ.get("LB2_MAP_SELF", "1") != "0"
         self.tile_order_of = {}
         self.to_scratch = torch.zeros((n_cap + 127) // 128, **i32)
         # per-offset (in,out) pair lists of the 3^3 maps of the sparse levels (gather-GEMM-scatter form)
@@ -174,7 +175,10 @@ class Geometry:
             mask = self.mask_of.get(nbr.data_ptr())
             if mask is None:
                 mask = self.mask_of[nbr.data_ptr()] = torch.zeros(N, dtype=torch.int32, device=nbr.device)
-            h.kernel_map(grid, self.C[l_out], self.d_n[l_out], N, ks, step, nbr, N, self.pairs[slot:slot + 1], mask)
+            if ks == 3 and self.map_self:            # a level onto itself: symmetric pair set, half the hash probes
+                h.kernel_map_self(grid, self.C[l_out], self.d_n[l_out], N, step, nbr, N, self.pairs[slot:slot + 1], mask)
+            else:
+                h.kernel_map(grid, self.C[l_out], self.d_n[l_out], N, ks, step, nbr, N, self.pairs[slot:slot + 1], mask)
             # 3^3 maps of the levels with many neighbours per row: rows of equal mask in Morton order (compact tiles, L2 locality)
             morton = ks == 3 and l_out in self.morton_levels
             h.row_order(mask, self.d_n[l_out], N, ks ** 3, perm, ro_scratch, self.C[l_out] if morton else None, l_out)

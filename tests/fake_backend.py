@@ -136,6 +136,9 @@ class FakeHandle:
                     row_mask[:nout_cap] = 0
                 row_mask[:n] |= torch.from_numpy((hit.astype(np.int64) << k).astype(np.int32))
 
+    def kernel_map_self(self, grid, coords, d_n, n_cap, step, nbr, nbr_stride, pair_count=None, row_mask=None):
+        self.kernel_map(grid, coords, d_n, n_cap, 3, step, nbr, nbr_stride, pair_count, row_mask)
+
     def row_order_scratch_bytes(self, n_cap):
         return 1024
 

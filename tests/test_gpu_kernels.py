@@ -292,6 +292,32 @@ def test_head_mlp_matches_torch(n_out, out_act, npass):
     assert (y[:, m:] == 7.0).all(), "rows beyond the live count must stay untouched"
 
 
+@pytest.mark.parametrize("spread,live", [(0.3, 1.0), (1.5, 0.6)])
+def test_kernel_map_self_equals_the_generic_map(spread, live):
+    """lb2_kernel_map_self (13 probes + mirrored writes) builds the table, row masks and pair count of lb2_kernel_map(ks=3) bit for bit,
+    also when fewer rows are live than the capacity"""
+    h = H()
+    pts, coords = random_field(40_000, spread, 11)
+    N = coords.shape[0]
+    from lidiff_b200.engine import Geometry
+    g = Geometry(h, N)
+    g.build(coords.to(DEV).contiguous(), N)
+    for lvl in (0, 2, 4):
+        M = g.sizes()[lvl]
+        C, d_n = g.C[lvl], g.d_n[lvl]
+        if live < 1.0:                                  # a grid over the first rows only: fewer live rows than the capacity
+            d_in = torch.tensor([max(1, int(M * live))], dtype=torch.int32, device=DEV)
+            C, d_n = torch.zeros_like(g.C[lvl]), torch.zeros(1, dtype=torch.int32, device=DEV)
+            h.unique_build(None, g.C[lvl], d_in, N, 1 << lvl, g.grid[lvl], C, torch.zeros_like(g.inv[lvl]), d_n, g.scratch)
+        a, b = torch.full((27, N), 5, dtype=torch.int32, device=DEV), torch.full((27, N), 6, dtype=torch.int32, device=DEV)
+        ma, mb = torch.full((N,), 9, dtype=torch.int32, device=DEV), torch.full((N,), 8, dtype=torch.int32, device=DEV)
+        pa, pb = torch.zeros(1, dtype=torch.int64, device=DEV), torch.zeros(1, dtype=torch.int64, device=DEV)
+        h.kernel_map(g.grid[lvl], C, d_n, N, 3, 1 << lvl, a, N, pa, ma)
+        h.kernel_map_self(g.grid[lvl], C, d_n, N, 1 << lvl, b, N, pb, mb)
+        torch.cuda.synchronize()
+        assert torch.equal(a, b) and torch.equal(ma, mb) and int(pa) == int(pb) and int(pa) >= int(d_n)
+
+
 def test_tile_order_sorts_tiles_by_the_offsets_they_run():
     """lb2_tile_order: order128 / order256 are permutations of the live tiles of the row order, by descending popcount of the OR of
     the tile's row masks; entries beyond the live tiles are -1"""
